@@ -1,0 +1,130 @@
+/*
+ * wiski_b200.h — C ABI of the B200-native WISKI online-update hot path (libwiski_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  The reference (wjmaddox/online_gp) is
+ * pure Python and issues every operation below as a chain of PyTorch/GPyTorch library calls; each entry point
+ * cites the reference interface it replaces (paths relative to the reference repo; "App. A" = GPyTorch semantics
+ * summarised in SURVEY.md Appendix A, source not vendored by the reference).
+ *
+ * Conventions
+ *   - every function returns 0 on success; non-zero: 1 invalid argument, 2 CUDA error, 3 unsupported shape.
+ *     wiski_last_error() gives the message for the calling thread.  Functions never allocate or free caller memory.
+ *   - pointers are DEVICE pointers unless the name starts with h_ (host).  Matrices are row-major, contiguous.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises unless stated.
+ *   - _f32 / _f64 variants compute in float / double ("dtype" in bench.py).  Indices are int64.
+ *   - panels: L, B, KL are m x r (m = prod g_i inducing points, r = root rank); grid axis 0 is the slowest.
+ */
+#ifndef WISKI_B200_H
+#define WISKI_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WISKI_MAX_DIMS 8
+
+const char* wiski_last_error(void);
+int wiski_abi_version(void);
+
+/* ---- k1: cubic-convolution interpolation stencils.
+ * Replaces GPyTorch Interpolation.interpolate (App. A.1) reached from
+ * online_gp/models/batched_fixed_noise_online_gp.py:143,205,261 and online_gp/mlls/streaming_partial_mll.py:20.
+ * x [q,d] -> idx [q,4^d] (flat C-order index, dim 0 slowest), val [q,4^d].
+ * h_lo[i]=grid_i[0], h_delta[i]=clamp_min(grid_i[1]-grid_i[0],1e-10) (computed by the caller in the grid's dtype),
+ * h_first4/h_last4 [d*4] = first/last four grid points per dim (boundary branch), h_gmin/h_gmax = grid extrema.
+ * oob_flag (device int, may be NULL) is OR-ed with 1 if any x lies outside [gmin-1e-7, gmax+1e-7]: the host wrapper
+ * turns that into GPyTorch's "out of bounds for the specified grid" RuntimeError. */
+int wiski_interp_fwd_f32(const float* x, int64_t q, int d, const int64_t* h_g, const float* h_lo,
+                         const float* h_delta, const float* h_first4, const float* h_last4, const float* h_gmin,
+                         const float* h_gmax, int64_t* idx, float* val, int* oob_flag, void* stream);
+int wiski_interp_fwd_f64(const double* x, int64_t q, int d, const int64_t* h_g, const double* h_lo,
+                         const double* h_delta, const double* h_first4, const double* h_last4, const double* h_gmin,
+                         const double* h_gmax, int64_t* idx, double* val, int* oob_flag, void* stream);
+/* d val / d x contracted with grad_val [q,4^d] -> grad_x [q,d] (autograd of A.1 through `lower_pt_rel_dists`;
+ * needed by the stem update, online_gp/models/online_ski_regression.py:148-162). */
+int wiski_interp_bwd_f32(const float* x, int64_t q, int d, const int64_t* h_g, const float* h_lo,
+                         const float* h_delta, const float* h_first4, const float* h_last4, const float* grad_val,
+                         float* grad_x, void* stream);
+int wiski_interp_bwd_f64(const double* x, int64_t q, int d, const int64_t* h_g, const double* h_lo,
+                         const double* h_delta, const double* h_first4, const double* h_last4, const double* grad_val,
+                         double* grad_x, void* stream);
+
+/* ---- k13 / k5: W @ src  (GPyTorch left_interp, App. A.1; batched_fixed_noise_online_gp.py:206-210,236-240).
+ * out[n,:] = sum_k val[n,k] * src[idx[n,k],:], src [m,c], out [q,c].  With src = inverse-root panel B and
+ * val = w / sqrt(D) this is the projection p^T = v^T B of updated_root_lazy_tensor.py:79. */
+int wiski_gather_f32(const int64_t* idx, const float* val, int64_t q, int64_t s, const float* src, int64_t m,
+                     int64_t c, float* out, void* stream);
+int wiski_gather_f64(const int64_t* idx, const double* val, int64_t q, int64_t s, const double* src, int64_t m,
+                     int64_t c, double* out, void* stream);
+/* ---- k2 / k3: dst += W^T @ src without densifying W^T (replaces _sparse_left_interp_t(...).to_dense() matmuls,
+ * batched_fixed_noise_online_gp.py:22-28,42-47,158-160).  src [q,c], dst [m,c] accumulated in place (atomics). */
+int wiski_scatter_add_f32(const int64_t* idx, const float* val, int64_t q, int64_t s, const float* src, int64_t m,
+                          int64_t c, float* dst, void* stream);
+int wiski_scatter_add_f64(const int64_t* idx, const double* val, int64_t q, int64_t s, const double* src, int64_t m,
+                          int64_t c, double* dst, void* stream);
+
+/* ---- k9: Kronecker-Toeplitz MVM  Y = (T(col_0) x ... x T(col_{d-1})) X,  X,Y [m,c]
+ * (replaces KroneckerProductLazyTensor._matmul / ToeplitzLazyTensor._matmul, App. A.4, reached from
+ * batched_fixed_noise_online_gp.py:348,366 and streaming_partial_mll.py:29).  cols [d,gmax] device (row i holds
+ * col_i in its first g_i entries; any 1/sigma^2 scaling is folded into a column by the caller),
+ * work = scratch [m,c]; X, Y, work must not alias. */
+int wiski_kron_toeplitz_mm_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, const float* X, int64_t c,
+                               float* Y, float* work, void* stream);
+int wiski_kron_toeplitz_mm_f64(const double* cols, int d, const int64_t* h_g, int64_t gmax, const double* X,
+                               int64_t c, double* Y, double* work, void* stream);
+/* ---- k15: gradient of sum(Z * (K X)) w.r.t. the Toeplitz columns (replaces the autograd of k9 /
+ * _quad_form_derivative; online_gp/models/online_ski_regression.py:141).
+ * grad_cols [d,gmax] is overwritten.  work = scratch of wiski_kron_toeplitz_bwd_work_elems(...) elements
+ * ((d+1) panels [m,c] + a double accumulator), elem_size = 4 or 8. */
+int64_t wiski_kron_toeplitz_bwd_work_elems(int d, int64_t m, int64_t c, int64_t gmax, int elem_size);
+int wiski_kron_toeplitz_bwd_cols_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, const float* Z,
+                                     const float* X, int64_t c, float* grad_cols, float* work, void* stream);
+int wiski_kron_toeplitz_bwd_cols_f64(const double* cols, int d, const int64_t* h_g, int64_t gmax, const double* Z,
+                                     const double* X, int64_t c, double* grad_cols, double* work, void* stream);
+
+/* ---- k7: panel right-multiply  Out = P @ M,  P,Out [m,r], M [r,r2], Out [m,r2]  (Out must not alias P)
+ * (replaces current_root.matmul(inner_root) / current_inv_root^T.matmul(inner_inv_root),
+ * updated_root_lazy_tensor.py:97-100,115-117, and Kuu_Lmat @ qmat_solve, batched_fixed_noise_online_gp.py:376). */
+int wiski_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, void* stream);
+int wiski_panel_rmul_f64(const double* P, int64_t m, int64_t r, const double* M, int64_t r2, double* Out,
+                         void* stream);
+/* In-place, row-local form of the same root update for q << r:  P <- P + (P @ U) @ Vt,  U [r,q], Vt [q,r]
+ * ((I + p p^T)^(+-1/2) = I + P f(S) P^T; identical L L^T / B B^T as :97-117, without the r x r GEMM). q <= 32. */
+int wiski_panel_lowrank_update_f32(float* P, int64_t m, int64_t r, const float* U, const float* Vt, int64_t q,
+                                   void* stream);
+int wiski_panel_lowrank_update_f64(double* P, int64_t m, int64_t r, const double* U, const double* Vt, int64_t q,
+                                   void* stream);
+
+/* ---- k10: Gram  G = A^T @ Bm,  A [m,r], Bm [m,r2], G [r,r2]  (Q - I = L^T (K L), and L^T (K b);
+ * batched_fixed_noise_online_gp.py:352-355,360-361).  work = scratch of wiski_gram_work_elems(m,r,r2) elements. */
+int64_t wiski_gram_work_elems(int64_t m, int64_t r, int64_t r2);
+int wiski_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
+                   void* stream);
+int wiski_gram_f64(const double* A, const double* Bm, int64_t m, int64_t r, int64_t r2, double* G, double* work,
+                   void* stream);
+
+/* ---- k11 (CG path): fused Q-MVM  w = v + L^T (KL v),  v,w [r,c]  — one pass over both panels
+ * (the matmul closure GPyTorch's linear_cg calls when r > max_cholesky_size, App. A.5).
+ * work = scratch of wiski_qmv_work_elems(m,r,c) elements. */
+int64_t wiski_qmv_work_elems(int64_t m, int64_t r, int64_t c);
+int wiski_q_matvec_f32(const float* L, const float* KL, int64_t m, int64_t r, const float* v, int64_t c, float* w,
+                       float* work, void* stream);
+int wiski_q_matvec_f64(const double* L, const double* KL, int64_t m, int64_t r, const double* v, int64_t c,
+                       double* w, double* work, void* stream);
+/* Conjugate gradients on Q x = rhs (rhs [r,c], x [r,c]) with the fused MVM above; GPyTorch linear_cg stopping
+ * rule (App. A.5): columns normalised, stop when mean residual norm < tol and it >= min(10, max_iter-1).
+ * Synchronises the stream every `check_every` iterations to read the residual.  h_iters / h_resid are host outputs.
+ * work = scratch of wiski_cg_work_elems(m,r,c) elements. */
+int64_t wiski_cg_work_elems(int64_t m, int64_t r, int64_t c);
+int wiski_cg_solve_f32(const float* L, const float* KL, int64_t m, int64_t r, const float* rhs, int64_t c,
+                       float tol, int max_iter, int check_every, float* x, int* h_iters, float* h_resid,
+                       float* work, void* stream);
+int wiski_cg_solve_f64(const double* L, const double* KL, int64_t m, int64_t r, const double* rhs, int64_t c,
+                       double tol, int max_iter, int check_every, double* x, int* h_iters, double* h_resid,
+                       double* work, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

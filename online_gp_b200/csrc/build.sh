@@ -1,0 +1,16 @@
+#!/bin/bash
+# Builds libwiski_b200.so for sm_100a in-tree (the .so travels to the GPU box with the snapshot).
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -Xptxas -v"
+OBJS=""
+for f in interp kron panel gemm_tc; do
+  if [ ! -f $f.o ] || [ $f.cu -nt $f.o ] || [ common.cuh -nt $f.o ] || [ ../../include/wiski_b200.h -nt $f.o ]; then
+    echo "nvcc $f.cu"
+    $NVCC $FLAGS -c $f.cu -o $f.o 2> $f.ptxas.log || { cat $f.ptxas.log; exit 1; }
+  fi
+  OBJS="$OBJS $f.o"
+done
+$NVCC -shared -o libwiski_b200.so $OBJS -lcudart -lcuda
+echo "built $(pwd)/libwiski_b200.so"

@@ -1,0 +1,61 @@
+// Shared helpers for libwiski_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/wiski_b200.h"
+
+namespace wiski {
+
+void set_error(const char* fmt, ...);
+
+#define WISKI_CHECK_ARG(cond, ...)                \
+    do {                                          \
+        if (!(cond)) {                            \
+            ::wiski::set_error(__VA_ARGS__);      \
+            return 1;                             \
+        }                                         \
+    } while (0)
+
+#define WISKI_CHECK_LAUNCH(name)                                                          \
+    do {                                                                                  \
+        cudaError_t _e = cudaGetLastError();                                              \
+        if (_e != cudaSuccess) {                                                          \
+            ::wiski::set_error("%s: CUDA error: %s", name, cudaGetErrorString(_e));       \
+            return 2;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+#define WISKI_CHECK_CUDA(expr, name)                                                      \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            ::wiski::set_error("%s: CUDA error: %s", name, cudaGetErrorString(_e));       \
+            return 2;                                                                     \
+        }                                                                                 \
+    } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// round-to-nearest, never contracted into FMA: used where the reference's op order must be reproduced exactly
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+}  // namespace wiski

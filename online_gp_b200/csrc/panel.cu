@@ -1,0 +1,565 @@
+// k5/k7/k10/k11: dense m x r panel kernels — right-multiply, row-local low-rank root update, Gram, fused Q-MVM
+// and the conjugate-gradient driver (sm_100a).  SIMT (FFMA/DFMA) versions for every dtype and shape; the fp32
+// tensor-core (tcgen05) versions of the two real contractions live in gemm_tc.cu and are dispatched from here.
+//
+// Reference operations replaced (online_gp/lazy/updated_root_lazy_tensor.py:79,97-100,115-117;
+// online_gp/models/batched_fixed_noise_online_gp.py:346-361,375-376; GPyTorch linear_cg).
+#include "common.cuh"
+
+namespace wiski {
+
+// gemm_tc.cu (fp32, tcgen05): return 0 if handled, 3 if the shape is not supported by the tensor-core path.
+int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
+                cudaStream_t st);
+int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st);
+int64_t tc_gram_work_elems(int64_t m, int64_t r, int64_t r2);
+
+// ------------------------------------------------------------------ Out[M x N] = P[M x K] @ Mm[K x N]
+template <typename T>
+__global__ void __launch_bounds__(256) rmul_tile_kernel(const T* __restrict__ P, const T* __restrict__ Mm,
+                                                        T* __restrict__ Out, int64_t M, int64_t K, int64_t N) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ T As[BK][BM + 1];
+    __shared__ T Bs[BK][BN];
+    int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    int64_t row0 = (int64_t)blockIdx.x * BM, col0 = (int64_t)blockIdx.y * BN;
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    for (int64_t k0 = 0; k0 < K; k0 += BK) {
+        // A tile: 64 rows x 16 k  (4 elements per thread), stored k-major
+        for (int e = threadIdx.x; e < BM * BK; e += 256) {
+            int rr = e / BK, kk = e % BK;
+            int64_t gr = row0 + rr, gk = k0 + kk;
+            As[kk][rr] = (gr < M && gk < K) ? P[gr * K + gk] : T(0);
+        }
+        for (int e = threadIdx.x; e < BK * BN; e += 256) {
+            int kk = e / BN, cc = e % BN;
+            int64_t gk = k0 + kk, gc = col0 + cc;
+            Bs[kk][cc] = (gk < K && gc < N) ? Mm[gk * N + gc] : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            T a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t gr = row0 + ty * 4 + i;
+        if (gr >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t gc = col0 + tx + 16 * j;
+            if (gc < N) Out[gr * N + gc] = acc[i][j];
+        }
+    }
+}
+
+// N small (<= 8): one warp per row, lanes strided over K.
+template <typename T, int NP>
+__global__ void rmul_skinny_kernel(const T* __restrict__ P, const T* __restrict__ Mm, T* __restrict__ Out, int64_t M,
+                                   int64_t K, int N) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < M; i += nwarps) {
+        T acc[NP];
+#pragma unroll
+        for (int t = 0; t < NP; ++t) acc[t] = T(0);
+        for (int64_t j = lane; j < K; j += 32) {
+            T x = P[i * K + j];
+#pragma unroll
+            for (int t = 0; t < NP; ++t)
+                if (t < N) acc[t] += x * Mm[j * N + t];
+        }
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+            T v = warp_sum(acc[t]);
+            if (lane == 0 && t < N) Out[i * N + t] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ P[i,:] += (P[i,:] @ U) @ Vt   (row-local)
+template <typename T, int QP>
+__global__ void lowrank_update_kernel(T* __restrict__ P, int64_t m, int64_t r, const T* __restrict__ U,
+                                      const T* __restrict__ Vt, int q) {
+    int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t i = warp; i < m; i += nwarps) {
+        T* row = P + i * r;
+        T dot[QP];
+#pragma unroll
+        for (int t = 0; t < QP; ++t) dot[t] = T(0);
+        for (int64_t j = lane; j < r; j += 32) {
+            T x = row[j];
+#pragma unroll
+            for (int t = 0; t < QP; ++t)
+                if (t < q) dot[t] += x * U[j * q + t];
+        }
+#pragma unroll
+        for (int t = 0; t < QP; ++t) dot[t] = warp_sum(dot[t]);
+        for (int64_t j = lane; j < r; j += 32) {
+            T x = row[j];
+#pragma unroll
+            for (int t = 0; t < QP; ++t)
+                if (t < q) x += dot[t] * Vt[(int64_t)t * r + j];
+            row[j] = x;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ Gram: G[r x r2] = A^T Bm, split over rows
+template <typename T>
+__global__ void __launch_bounds__(256) gram_tile_kernel(const T* __restrict__ A, const T* __restrict__ Bm, int64_t m,
+                                                        int64_t r, int64_t r2, int64_t rows_per_split,
+                                                        T* __restrict__ part) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ T As[BK][BM];
+    __shared__ T Bs[BK][BN];
+    int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+    int64_t i0 = (int64_t)blockIdx.x * BM, j0 = (int64_t)blockIdx.y * BN;
+    int64_t k_begin = (int64_t)blockIdx.z * rows_per_split;
+    int64_t k_end = k_begin + rows_per_split;
+    if (k_end > m) k_end = m;
+    T acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = T(0);
+    for (int64_t k0 = k_begin; k0 < k_end; k0 += BK) {
+        for (int e = threadIdx.x; e < BK * BM; e += 256) {
+            int kk = e / BM, cc = e % BM;
+            int64_t gk = k0 + kk, gc = i0 + cc;
+            As[kk][cc] = (gk < k_end && gc < r) ? A[gk * r + gc] : T(0);
+        }
+        for (int e = threadIdx.x; e < BK * BN; e += 256) {
+            int kk = e / BN, cc = e % BN;
+            int64_t gk = k0 + kk, gc = j0 + cc;
+            Bs[kk][cc] = (gk < k_end && gc < r2) ? Bm[gk * r2 + gc] : T(0);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            T a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+        }
+        __syncthreads();
+    }
+    T* out = part + (int64_t)blockIdx.z * r * r2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        int64_t gi = i0 + ty + 16 * i;
+        if (gi >= r) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int64_t gj = j0 + tx + 16 * j;
+            if (gj < r2) out[gi * r2 + gj] = acc[i][j];
+        }
+    }
+}
+
+// r2 small (<= 4): block accumulates A[i, j] * Bm[i, t] over its row slab; thread j strided over r.
+template <typename T, int NP>
+__global__ void gram_skinny_kernel(const T* __restrict__ A, const T* __restrict__ Bm, int64_t m, int64_t r, int r2,
+                                   int64_t rows_per_block, T* __restrict__ part) {
+    int64_t k_begin = (int64_t)blockIdx.x * rows_per_block;
+    int64_t k_end = k_begin + rows_per_block;
+    if (k_end > m) k_end = m;
+    for (int64_t j = threadIdx.x; j < r; j += blockDim.x) {
+        T acc[NP];
+#pragma unroll
+        for (int t = 0; t < NP; ++t) acc[t] = T(0);
+        for (int64_t i = k_begin; i < k_end; ++i) {
+            T a = A[i * r + j];
+#pragma unroll
+            for (int t = 0; t < NP; ++t)
+                if (t < r2) acc[t] += a * Bm[i * r2 + t];
+        }
+#pragma unroll
+        for (int t = 0; t < NP; ++t)
+            if (t < r2) part[((int64_t)blockIdx.x * r + j) * r2 + t] = acc[t];
+    }
+}
+
+// out[e] = (init ? init[e] : 0) + sum_s part[s][e]   (summed in double)
+template <typename T>
+__global__ void reduce_parts_kernel(const T* __restrict__ part, int64_t nparts, int64_t n, const T* __restrict__ init,
+                                    T* __restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double s = init ? (double)init[e] : 0.0;
+    for (int64_t p = 0; p < nparts; ++p) s += (double)part[p * n + e];
+    out[e] = (T)s;
+}
+
+// ------------------------------------------------------------------ fused Q-MVM partials
+// Each warp walks rows i: t[cc] = KL[i,:] . v[:,cc];  acc[j][cc] += L[i,j] * t[cc].  One pass over both panels.
+template <typename T, int RJ, int C>
+__global__ void __launch_bounds__(256) qmv_kernel(const T* __restrict__ L, const T* __restrict__ KL, int64_t m,
+                                                  int64_t r, const T* __restrict__ v, int c, T* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* red = reinterpret_cast<T*>(smem_raw);  // [8 warps][r*C]
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T vr[RJ][C], acc[RJ][C];
+#pragma unroll
+    for (int jj = 0; jj < RJ; ++jj) {
+        int64_t j = lane + 32 * jj;
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            vr[jj][cc] = (j < r && cc < c) ? v[j * c + cc] : T(0);
+            acc[jj][cc] = T(0);
+        }
+    }
+    int64_t gw = (int64_t)blockIdx.x * 8 + warp, nw = (int64_t)gridDim.x * 8;
+    for (int64_t i = gw; i < m; i += nw) {
+        const T* kr = KL + i * r;
+        const T* lr = L + i * r;
+        T kv[RJ], lv[RJ];
+#pragma unroll
+        for (int jj = 0; jj < RJ; ++jj) {
+            int64_t j = lane + 32 * jj;
+            kv[jj] = (j < r) ? kr[j] : T(0);
+            lv[jj] = (j < r) ? lr[j] : T(0);
+        }
+        T t[C];
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc) {
+            T s = T(0);
+#pragma unroll
+            for (int jj = 0; jj < RJ; ++jj) s += kv[jj] * vr[jj][cc];
+            t[cc] = warp_sum(s);
+        }
+#pragma unroll
+        for (int jj = 0; jj < RJ; ++jj)
+#pragma unroll
+            for (int cc = 0; cc < C; ++cc) acc[jj][cc] += lv[jj] * t[cc];
+    }
+    int64_t rc = r * c;
+#pragma unroll
+    for (int jj = 0; jj < RJ; ++jj) {
+        int64_t j = lane + 32 * jj;
+#pragma unroll
+        for (int cc = 0; cc < C; ++cc)
+            if (j < r && cc < c) red[warp * rc + j * c + cc] = acc[jj][cc];
+    }
+    __syncthreads();
+    for (int64_t e = threadIdx.x; e < rc; e += blockDim.x) {
+        T s = T(0);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w * rc + e];
+        part[(int64_t)blockIdx.x * rc + e] = s;
+    }
+}
+
+// ------------------------------------------------------------------ CG vector kernels (single block; r*c is tiny)
+template <typename T>
+struct CgState {   // all device pointers into the work buffer
+    T* x; T* rs; T* p; T* Ap; T* rz; T* rhs_norm; T* resid;   // rz, rhs_norm [c]; resid [1] mean residual norm
+};
+
+template <typename T>
+__device__ T block_sum(T v, T* sh) {
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    T s = T(0);
+    int nw = (blockDim.x + 31) >> 5;
+    for (int w = 0; w < nw; ++w) s += sh[w];
+    return s;
+}
+
+template <typename T>
+__global__ void cg_init_kernel(const T* __restrict__ rhs, int64_t r, int c, CgState<T> s) {
+    __shared__ T sh[32];
+    for (int cc = 0; cc < c; ++cc) {
+        T a = T(0);
+        for (int64_t j = threadIdx.x; j < r; j += blockDim.x) a += rhs[j * c + cc] * rhs[j * c + cc];
+        T nrm = sqrt(block_sum(a, sh));
+        if (nrm < T(1e-10)) nrm = T(1);
+        T rz = T(0);
+        for (int64_t j = threadIdx.x; j < r; j += blockDim.x) {
+            T v = rhs[j * c + cc] / nrm;
+            s.x[j * c + cc] = T(0);
+            s.rs[j * c + cc] = v;
+            s.p[j * c + cc] = v;
+            rz += v * v;
+        }
+        rz = block_sum(rz, sh);
+        if (threadIdx.x == 0) { s.rz[cc] = rz; s.rhs_norm[cc] = nrm; }
+    }
+    if (threadIdx.x == 0) s.resid[0] = T(1);
+}
+
+template <typename T>
+__global__ void cg_update_kernel(int64_t r, int c, T tol, CgState<T> s) {
+    __shared__ T sh[32];
+    T mean = T(0);
+    for (int cc = 0; cc < c; ++cc) {
+        T a = T(0);
+        for (int64_t j = threadIdx.x; j < r; j += blockDim.x) a += s.p[j * c + cc] * s.Ap[j * c + cc];
+        T pAp = block_sum(a, sh);
+        T rz = s.rz[cc];
+        T alpha = (fabs(pAp) > T(1e-30)) ? rz / pAp : T(0);
+        T rz_new = T(0);
+        for (int64_t j = threadIdx.x; j < r; j += blockDim.x) {
+            s.x[j * c + cc] += alpha * s.p[j * c + cc];
+            T rv = s.rs[j * c + cc] - alpha * s.Ap[j * c + cc];
+            s.rs[j * c + cc] = rv;
+            rz_new += rv * rv;
+        }
+        rz_new = block_sum(rz_new, sh);
+        T beta = (rz > T(1e-30)) ? rz_new / rz : T(0);
+        for (int64_t j = threadIdx.x; j < r; j += blockDim.x)
+            s.p[j * c + cc] = s.rs[j * c + cc] + beta * s.p[j * c + cc];
+        __syncthreads();
+        if (threadIdx.x == 0) s.rz[cc] = rz_new;
+        mean += sqrt(rz_new);
+    }
+    if (threadIdx.x == 0) s.resid[0] = mean / T(c);
+}
+
+template <typename T>
+__global__ void cg_finish_kernel(int64_t r, int c, CgState<T> s, T* __restrict__ xout) {
+    for (int64_t e = threadIdx.x; e < r * c; e += blockDim.x) xout[e] = s.x[e] * s.rhs_norm[e % c];
+}
+
+// ------------------------------------------------------------------ host dispatch
+template <typename T>
+static int panel_rmul(const T* P, int64_t m, int64_t r, const T* M, int64_t r2, T* Out, void* stream) {
+    WISKI_CHECK_ARG(m >= 0 && r >= 1 && r2 >= 1, "panel_rmul: bad sizes");
+    WISKI_CHECK_ARG((const void*)P != (const void*)Out, "panel_rmul: Out must not alias P");
+    if (m == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    if (r2 <= 8) {
+        int64_t blocks = ceil_div(m, 8);
+        if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+        if (r2 == 1) rmul_skinny_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(P, M, Out, m, r, (int)r2);
+        else if (r2 <= 2) rmul_skinny_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(P, M, Out, m, r, (int)r2);
+        else if (r2 <= 4) rmul_skinny_kernel<T, 4><<<(unsigned)blocks, 256, 0, st>>>(P, M, Out, m, r, (int)r2);
+        else rmul_skinny_kernel<T, 8><<<(unsigned)blocks, 256, 0, st>>>(P, M, Out, m, r, (int)r2);
+    } else {
+        dim3 grid((unsigned)ceil_div(m, 64), (unsigned)ceil_div(r2, 64));
+        rmul_tile_kernel<T><<<grid, 256, 0, st>>>(P, M, Out, m, r, r2);
+    }
+    WISKI_CHECK_LAUNCH("panel_rmul");
+    return 0;
+}
+
+template <typename T>
+static int lowrank_update(T* P, int64_t m, int64_t r, const T* U, const T* Vt, int64_t q, void* stream) {
+    WISKI_CHECK_ARG(m >= 0 && r >= 1 && q >= 1 && q <= 32, "panel_lowrank_update: need 1 <= q <= 32 (q=%lld)",
+                    (long long)q);
+    if (m == 0) return 0;
+    cudaStream_t st = as_stream(stream);
+    int64_t blocks = ceil_div(m, 8);
+    if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
+#define LR(QP) lowrank_update_kernel<T, QP><<<(unsigned)blocks, 256, 0, st>>>(P, m, r, U, Vt, (int)q)
+    if (q == 1) LR(1);
+    else if (q <= 2) LR(2);
+    else if (q <= 4) LR(4);
+    else if (q <= 8) LR(8);
+    else if (q <= 16) LR(16);
+    else LR(32);
+#undef LR
+    WISKI_CHECK_LAUNCH("panel_lowrank_update");
+    return 0;
+}
+
+static inline int64_t gram_splits(int64_t m, int64_t r, int64_t r2) {
+    int64_t tiles = ceil_div(r, 64) * ceil_div(r2, 64);
+    int64_t ks = ceil_div((int64_t)kNumSMs * 4, tiles);
+    int64_t max_ks = ceil_div(m, 256);
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+    return ks;
+}
+static inline int64_t gram_skinny_blocks(int64_t m) {
+    int64_t nb = ceil_div(m, 64);
+    if (nb > (int64_t)kNumSMs * 4) nb = (int64_t)kNumSMs * 4;
+    if (nb < 1) nb = 1;
+    return nb;
+}
+
+template <typename T>
+static int gram(const T* A, const T* Bm, int64_t m, int64_t r, int64_t r2, T* G, T* work, void* stream) {
+    WISKI_CHECK_ARG(m >= 1 && r >= 1 && r2 >= 1 && work != nullptr, "gram: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    int64_t n = r * r2;
+    if (r2 <= 4) {
+        int64_t nb = gram_skinny_blocks(m);
+        int64_t rpb = ceil_div(m, nb);
+        nb = ceil_div(m, rpb);
+        if (r2 == 1) gram_skinny_kernel<T, 1><<<(unsigned)nb, 256, 0, st>>>(A, Bm, m, r, (int)r2, rpb, work);
+        else if (r2 == 2) gram_skinny_kernel<T, 2><<<(unsigned)nb, 256, 0, st>>>(A, Bm, m, r, (int)r2, rpb, work);
+        else gram_skinny_kernel<T, 4><<<(unsigned)nb, 256, 0, st>>>(A, Bm, m, r, (int)r2, rpb, work);
+        reduce_parts_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nb, n, (const T*)nullptr, G);
+    } else {
+        int64_t ks = gram_splits(m, r, r2);
+        int64_t rps = ceil_div(ceil_div(m, ks), 16) * 16;
+        ks = ceil_div(m, rps);
+        dim3 grid((unsigned)ceil_div(r, 64), (unsigned)ceil_div(r2, 64), (unsigned)ks);
+        gram_tile_kernel<T><<<grid, 256, 0, st>>>(A, Bm, m, r, r2, rps, work);
+        reduce_parts_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, ks, n, (const T*)nullptr, G);
+    }
+    WISKI_CHECK_LAUNCH("gram");
+    return 0;
+}
+
+static inline int64_t qmv_blocks(int64_t m) {
+    int64_t nb = ceil_div(m, 8);
+    if (nb > (int64_t)kNumSMs * 2) nb = (int64_t)kNumSMs * 2;
+    if (nb < 1) nb = 1;
+    return nb;
+}
+
+template <typename T>
+static int q_matvec(const T* L, const T* KL, int64_t m, int64_t r, const T* v, int64_t c, T* w, T* work,
+                    void* stream) {
+    WISKI_CHECK_ARG(m >= 1 && r >= 1 && c >= 1 && work != nullptr, "q_matvec: bad arguments");
+    WISKI_CHECK_ARG(r <= 1024, "q_matvec: fused kernel supports r <= 1024 (r=%lld)", (long long)r);
+    WISKI_CHECK_ARG(c <= 4, "q_matvec: c <= 4 per call (c=%lld); split the right-hand sides", (long long)c);
+    cudaStream_t st = as_stream(stream);
+    int64_t nb = qmv_blocks(m);
+    size_t smem = (size_t)8 * r * c * sizeof(T);
+    WISKI_CHECK_ARG(smem <= 200 * 1024, "q_matvec: r*c too large for the fused kernel (r=%lld, c=%lld)", (long long)r,
+                    (long long)c);
+    int rj = (int)ceil_div(r, 32);
+#define QMV(RJ, C)                                                                                          \
+    do {                                                                                                    \
+        auto kfn = qmv_kernel<T, RJ, C>;                                                                    \
+        if (smem > 48 * 1024)                                                                               \
+            WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
+                             "q_matvec(attr)");                                                             \
+        kfn<<<(unsigned)nb, 256, smem, st>>>(L, KL, m, r, v, (int)c, work);                                 \
+    } while (0)
+#define QMV_C(RJ)                      \
+    do {                               \
+        if (c == 1) QMV(RJ, 1);        \
+        else if (c == 2) QMV(RJ, 2);   \
+        else QMV(RJ, 4);               \
+    } while (0)
+    if (rj <= 4) QMV_C(4);
+    else if (rj <= 8) QMV_C(8);
+    else if (rj <= 16) QMV_C(16);
+    else QMV_C(32);
+#undef QMV_C
+#undef QMV
+    int64_t n = r * c;
+    reduce_parts_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nb, n, v, w);
+    WISKI_CHECK_LAUNCH("q_matvec");
+    return 0;
+}
+
+template <typename T>
+static int cg_solve(const T* L, const T* KL, int64_t m, int64_t r, const T* rhs, int64_t c, T tol, int max_iter,
+                    int check_every, T* x, int* h_iters, T* h_resid, T* work, void* stream) {
+    WISKI_CHECK_ARG(m >= 1 && r >= 1 && c >= 1 && c <= 4 && work != nullptr && max_iter >= 1, "cg_solve: bad arguments");
+    if (check_every < 1) check_every = 1;
+    cudaStream_t st = as_stream(stream);
+    int64_t n = r * c;
+    CgState<T> s;
+    s.x = work; s.rs = s.x + n; s.p = s.rs + n; s.Ap = s.p + n; s.rz = s.Ap + n; s.rhs_norm = s.rz + c;
+    s.resid = s.rhs_norm + c;
+    T* qwork = s.resid + 8;
+    cg_init_kernel<T><<<1, 256, 0, st>>>(rhs, r, (int)c, s);
+    int min_iter = max_iter - 1 < 10 ? max_iter - 1 : 10;
+    int it = 0;
+    T resid = T(1);
+    while (it < max_iter) {
+        if (int rc = q_matvec<T>(L, KL, m, r, s.p, c, s.Ap, qwork, stream)) return rc;
+        cg_update_kernel<T><<<1, 256, 0, st>>>(r, (int)c, tol, s);
+        ++it;
+        if (it % check_every == 0 || it == max_iter) {
+            WISKI_CHECK_CUDA(cudaMemcpyAsync(&resid, s.resid, sizeof(T), cudaMemcpyDeviceToHost, st), "cg_solve");
+            WISKI_CHECK_CUDA(cudaStreamSynchronize(st), "cg_solve");
+            if (it >= min_iter && resid < tol) break;
+        }
+    }
+    cg_finish_kernel<T><<<1, 256, 0, st>>>(r, (int)c, s, x);
+    WISKI_CHECK_LAUNCH("cg_solve");
+    if (h_iters) *h_iters = it;
+    if (h_resid) *h_resid = resid;
+    return 0;
+}
+
+}  // namespace wiski
+
+extern "C" {
+int wiski_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, void* stream) {
+    int rc = wiski::tc_panel_rmul_f32(P, m, r, M, r2, Out, wiski::as_stream(stream));
+    if (rc != 3) return rc;
+    return wiski::panel_rmul<float>(P, m, r, M, r2, Out, stream);
+}
+int wiski_panel_rmul_f64(const double* P, int64_t m, int64_t r, const double* M, int64_t r2, double* Out,
+                         void* stream) {
+    return wiski::panel_rmul<double>(P, m, r, M, r2, Out, stream);
+}
+int wiski_panel_lowrank_update_f32(float* P, int64_t m, int64_t r, const float* U, const float* Vt, int64_t q,
+                                   void* stream) {
+    return wiski::lowrank_update<float>(P, m, r, U, Vt, q, stream);
+}
+int wiski_panel_lowrank_update_f64(double* P, int64_t m, int64_t r, const double* U, const double* Vt, int64_t q,
+                                   void* stream) {
+    return wiski::lowrank_update<double>(P, m, r, U, Vt, q, stream);
+}
+int64_t wiski_gram_work_elems(int64_t m, int64_t r, int64_t r2) {
+    int64_t simt = (r2 <= 4) ? wiski::gram_skinny_blocks(m) * r * r2 : wiski::gram_splits(m, r, r2) * r * r2;
+    int64_t tc = wiski::tc_gram_work_elems(m, r, r2);
+    return simt > tc ? simt : tc;
+}
+int wiski_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
+                   void* stream) {
+    int rc = wiski::tc_gram_f32(A, Bm, m, r, r2, G, work, wiski::as_stream(stream));
+    if (rc != 3) return rc;
+    return wiski::gram<float>(A, Bm, m, r, r2, G, work, stream);
+}
+int wiski_gram_f64(const double* A, const double* Bm, int64_t m, int64_t r, int64_t r2, double* G, double* work,
+                   void* stream) {
+    return wiski::gram<double>(A, Bm, m, r, r2, G, work, stream);
+}
+int64_t wiski_qmv_work_elems(int64_t m, int64_t r, int64_t c) { return wiski::qmv_blocks(m) * r * c; }
+int wiski_q_matvec_f32(const float* L, const float* KL, int64_t m, int64_t r, const float* v, int64_t c, float* w,
+                       float* work, void* stream) {
+    return wiski::q_matvec<float>(L, KL, m, r, v, c, w, work, stream);
+}
+int wiski_q_matvec_f64(const double* L, const double* KL, int64_t m, int64_t r, const double* v, int64_t c,
+                       double* w, double* work, void* stream) {
+    return wiski::q_matvec<double>(L, KL, m, r, v, c, w, work, stream);
+}
+int64_t wiski_cg_work_elems(int64_t m, int64_t r, int64_t c) {
+    return 4 * r * c + 2 * c + 8 + wiski::qmv_blocks(m) * r * c;
+}
+int wiski_cg_solve_f32(const float* L, const float* KL, int64_t m, int64_t r, const float* rhs, int64_t c,
+                       float tol, int max_iter, int check_every, float* x, int* h_iters, float* h_resid,
+                       float* work, void* stream) {
+    return wiski::cg_solve<float>(L, KL, m, r, rhs, c, tol, max_iter, check_every, x, h_iters, h_resid, work, stream);
+}
+int wiski_cg_solve_f64(const double* L, const double* KL, int64_t m, int64_t r, const double* rhs, int64_t c,
+                       double tol, int max_iter, int check_every, double* x, int* h_iters, double* h_resid,
+                       double* work, void* stream) {
+    return wiski::cg_solve<double>(L, KL, m, r, rhs, c, tol, max_iter, check_every, x, h_iters, h_resid, work, stream);
+}
+}

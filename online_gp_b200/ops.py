@@ -1,0 +1,363 @@
+"""Torch-facing wrappers of the C ABI (device pointers + current stream) and their autograd Functions.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); the arithmetic of every op in this file
+runs in libwiski_b200.so.  All tensors must live on a CUDA device — there is no CPU path.
+"""
+import ctypes
+from ctypes import c_double, c_float, c_int, c_int64
+
+import torch
+
+from . import _lib
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("online_gp_b200 ops require CUDA tensors (got a %s tensor); there is no CPU fallback"
+                               % t.device.type)
+
+
+def _sfx(dtype):
+    if dtype == torch.float32:
+        return "f32"
+    if dtype == torch.float64:
+        return "f64"
+    raise TypeError(f"online_gp_b200: unsupported dtype {dtype} (float32 / float64 only)")
+
+
+def _real(dtype):
+    return c_float if dtype == torch.float32 else c_double
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _call(name, dtype, *args):
+    fn = getattr(_lib.load(), f"{name}_{_sfx(dtype)}")
+    _lib.check(fn(*args), name)
+
+
+class GridSpec:
+    """Host-side description of the inducing grid, in the form the interpolation / Kronecker kernels consume.
+
+    Built from the per-dimension grid buffers exactly as GPyTorch's ``Interpolation.interpolate`` reads them
+    (SURVEY.md App. A.1): ``lo = grid[0]``, ``delta = (grid[1] - grid[0]).clamp_min(1e-10)`` evaluated in the
+    *grid's* dtype (float32 by default, A.2) and only then widened to the working dtype.
+    """
+
+    def __init__(self, grid):
+        self.d = len(grid)
+        if not 1 <= self.d <= 8:
+            raise ValueError("grid dimension must be in [1, 8]")
+        self.sizes = [int(g.numel()) for g in grid]
+        self.m = 1
+        for g in self.sizes:
+            self.m *= g
+        self.s = 4 ** self.d
+        self.gmax = max(self.sizes)
+        gc = [g.detach().cpu() for g in grid]
+        self.lo = [float(g[0]) for g in gc]
+        self.delta = [float((g[1] - g[0]).clamp_min(1e-10)) for g in gc]
+        self.first4 = [float(v) for g in gc for v in g[:4]]
+        self.last4 = [float(v) for g in gc for v in g[-4:]]
+        self.gmin = [float(g.min()) for g in gc]
+        self.gmax_v = [float(g.max()) for g in gc]
+        self.h_sizes = (c_int64 * self.d)(*self.sizes)
+        self._host = {}
+
+    def host(self, dtype):
+        if dtype not in self._host:
+            R = _real(dtype)
+            self._host[dtype] = dict(
+                lo=(R * self.d)(*self.lo), delta=(R * self.d)(*self.delta), first4=(R * (4 * self.d))(*self.first4),
+                last4=(R * (4 * self.d))(*self.last4), gmin=(R * self.d)(*self.gmin), gmax=(R * self.d)(*self.gmax_v))
+        return self._host[dtype]
+
+
+# ---------------------------------------------------------------------------------------------- interpolation
+def _interp_fwd(x, spec, check_bounds):
+    _require_cuda(x)
+    x = x.contiguous()
+    q = x.shape[0]
+    idx = torch.empty(q, spec.s, dtype=torch.int64, device=x.device)
+    val = torch.empty(q, spec.s, dtype=x.dtype, device=x.device)
+    flag = torch.zeros(1, dtype=torch.int32, device=x.device) if check_bounds else None
+    h = spec.host(x.dtype)
+    _call("wiski_interp_fwd", x.dtype, _ptr(x), q, spec.d, spec.h_sizes, h["lo"], h["delta"], h["first4"], h["last4"],
+          h["gmin"], h["gmax"], _ptr(idx), _ptr(val), _ptr(flag), _stream())
+    if check_bounds and q > 0 and int(flag.item()) != 0:
+        xmin, xmax = x.min().item(), x.max().item()
+        raise RuntimeError(
+            "Received data that was out of bounds for the specified grid. Grid bounds were (%.3f, %.3f), but min = "
+            "%.3f, max = %.3f" % (min(spec.gmin), max(spec.gmax_v), xmin, xmax))
+    return idx, val
+
+
+class _InterpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, spec, check_bounds):
+        idx, val = _interp_fwd(x, spec, check_bounds)
+        ctx.save_for_backward(x)
+        ctx.spec = spec
+        ctx.mark_non_differentiable(idx)
+        return idx, val
+
+    @staticmethod
+    def backward(ctx, _gidx, gval):
+        (x,) = ctx.saved_tensors
+        spec = ctx.spec
+        x = x.contiguous()
+        gval = gval.contiguous()
+        gx = torch.empty_like(x)
+        h = spec.host(x.dtype)
+        _call("wiski_interp_bwd", x.dtype, _ptr(x), x.shape[0], spec.d, spec.h_sizes, h["lo"], h["delta"],
+              h["first4"], h["last4"], _ptr(gval), _ptr(gx), _stream())
+        return gx, None, None
+
+
+def interpolate(x, spec, check_bounds=True):
+    """x [q,d] -> (idx int64 [q,4^d], val [q,4^d]); differentiable w.r.t. x through val."""
+    if x.dim() != 2 or x.shape[1] != spec.d:
+        raise ValueError(f"interpolate: expected x of shape [q,{spec.d}], got {tuple(x.shape)}")
+    if x.requires_grad and torch.is_grad_enabled():
+        return _InterpFn.apply(x, spec, check_bounds)
+    return _interp_fwd(x.detach(), spec, check_bounds)
+
+
+def _gather(idx, val, src):
+    _require_cuda(idx, val, src)
+    q, s = idx.shape
+    m, c = src.shape
+    out = torch.empty(q, c, dtype=src.dtype, device=src.device)
+    _call("wiski_gather", src.dtype, _ptr(idx), _ptr(val), q, s, _ptr(src), m, c, _ptr(out), _stream())
+    return out
+
+
+def _scatter_add(idx, val, src, dst):
+    _require_cuda(idx, val, src, dst)
+    q, s = idx.shape
+    m, c = dst.shape
+    _call("wiski_scatter_add", dst.dtype, _ptr(idx), _ptr(val), q, s, _ptr(src), m, c, _ptr(dst), _stream())
+    return dst
+
+
+class _LeftInterpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, val, src):
+        ctx.save_for_backward(idx, val, src)
+        return _gather(idx, val.contiguous(), src.contiguous())
+
+    @staticmethod
+    def backward(ctx, gout):
+        idx, val, src = ctx.saved_tensors
+        gout = gout.contiguous()
+        gval = gsrc = None
+        if ctx.needs_input_grad[1]:
+            gval = (src[idx] * gout.unsqueeze(1)).sum(-1)
+        if ctx.needs_input_grad[2]:
+            gsrc = torch.zeros_like(src)
+            _scatter_add(idx, val.contiguous(), gout, gsrc)
+        return None, gval, gsrc
+
+
+def left_interp(idx, val, src):
+    """W @ src: out[n,:] = sum_k val[n,k] src[idx[n,k],:]  (src [m,c] -> [q,c])."""
+    if src.dim() != 2:
+        raise ValueError("left_interp: src must be [m,c]")
+    if torch.is_grad_enabled() and (val.requires_grad or src.requires_grad):
+        return _LeftInterpFn.apply(idx, val, src)
+    return _gather(idx, val.detach().contiguous(), src.detach().contiguous())
+
+
+def left_t_interp(idx, val, src, m):
+    """W^T @ src: [m,c] from src [q,c] (no autograd; used for cache accumulation under no_grad)."""
+    dst = torch.zeros(m, src.shape[-1], dtype=src.dtype, device=src.device)
+    return _scatter_add(idx, val.detach().contiguous(), src.detach().contiguous(), dst)
+
+
+def scatter_add_(dst, idx, val, src):
+    return _scatter_add(idx, val.detach().contiguous(), src.detach().contiguous(), dst)
+
+
+# ---------------------------------------------------------------------------------------------- Kronecker-Toeplitz
+def _kron_mm(cols, sizes, X):
+    _require_cuda(cols, X)
+    d, gmax = cols.shape
+    m, c = X.shape
+    X = X.contiguous()
+    Y = torch.empty_like(X)
+    work = torch.empty_like(X) if d > 1 else None
+    h_g = (c_int64 * d)(*sizes)
+    _call("wiski_kron_toeplitz_mm", X.dtype, _ptr(cols), d, h_g, gmax, _ptr(X), c, _ptr(Y), _ptr(work), _stream())
+    return Y
+
+
+def _kron_bwd_cols(cols, sizes, Z, X):
+    d, gmax = cols.shape
+    m, c = X.shape
+    esz = X.element_size()
+    n = _lib.load().wiski_kron_toeplitz_bwd_work_elems(d, m, c, gmax, esz)
+    work = torch.empty(n, dtype=X.dtype, device=X.device)
+    g = torch.empty_like(cols)
+    h_g = (c_int64 * d)(*sizes)
+    _call("wiski_kron_toeplitz_bwd_cols", X.dtype, _ptr(cols), d, h_g, gmax, _ptr(Z.contiguous()), _ptr(X.contiguous()),
+          c, _ptr(g), _ptr(work), _stream())
+    return g
+
+
+class _KronFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cols, X, sizes):
+        cols = cols.contiguous()
+        ctx.save_for_backward(cols, X)
+        ctx.sizes = sizes
+        return _kron_mm(cols, sizes, X)
+
+    @staticmethod
+    def backward(ctx, gY):
+        cols, X = ctx.saved_tensors
+        gY = gY.contiguous()
+        gcols = gX = None
+        if ctx.needs_input_grad[0]:
+            gcols = _kron_bwd_cols(cols, ctx.sizes, gY, X)
+        if ctx.needs_input_grad[1]:
+            gX = _kron_mm(cols, ctx.sizes, gY)
+        return gcols, gX, None
+
+
+def kron_toeplitz_matmul(cols, sizes, X):
+    """(T(cols[0]) x ... x T(cols[d-1])) @ X for X [m,c]; cols [d,gmax] (row i valid in its first sizes[i] entries).
+    Differentiable w.r.t. cols and X."""
+    if X.dim() != 2:
+        raise ValueError("kron_toeplitz_matmul: X must be [m,c]")
+    if cols.dtype != X.dtype:
+        raise TypeError("kron_toeplitz_matmul: cols and X must share a dtype")
+    if torch.is_grad_enabled() and (cols.requires_grad or X.requires_grad):
+        return _KronFn.apply(cols, X, tuple(sizes))
+    return _kron_mm(cols.detach().contiguous(), tuple(sizes), X.detach())
+
+
+# ---------------------------------------------------------------------------------------------- panels
+def _rmul(P, M):
+    _require_cuda(P, M)
+    P, M = P.contiguous(), M.contiguous()
+    m, r = P.shape
+    r2 = M.shape[1]
+    out = torch.empty(m, r2, dtype=P.dtype, device=P.device)
+    _call("wiski_panel_rmul", P.dtype, _ptr(P), m, r, _ptr(M), r2, _ptr(out), _stream())
+    return out
+
+
+def _gram(A, B):
+    _require_cuda(A, B)
+    A, B = A.contiguous(), B.contiguous()
+    m, r = A.shape
+    r2 = B.shape[1]
+    n = _lib.load().wiski_gram_work_elems(m, r, r2)
+    work = torch.empty(max(int(n), 1), dtype=A.dtype, device=A.device)
+    G = torch.empty(r, r2, dtype=A.dtype, device=A.device)
+    _call("wiski_gram", A.dtype, _ptr(A), _ptr(B), m, r, r2, _ptr(G), _ptr(work), _stream())
+    return G
+
+
+class _RmulFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, P, M):
+        ctx.save_for_backward(P, M)
+        return _rmul(P, M)
+
+    @staticmethod
+    def backward(ctx, gO):
+        P, M = ctx.saved_tensors
+        gP = gM = None
+        if ctx.needs_input_grad[0]:
+            gP = _rmul(gO, M.t().contiguous())
+        if ctx.needs_input_grad[1]:
+            gM = _gram(P, gO)
+        return gP, gM
+
+
+class _GramFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, A, B):
+        ctx.save_for_backward(A, B)
+        return _gram(A, B)
+
+    @staticmethod
+    def backward(ctx, gG):
+        A, B = ctx.saved_tensors
+        gA = gB = None
+        if ctx.needs_input_grad[0]:
+            gA = _rmul(B, gG.t().contiguous())
+        if ctx.needs_input_grad[1]:
+            gB = _rmul(A, gG.contiguous())
+        return gA, gB
+
+
+def panel_rmul(P, M):
+    """P [m,r] @ M [r,r2] -> [m,r2]."""
+    if torch.is_grad_enabled() and (P.requires_grad or M.requires_grad):
+        return _RmulFn.apply(P, M)
+    return _rmul(P.detach(), M.detach())
+
+
+def gram(A, B):
+    """A^T @ B for panels A [m,r], B [m,r2] -> [r,r2]."""
+    if torch.is_grad_enabled() and (A.requires_grad or B.requires_grad):
+        return _GramFn.apply(A, B)
+    return _gram(A.detach(), B.detach())
+
+
+def panel_lowrank_update_(P, U, Vt):
+    """In place: P <- P + (P @ U) @ Vt with U [r,q], Vt [q,r], q <= 32."""
+    _require_cuda(P, U, Vt)
+    if not P.is_contiguous():
+        raise ValueError("panel_lowrank_update_: P must be contiguous")
+    m, r = P.shape
+    q = U.shape[1]
+    _call("wiski_panel_lowrank_update", P.dtype, _ptr(P), m, r, _ptr(U.contiguous()), _ptr(Vt.contiguous()), q, _stream())
+    return P
+
+
+def q_matvec(L, KL, v):
+    """w = v + L^T (KL v) for v [r,c] (c <= 4 per launch; wider right-hand sides are split)."""
+    _require_cuda(L, KL, v)
+    m, r = L.shape
+    v = v.contiguous()
+    outs = []
+    lib = _lib.load()
+    for c0 in range(0, v.shape[1], 4):
+        vc = v[:, c0:c0 + 4].contiguous()
+        c = vc.shape[1]
+        work = torch.empty(int(lib.wiski_qmv_work_elems(m, r, c)), dtype=L.dtype, device=L.device)
+        w = torch.empty_like(vc)
+        _call("wiski_q_matvec", L.dtype, _ptr(L), _ptr(KL), m, r, _ptr(vc), c, _ptr(w), _ptr(work), _stream())
+        outs.append(w)
+    return outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)
+
+
+def cg_solve(L, KL, rhs, tol=1e-2, max_iter=1000, check_every=4):
+    """Solve (I + L^T KL) x = rhs by CG with the fused panel MVM. Returns (x, iters, residual)."""
+    _require_cuda(L, KL, rhs)
+    m, r = L.shape
+    rhs = rhs.contiguous()
+    lib = _lib.load()
+    outs, iters, resid = [], 0, 0.0
+    R = _real(L.dtype)
+    for c0 in range(0, rhs.shape[1], 4):
+        rc = rhs[:, c0:c0 + 4].contiguous()
+        c = rc.shape[1]
+        work = torch.empty(int(lib.wiski_cg_work_elems(m, r, c)), dtype=L.dtype, device=L.device)
+        x = torch.empty_like(rc)
+        h_it, h_res = c_int(0), R(0)
+        _call("wiski_cg_solve", L.dtype, _ptr(L), _ptr(KL), m, r, _ptr(rc), c, R(tol), int(max_iter), int(check_every),
+              _ptr(x), ctypes.byref(h_it), ctypes.byref(h_res), _ptr(work), _stream())
+        outs.append(x)
+        iters, resid = max(iters, h_it.value), max(resid, h_res.value)
+    return (outs[0] if len(outs) == 1 else torch.cat(outs, dim=1)), iters, resid

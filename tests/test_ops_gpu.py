@@ -1,0 +1,213 @@
+"""GPU parity of every C-ABI kernel against the CPU oracle (run with -m gpu on the B200 box).
+
+Tolerances: interpolation indices bit-exact; fp64 kernels rtol 1e-10 (pure reorderings of fp64 sums);
+fp32 kernels rtol 1e-4 against the fp64 oracle evaluated on the same fp32 inputs.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle.gridkernel import Hypers, kron_toeplitz_matmul as o_kron, kuu_columns
+from oracle.interp import create_grid, interpolate as o_interp, left_interp as o_left_interp
+
+DEV = "cuda:0"
+DT = [torch.float64, torch.float32]
+
+
+def _tol(dt):
+    return dict(rtol=1e-10, atol=1e-11) if dt == torch.float64 else dict(rtol=2e-4, atol=2e-5)
+
+
+def _ops():
+    from online_gp_b200 import ops
+    return ops
+
+
+def _pad_cols(cols, dt):
+    gmax = max(c.numel() for c in cols)
+    out = torch.zeros(len(cols), gmax, dtype=dt)
+    for i, c in enumerate(cols):
+        out[i, : c.numel()] = c.to(dt)
+    return out
+
+
+@pytest.mark.parametrize("name", ["d1", "d2", "d3", "d4"])
+@pytest.mark.parametrize("tag,dt", [("f32", torch.float32), ("f64", torch.float64)])
+def test_interp_golden(golden_dir, name, tag, dt):
+    ops = _ops()
+    z = np.load(os.path.join(golden_dir, "g0_interp.npz"))
+    grid = create_grid(z[f"{name}_sizes"].tolist(), [tuple(b) for b in z[f"{name}_bounds"].tolist()])
+    spec = ops.GridSpec(grid)
+    x = torch.from_numpy(z[f"{name}_{tag}_x"]).to(DEV)
+    idx, val = ops.interpolate(x, spec)
+    assert idx.dtype == torch.int64 and val.dtype == dt
+    assert np.array_equal(idx.cpu().numpy(), z[f"{name}_{tag}_idx"]), "interpolation indices must be bit-exact"
+    ref = z[f"{name}_{tag}_val"]
+    # values: same op order with explicit rn intrinsics -> expected bit-exact; allow 2 ulp
+    eps = np.finfo(ref.dtype).eps
+    assert np.allclose(val.cpu().numpy(), ref, rtol=4 * eps, atol=4 * eps)
+
+
+def test_interp_out_of_bounds():
+    ops = _ops()
+    spec = ops.GridSpec(create_grid([10, 10], [(0.0, 1.0)] * 2))
+    with pytest.raises(RuntimeError, match="out of bounds"):
+        ops.interpolate(torch.tensor([[0.5, 1.7]], device=DEV), spec)
+    idx, val = ops.interpolate(torch.zeros(0, 2, device=DEV), spec)     # empty input
+    assert idx.shape == (0, 16) and val.shape == (0, 16)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_interp_backward(dt):
+    ops = _ops()
+    grid = create_grid([9, 11], [(-1.0, 1.0)] * 2)
+    spec = ops.GridSpec(grid)
+    x = (torch.rand(7, 2, dtype=torch.float64) * 1.8 - 0.9).to(dt)
+    gv = torch.randn(7, 16, dtype=dt)
+    xo = x.clone().requires_grad_(True)
+    _, vo = o_interp(grid, xo)
+    (vo * gv).sum().backward()
+    xg = x.to(DEV).requires_grad_(True)
+    _, vg = ops.interpolate(xg, spec)
+    (vg * gv.to(DEV)).sum().backward()
+    tol = dict(rtol=1e-9, atol=1e-9) if dt == torch.float64 else dict(rtol=1e-3, atol=1e-3)
+    assert torch.allclose(xg.grad.cpu(), xo.grad, **tol)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("c", [1, 3, 40, 200])
+def test_gather_scatter(dt, c):
+    ops = _ops()
+    grid = create_grid([7, 8, 6], [(-1.0, 1.0)] * 3)
+    spec = ops.GridSpec(grid)
+    x = (torch.rand(11, 3, dtype=torch.float64) * 2 - 1).to(dt)
+    idx, val = o_interp(grid, x)
+    src = torch.randn(spec.m, c, dtype=dt)
+    ref = o_left_interp(idx, val.double(), src.double())
+    out = ops.left_interp(idx.to(DEV), val.to(DEV), src.to(DEV))
+    assert torch.allclose(out.cpu().double(), ref, **_tol(dt))
+    rhs = torch.randn(11, c, dtype=dt)
+    ref_t = torch.zeros(spec.m, c, dtype=torch.float64)
+    ref_t.index_add_(0, idx.reshape(-1), (val.double().unsqueeze(-1) * rhs.double().unsqueeze(1)).reshape(-1, c))
+    out_t = ops.left_t_interp(idx.to(DEV), val.to(DEV), rhs.to(DEV), spec.m)
+    assert torch.allclose(out_t.cpu().double(), ref_t, **_tol(dt))
+
+
+KRON_CASES = [([128], 3), ([12, 9], 5), ([32, 32], 33), ([10, 10, 10], 7), ([8, 8, 8, 8], 16), ([5, 40, 6], 4),
+              ([300], 2), ([64, 16], 1), ([16, 16, 16, 16], 1)]
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("sizes,c", KRON_CASES)
+def test_kron_toeplitz_mm(dt, sizes, c):
+    ops = _ops()
+    d = len(sizes)
+    grid = create_grid(sizes, [(-1.1, 1.1)] * d)
+    hyp = Hypers(d, kind="rbf")
+    with torch.no_grad():
+        hyp.raw_lengthscale.copy_(torch.linspace(-1.0, 0.5, d))
+    cols = [cc.detach() for cc in kuu_columns(grid, hyp)]
+    m = int(np.prod(sizes))
+    X = torch.randn(m, c, dtype=dt)
+    ref = o_kron([cc.double() for cc in cols], X.double())
+    out = ops.kron_toeplitz_matmul(_pad_cols(cols, dt).to(DEV), sizes, X.to(DEV))
+    assert torch.allclose(out.cpu().double(), ref, **_tol(dt))
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("sizes,c", [([20], 3), ([12, 9], 5), ([6, 7, 5], 4), ([8, 8, 8, 8], 6), ([40, 6], 3),
+                                      ([32, 32], 17)])
+def test_kron_toeplitz_backward(dt, sizes, c):
+    ops = _ops()
+    d = len(sizes)
+    m = int(np.prod(sizes))
+    gen = torch.Generator().manual_seed(3)
+    cols = [torch.rand(g, generator=gen, dtype=torch.float64) for g in sizes]
+    X = torch.randn(m, c, generator=gen, dtype=torch.float64)
+    Z = torch.randn(m, c, generator=gen, dtype=torch.float64)
+    cols_o = [cc.clone().requires_grad_(True) for cc in cols]
+    Xo = X.clone().requires_grad_(True)
+    (o_kron(cols_o, Xo) * Z).sum().backward()
+    cg = _pad_cols(cols, dt).to(DEV).requires_grad_(True)
+    Xg = X.to(dt).to(DEV).requires_grad_(True)
+    (ops.kron_toeplitz_matmul(cg, sizes, Xg) * Z.to(dt).to(DEV)).sum().backward()
+    tol = dict(rtol=1e-9, atol=1e-9) if dt == torch.float64 else dict(rtol=1e-3, atol=1e-2)
+    for i, g in enumerate(sizes):
+        assert torch.allclose(cg.grad[i, :g].cpu().double(), cols_o[i].grad, **tol), f"grad col {i}"
+        assert float(cg.grad[i, g:].abs().sum()) == 0.0
+    assert torch.allclose(Xg.grad.cpu().double(), Xo.grad, **(_tol(dt) if dt == torch.float64 else dict(rtol=1e-3, atol=1e-3)))
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("m,r,r2", [(1000, 25, 25), (4096, 128, 128), (777, 100, 1), (5000, 432, 432), (300, 64, 5),
+                                    (2048, 512, 512)])
+def test_panel_rmul_and_gram(dt, m, r, r2):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(0)
+    P = torch.randn(m, r, generator=gen, dtype=dt)
+    M = torch.randn(r, r2, generator=gen, dtype=dt)
+    Bp = torch.randn(m, r2, generator=gen, dtype=dt)
+    out = ops.panel_rmul(P.to(DEV), M.to(DEV))
+    ref = P.double() @ M.double()
+    tol = dict(rtol=1e-10, atol=1e-9) if dt == torch.float64 else dict(rtol=1e-3, atol=2e-3)
+    assert torch.allclose(out.cpu().double(), ref, **tol)
+    G = ops.gram(P.to(DEV), Bp.to(DEV))
+    refg = P.double().t() @ Bp.double()
+    tolg = dict(rtol=1e-10, atol=1e-8) if dt == torch.float64 else dict(rtol=1e-3, atol=2e-2)
+    assert torch.allclose(G.cpu().double(), refg, **tolg)
+
+
+@pytest.mark.parametrize("dt", DT)
+def test_gram_rmul_autograd(dt):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(1)
+    A = torch.randn(300, 20, generator=gen, dtype=torch.float64)
+    B = torch.randn(300, 12, generator=gen, dtype=torch.float64)
+    M = torch.randn(12, 7, generator=gen, dtype=torch.float64)
+    Ao, Bo, Mo = (t.clone().requires_grad_(True) for t in (A, B, M))
+    ((Ao.t() @ (Bo @ Mo)) ** 2).sum().backward()
+    Ag, Bg, Mg = (t.to(dt).to(DEV).requires_grad_(True) for t in (A, B, M))
+    (ops.gram(Ag, ops.panel_rmul(Bg, Mg)) ** 2).sum().backward()
+    tol = dict(rtol=1e-9, atol=1e-7) if dt == torch.float64 else dict(rtol=2e-3, atol=1.0)
+    for g, o in ((Ag, Ao), (Bg, Bo), (Mg, Mo)):
+        assert torch.allclose(g.grad.cpu().double(), o.grad, **tol)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("m,r,q", [(1000, 30, 1), (513, 432, 3), (2000, 512, 8), (100, 100, 32)])
+def test_lowrank_update(dt, m, r, q):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(2)
+    P = torch.randn(m, r, generator=gen, dtype=dt)
+    U = torch.randn(r, q, generator=gen, dtype=dt) / r ** 0.5
+    Vt = torch.randn(q, r, generator=gen, dtype=dt)
+    ref = P.double() + (P.double() @ U.double()) @ Vt.double()
+    Pg = P.to(DEV).clone()
+    ops.panel_lowrank_update_(Pg, U.to(DEV), Vt.to(DEV))
+    assert torch.allclose(Pg.cpu().double(), ref, **(_tol(dt) if dt == torch.float64 else dict(rtol=1e-4, atol=1e-4)))
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("m,r,c", [(3000, 40, 1), (5000, 432, 1), (4096, 512, 2), (1500, 100, 3), (2000, 700, 1)])
+def test_q_matvec_and_cg(dt, m, r, c):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(4)
+    L = torch.randn(m, r, generator=gen, dtype=dt) / m ** 0.5
+    KL = (L + 0.1 * torch.randn(m, r, generator=gen, dtype=dt) / m ** 0.5)
+    v = torch.randn(r, c, generator=gen, dtype=dt)
+    Q = torch.eye(r, dtype=torch.float64) + L.double().t() @ KL.double()
+    w = ops.q_matvec(L.to(DEV), KL.to(DEV), v.to(DEV))
+    tol = dict(rtol=1e-10, atol=1e-10) if dt == torch.float64 else dict(rtol=1e-4, atol=1e-4)
+    assert torch.allclose(w.cpu().double(), Q @ v.double(), **tol)
+    # CG on the symmetric part: use KL = K L with K = 2 I so that Q is SPD
+    KL2 = 2.0 * L
+    Q2 = torch.eye(r, dtype=torch.float64) + 2.0 * L.double().t() @ L.double()
+    x, iters, resid = ops.cg_solve(L.to(DEV), KL2.to(DEV), v.to(DEV), tol=1e-8 if dt == torch.float64 else 1e-5,
+                                   max_iter=200, check_every=4)
+    ref = torch.linalg.solve(Q2, v.double())
+    assert iters <= 200
+    assert torch.allclose(x.cpu().double(), ref, **(dict(rtol=1e-6, atol=1e-7) if dt == torch.float64 else dict(rtol=1e-3, atol=1e-4)))
