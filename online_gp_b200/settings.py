@@ -1,0 +1,140 @@
+"""Feature flags and value contexts steering the hot path.
+
+Mirrors ``online_gp/settings.py:3-7`` (``check_decomposition``, ``detach_interp_coeff``) and the subset of
+``gpytorch.settings`` the reference path reads (SURVEY.md §5 "Config / flags", App. A.5 for the defaults):
+``max_cholesky_size`` (800), ``max_root_decomposition_size`` (100), ``cg_tolerance`` (1.0), ``eval_cg_tolerance``
+(0.01), ``max_cg_iterations`` (1000), ``cholesky_jitter``, ``skip_logdet_forward``, ``skip_posterior_variances``,
+``fast_pred_var``, ``fast_pred_samples``, ``use_toeplitz``, ``detach_test_caches``.  Same usage:
+``with max_cholesky_size(2048), cg_tolerance(1e-2): ...`` / ``flag.on()`` / ``value_ctx.value()``.
+"""
+import torch
+
+
+class _feature_flag:
+    _state = False
+
+    @classmethod
+    def on(cls):
+        return cls._state
+
+    @classmethod
+    def off(cls):
+        return not cls._state
+
+    @classmethod
+    def _set_state(cls, state):
+        cls._state = state
+
+    def __init__(self, state=True):
+        self.prev = self.__class__.on()
+        self.state = state
+
+    def __enter__(self):
+        self.__class__._set_state(self.state)
+
+    def __exit__(self, *args):
+        self.__class__._set_state(self.prev)
+        return False
+
+
+class _value_context:
+    _global_value = None
+
+    @classmethod
+    def value(cls):
+        return cls._global_value
+
+    @classmethod
+    def _set_value(cls, value):
+        cls._global_value = value
+
+    def __init__(self, value):
+        self._orig_value = self.__class__.value()
+        self._instance_value = value
+
+    def __enter__(self):
+        self.__class__._set_value(self._instance_value)
+
+    def __exit__(self, *args):
+        self.__class__._set_value(self._orig_value)
+        return False
+
+
+# --- online_gp/settings.py
+class check_decomposition(_feature_flag):
+    _state = False
+
+
+class detach_interp_coeff(_feature_flag):
+    _state = False
+
+
+# --- gpytorch.settings subset
+class max_cholesky_size(_value_context):
+    _global_value = 800
+
+
+class max_root_decomposition_size(_value_context):
+    _global_value = 100
+
+
+class cg_tolerance(_value_context):
+    _global_value = 1.0
+
+
+class eval_cg_tolerance(_value_context):
+    _global_value = 0.01
+
+
+class max_cg_iterations(_value_context):
+    _global_value = 1000
+
+
+class cholesky_jitter(_value_context):
+    _global_value = None     # None -> dtype default (1e-6 fp32, 1e-8 fp64)
+
+    @classmethod
+    def value(cls, dtype=None):
+        if cls._global_value is not None:
+            return cls._global_value
+        return 1e-6 if dtype == torch.float32 else 1e-8
+
+
+class skip_logdet_forward(_feature_flag):
+    _state = False
+
+
+class skip_posterior_variances(_feature_flag):
+    _state = False
+
+
+class fast_pred_var(_feature_flag):
+    _state = False
+
+
+class fast_pred_samples(_feature_flag):
+    _state = False
+
+
+class use_toeplitz(_feature_flag):
+    _state = True
+
+
+class detach_test_caches(_feature_flag):
+    _state = True
+
+
+# --- additions of this implementation
+class root_update_mode(_value_context):
+    """How ``UpdatedRootLazyTensor.collect_vector`` applies the rank-q update (updated_root_lazy_tensor.py:69-119).
+
+    "sym": row-local  P <- P + (P U) V^T  with  (I + p p^T)^(+-1/2) = I + U f(S) U^T  (two panel passes, no GEMM);
+    "svd": the reference's literal form — full SVD of p, two m x r x r panel GEMMs.  Both give the same
+    L L^T and B B^T; they differ by an orthogonal right factor, which no downstream quantity sees.
+    """
+    _global_value = "sym"
+
+
+class check_interp_bounds(_feature_flag):
+    """Raise GPyTorch's out-of-bounds RuntimeError eagerly (costs one device->host flag read per call)."""
+    _state = True
