@@ -76,7 +76,7 @@ class Kernel(nn.Module, _PriorMixin):
         self._priors = {}
         if self.has_lengthscale:
             nd = 1 if ard_num_dims is None else ard_num_dims
-            self.raw_lengthscale = nn.Parameter(torch.zeros(*self.batch_shape, 1, nd))
+            self.raw_lengthscale = nn.Parameter(torch.zeros(tuple(self.batch_shape) + (1, nd)))
             self.raw_lengthscale_constraint = lengthscale_constraint if lengthscale_constraint is not None else Positive()
             if lengthscale_prior is not None:
                 self._priors["lengthscale_prior"] = (lengthscale_prior, lambda m: m.lengthscale)
@@ -140,7 +140,7 @@ class ScaleKernel(Kernel):
         bs = base_kernel.batch_shape if batch_shape is None else batch_shape
         super().__init__(batch_shape=bs, **kwargs)
         self.base_kernel = base_kernel
-        self.raw_outputscale = nn.Parameter(torch.zeros(*self.batch_shape))
+        self.raw_outputscale = nn.Parameter(torch.zeros(tuple(self.batch_shape)))
         self.raw_outputscale_constraint = outputscale_constraint if outputscale_constraint is not None else Positive()
         if outputscale_prior is not None:
             self._priors["outputscale_prior"] = (outputscale_prior, lambda m: m.outputscale)

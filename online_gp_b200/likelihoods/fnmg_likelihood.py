@@ -10,7 +10,7 @@ from ..kernels import GreaterThan, _PriorMixin
 class HomoskedasticNoise(nn.Module):
     def __init__(self, noise_prior=None, noise_constraint=None, batch_shape=torch.Size()):
         super().__init__()
-        self.raw_noise = nn.Parameter(torch.zeros(*batch_shape, 1))
+        self.raw_noise = nn.Parameter(torch.zeros(tuple(batch_shape) + (1,)))
         self.raw_noise_constraint = noise_constraint if noise_constraint is not None else GreaterThan(1e-4)
         self._priors = {}
         if noise_prior is not None:

@@ -1,0 +1,325 @@
+"""Parity cases for the WISKI model core / MLL / regression wrapper against the CPU oracle and the golden vectors.
+Shared by ``test_model_gpu.py`` (real CUDA kernels, ``-m gpu``) and ``test_model_host_cpu.py`` (host logic with the
+kernels mocked by the oracle, CPU).  ``DEV`` is set by the importing module.
+
+Bar (BASELINE.json north_star): posterior mean / variance and MLL within 1e-4 relative in fp64, 1e-2 in fp32.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.gridkernel import Hypers
+from oracle.interp import create_grid
+from oracle.wiski_matfree import WiskiMatFree
+from oracle.wiski_ref import WiskiRef
+
+DEV = "cuda:0"
+
+def _dev():
+    return DEV
+
+
+@pytest.fixture(autouse=True)
+def fp64_default():
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float64)
+    yield
+    torch.set_default_dtype(prev)
+
+
+def _mods():
+    import online_gp_b200.settings as S
+    from online_gp_b200.kernels import GridInterpolationKernel, MaternKernel, RBFKernel, ScaleKernel
+    from online_gp_b200.mlls import BatchedWoodburyMarginalLogLikelihood, sm_partial_mll
+    from online_gp_b200.models import FixedNoiseOnlineSKIGP, OnlineSKIRegression
+    from online_gp_b200.models.stems import Identity
+    return locals()
+
+
+def _grads(model):
+    """[t, (raw_ls..., raw_outputscale[, raw_noise])] in the golden's order."""
+    sk = model.covar_module.base_kernel
+    ls = sk.base_kernel.raw_lengthscale.grad
+    os_ = sk.raw_outputscale.grad
+    t = model._num_models
+    rows = []
+    for o in range(t):
+        parts = [ls.reshape(-1, ls.shape[-1])[o if ls.dim() > 2 else 0].cpu().numpy().reshape(-1),
+                 os_.reshape(-1)[o if os_.dim() > 0 else 0].cpu().numpy().reshape(-1)]
+        if model.has_learnable_noise:
+            parts.append(model.likelihood.second_noise_covar.raw_noise.grad.reshape(-1)[o].cpu().numpy().reshape(-1))
+        rows.append(np.concatenate(parts))
+    return np.stack(rows)
+
+
+@pytest.mark.parametrize("tag", ["t1", "t3"])
+@pytest.mark.parametrize("lt,learn", [("fixed", False), ("learn", True)])
+def test_g1_mll_and_grads(golden_dir, tag, lt, learn):
+    """tests/mlls/test_batched_woodbury_marginal_log_likelihood.py:55-82: MLL and hyper gradients == exact GP."""
+    M = _mods()
+    z = np.load(os.path.join(golden_dir, "g1_mll.npz"))
+    x, y, yvar = (torch.from_numpy(z[f"{tag}_{k}"]).to(_dev()) for k in ("x", "y", "yvar"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = M["FixedNoiseOnlineSKIGP"](train_inputs=x, train_targets=y, train_noise_term=yvar,
+                                           grid_bounds=torch.tensor([[0.0, 1.0], [0.0, 1.0]]), grid_size=5,
+                                           learn_additional_noise=learn)
+        mll = M["BatchedWoodburyMarginalLogLikelihood"](model.likelihood, model)
+        model.train()
+        with M["S"].skip_logdet_forward(False):
+            loss = mll(model(x), y)
+    loss.sum().backward()
+    assert np.allclose(loss.detach().cpu().numpy().reshape(-1), z[f"{tag}_{lt}_mll"], rtol=1e-5, atol=1e-8)
+    assert np.allclose(_grads(model), z[f"{tag}_{lt}_grad"], rtol=1e-4, atol=1e-7)
+    if tag == "t1" and not learn:
+        model.eval()
+        xs = torch.from_numpy(z["t1_xs"]).to(_dev())
+        dist = model(xs)
+        assert np.allclose(dist.mean.detach().cpu().numpy(), z["t1_mean"], rtol=1e-4, atol=1e-6)
+        assert np.allclose(dist.covariance_matrix.detach().cpu().numpy(), z["t1_cov"], rtol=1e-4, atol=1e-6)
+        assert np.allclose(dist.variance.detach().cpu().numpy(), np.diag(z["t1_cov"]), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("inplace", [True, False])
+@pytest.mark.parametrize("mode", ["sym", "svd"])
+def test_g2_update_sequence(golden_dir, inplace, mode):
+    M = _mods()
+    z = np.load(os.path.join(golden_dir, "g2_sequence.npz"))
+    tp = torch.from_numpy(z["test_points"]).to(_dev())
+    kern = M["RBFKernel"]()
+    kern.lengthscale = 10.0
+    model = None
+    with warnings.catch_warnings(), M["S"].root_update_mode(mode), M["S"].max_cholesky_size(2048):
+        warnings.simplefilter("ignore")
+        for k in range(5):
+            xk = torch.from_numpy(z[f"x{k}"]).to(_dev())
+            yk = torch.from_numpy(z[f"y{k}"]).to(_dev()).unsqueeze(-1)
+            if model is None:
+                model = M["FixedNoiseOnlineSKIGP"](xk, yk, torch.ones_like(yk), covar_module=kern,
+                                                   grid_bounds=[(-4.0, 14.0)], grid_size=20, learn_additional_noise=True)
+                model.likelihood.second_noise = 0.01
+            elif inplace:
+                model.condition_on_observations(xk, yk, torch.ones_like(yk), inplace=True)
+            else:
+                model = model.condition_on_observations(xk, yk, torch.ones_like(yk), inplace=False)
+            model.eval()
+            dist = model(tp)
+            assert np.allclose(dist.mean.detach().cpu().numpy(), z[f"mean{k}"], rtol=1e-4, atol=1e-6), k
+            assert np.allclose(dist.covariance_matrix.detach().cpu().numpy(), z[f"cov{k}"], rtol=1e-3, atol=1e-7), k
+            mll = M["BatchedWoodburyMarginalLogLikelihood"](model.likelihood, model)
+            model.train()
+            val = mll(model(None), None)
+            assert np.allclose(val.item(), z[f"mll{k}"], rtol=1e-4), k
+            assert model.num_data == sum(z[f"x{j}"].shape[0] for j in range(k + 1))
+
+
+@pytest.mark.parametrize("g", [4, 10])
+def test_g3_fantasy(golden_dir, g):
+    M = _mods()
+    z = np.load(os.path.join(golden_dir, "g3_strategy.npz"))
+    xs, labels = torch.from_numpy(z["xs"]).to(_dev()), torch.from_numpy(z["labels"]).to(_dev()).unsqueeze(-1)
+    npts = torch.from_numpy(z["new_points"]).to(_dev())
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = M["FixedNoiseOnlineSKIGP"](xs, labels, torch.ones_like(labels), covar_module=M["RBFKernel"](),
+                                           grid_bounds=[(-0.4, 1.4)], grid_size=g, learn_additional_noise=True)
+        model.likelihood.second_noise = 0.1
+        model.eval()
+        dist = model(npts)
+        assert np.allclose(dist.mean.detach().cpu().numpy(), z[f"g{g}_mean"], rtol=1e-5, atol=1e-6)
+        assert np.allclose(dist.covariance_matrix.detach().cpu().numpy(), z[f"g{g}_cov"], rtol=1e-5, atol=1e-6)
+        fant = model.get_fantasy_model(torch.from_numpy(z["fant_x"]).to(_dev()), torch.from_numpy(z["fant_y"]).to(_dev()),
+                                       torch.ones(1, 1, device=_dev()))
+        fant.eval()
+        dist2 = fant(npts)
+    assert np.allclose(dist2.mean.detach().cpu().numpy(), z[f"g{g}_fant_mean"], rtol=1e-5, atol=1e-6)
+    assert np.allclose(dist2.covariance_matrix.detach().cpu().numpy(), z[f"g{g}_fant_cov"], rtol=1e-5, atol=1e-6)
+    # the original model is untouched by the fantasy
+    dist3 = model(npts)
+    assert np.allclose(dist3.mean.detach().cpu().numpy(), z[f"g{g}_mean"], rtol=1e-5, atol=1e-6)
+
+
+def test_g4_cache_shapes():
+    """tests/models/test_batched_online_ski_gp_model.py:96-133."""
+    M = _mods()
+    train_x = torch.rand(10, 1, device=_dev())
+    train_y = torch.stack((torch.sin(3.0 * train_x), torch.sin(5.0 * train_x)))[..., 0].t()
+    train_y_var = 0.01 * train_y ** 2 + 1e-4
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = M["FixedNoiseOnlineSKIGP"](train_x[:5], train_y[:5], train_y_var[:5],
+                                           grid_bounds=torch.tensor([[0.0, 1.0]]), grid_size=10)
+        model.train()
+        dist = model(*model.train_inputs)
+        assert dist.mean.shape == torch.Size((2, 5)) and float(dist.mean.norm()) <= 1e-5
+        assert model.current_qmatrix.shape == torch.Size((2, 10, 10))
+        assert model._kernel_cache["WtW"].shape == torch.Size((2, 10, 10))
+        assert model._kernel_cache["D_logdet"].shape == torch.Size((2,))
+        assert model._kernel_cache["response_cache"].shape == torch.Size((2, 1, 1))
+        assert model._kernel_cache["interpolation_cache"].shape == torch.Size((2, 10, 1))
+        model.eval()
+        dist = model(train_x[5:])
+        assert dist.mean.shape == torch.Size((2, 5)) and dist.covariance_matrix.shape == torch.Size((2, 5, 5))
+        n0 = model.num_data
+        new_model = model.condition_on_observations(train_x[5:6], train_y[5:6], train_y_var[5:6], inplace=False)
+        assert new_model.num_data == n0 + 1 and model.num_data == n0
+        model.condition_on_observations(train_x[5:6], train_y[5:6], train_y_var[5:6], inplace=True)
+        assert model.num_data == n0 + 1
+        new_model.eval()
+        a, b = model(train_x[6:]), new_model(train_x[6:])
+        assert torch.allclose(a.mean, b.mean, rtol=1e-8, atol=1e-10)
+
+
+def _oracle_and_model(M, d, g, n0, dt, mcs, mode, kind="rbf", seed=0, max_root=512):
+    gen = torch.Generator().manual_seed(seed)
+    X = torch.rand(n0 + 40, d, generator=gen, dtype=torch.float64) * 2 - 1
+    y = torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + 40, generator=gen, dtype=torch.float64)
+    grid = create_grid([g] * d, [(-1.1, 1.1)] * d)
+    hyp = Hypers(d, kind=kind, has_scale=True, learn_noise=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        orc = WiskiMatFree(grid, hyp, X[:n0], y[:n0], torch.ones(n0, dtype=torch.float64), max_cholesky_size=mcs,
+                           max_root=max_root, update_mode="svd")
+        base = M["RBFKernel"](ard_num_dims=d) if kind == "rbf" else M["MaternKernel"](nu=float(kind[6:]), ard_num_dims=d)
+        with M["S"].max_cholesky_size(mcs), M["S"].max_root_decomposition_size(max_root), M["S"].root_update_mode(mode):
+            model = M["FixedNoiseOnlineSKIGP"](X[:n0].to(dt).to(_dev()), y[:n0].to(dt).to(_dev()).unsqueeze(-1),
+                                               torch.ones(n0, 1, dtype=dt, device=_dev()),
+                                               covar_module=M["ScaleKernel"](base),
+                                               grid_bounds=[(-1.1, 1.1)] * d, grid_size=[g] * d,
+                                               learn_additional_noise=True)
+    return orc, model, X, y, hyp
+
+
+CASES = [
+    # d, g, n0, max_cholesky_size (0 => low-rank matrix-free regime), kernel
+    (2, 12, 30, 2048, "rbf"),
+    (2, 24, 40, 0, "rbf"),
+    (3, 10, 50, 0, "matern2.5"),
+    (4, 8, 60, 0, "rbf"),
+    (1, 128, 25, 2048, "rbf"),
+    (2, 40, 30, 0, "matern0.5"),
+]
+
+
+@pytest.mark.parametrize("d,g,n0,mcs,kind", CASES)
+@pytest.mark.parametrize("mode", ["sym", "svd"])
+@pytest.mark.parametrize("dt", [torch.float64, torch.float32])
+def test_posterior_mll_grads_vs_matfree_oracle(d, g, n0, mcs, kind, mode, dt):
+    M = _mods()
+    orc, model, X, y, hyp = _oracle_and_model(M, d, g, n0, dt, mcs, mode, kind)
+    rt = 1e-4 if dt == torch.float64 else 1e-2
+    Xs = (torch.rand(9, d, dtype=torch.float64) * 2 - 1)
+    with M["S"].max_cholesky_size(max(mcs, 800)), M["S"].root_update_mode(mode), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for step in range(3):
+            model.eval()
+            dist = model(Xs.to(dt).to(_dev()))
+            mo, co = orc.predict(Xs)
+            scale_m = float(mo.abs().max())
+            assert np.allclose(dist.mean.detach().cpu().double().numpy(), mo.detach().numpy(), rtol=rt, atol=rt * scale_m)
+            vo = co.diagonal().detach().numpy()
+            assert np.allclose(dist.variance.detach().cpu().double().numpy(), vo, rtol=rt, atol=rt * float(vo.max()))
+            # MLL and hyper-parameter gradients
+            model.train()
+            model.zero_grad()
+            mll = M["BatchedWoodburyMarginalLogLikelihood"](model.likelihood, model)
+            val = mll(model(None), None)
+            val.sum().backward()
+            for p in hyp.params():
+                p.grad = None
+            vo_ = orc.mll()
+            vo_.backward()
+            assert np.allclose(val.item(), vo_.item(), rtol=rt), (val.item(), vo_.item())
+            if dt == torch.float64:
+                go = np.concatenate([p.grad.numpy().reshape(-1) for p in hyp.params()])
+                assert np.allclose(_grads(model)[0], go, rtol=1e-4, atol=1e-7 + 1e-4 * np.abs(go).max())
+            # condition on a few new points (q = 1, 3, 8)
+            q = [1, 3, 8][step]
+            s0 = n0 + sum([1, 3, 8][:step])
+            xn, yn = X[s0:s0 + q], y[s0:s0 + q]
+            orc.condition_on_observations(xn, yn, torch.ones(q, dtype=torch.float64))
+            model.condition_on_observations(xn.to(dt).to(_dev()), yn.to(dt).to(_dev()).unsqueeze(-1),
+                                            torch.ones(q, 1, dtype=dt, device=_dev()), inplace=True)
+
+
+def test_regression_wrapper_stream_matches_oracle_loop():
+    """OnlineSKIRegression.evaluate + update over a short stream == the same loop on the oracle (fp64):
+    Adam step on -MLL (logdet value skipped, gradient kept) then conditioning; experiments/regression.py:48-54."""
+    M = _mods()
+    d, g, n0, steps = 2, 10, 20, 6
+    gen = torch.Generator().manual_seed(5)
+    X = torch.rand(n0 + steps, d, generator=gen) * 2 - 1
+    y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen)).unsqueeze(-1)
+    with warnings.catch_warnings(), M["S"].max_cholesky_size(2048):
+        warnings.simplefilter("ignore")
+        reg = M["OnlineSKIRegression"](M["Identity"](d), X[:n0].to(_dev()), y[:n0].to(_dev()), lr=1e-2, grid_size=g,
+                                       grid_bound=1.0)
+        reg.set_lr(1e-2)
+        grid = create_grid([g] * d, [(-1.1, 1.1)] * d)
+        hyp = Hypers(d, learn_noise=True)
+        orc = WiskiRef(grid, hyp, X[:n0], y[:n0, 0], torch.ones(n0))
+        opt = torch.optim.Adam(hyp.params(), lr=1e-2)
+        for t in range(steps):
+            xt, yt = X[n0 + t:n0 + t + 1], y[n0 + t:n0 + t + 1]
+            with M["S"].detach_interp_coeff(True):
+                rmse, nll = reg.evaluate(xt.to(_dev()), yt.to(_dev()))
+            mo, co = orc.predict(xt)
+            var_o = co.diagonal() + hyp.noise
+            rmse_o = float((mo - yt[:, 0]).pow(2).mean().sqrt())
+            nll_o = float(-torch.distributions.Normal(mo, var_o.sqrt()).log_prob(yt[:, 0]).mean())
+            assert abs(rmse - rmse_o) <= 1e-4 * max(1.0, abs(rmse_o)), (t, rmse, rmse_o)
+            assert abs(nll - nll_o) <= 1e-4 * max(1.0, abs(nll_o)), (t, nll, nll_o)
+            stem_loss, gp_loss = reg.update(xt.to(_dev()), yt.to(_dev()), update_stem=True)
+            opt.zero_grad()
+            (-orc.mll()).backward()
+            opt.step()
+            orc.condition_on_observations(xt, yt[:, 0], torch.ones(1))
+            assert abs(float(reg.noise.mean()) - float(hyp.noise)) <= 1e-6
+        ls = reg.gp.covar_module.base_kernel.base_kernel.lengthscale.detach().cpu().reshape(-1)
+        assert torch.allclose(ls, hyp.lengthscale.detach(), rtol=1e-6)
+
+
+def test_cg_path_matches_cholesky_path():
+    """max_cholesky_size(0) forces Q solves through the fused-MVM CG driver (the stale reference tests do the
+    same, tests/models/test_woodbury_prediction_strategy.py:57-61); with a tight tolerance it must agree."""
+    M = _mods()
+    orc, model, X, y, hyp = _oracle_and_model(M, 2, 24, 60, torch.float64, 0, "sym")
+    Xs = (torch.rand(7, 2) * 2 - 1).to(_dev())
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.eval()
+        with M["S"].max_cholesky_size(800):
+            ref = model(Xs)
+            rm, rv = ref.mean.clone(), ref.variance.clone()
+        model._dump_caches()
+        with M["S"].max_cholesky_size(0), M["S"].eval_cg_tolerance(1e-10):
+            out = model(Xs)
+            om, ov = out.mean.clone(), out.variance.clone()
+            it, res = model.current_qmatrix[0].last_cg
+    assert it > 0 and res < 1e-8
+    assert torch.allclose(om, rm, rtol=1e-6, atol=1e-8) and torch.allclose(ov, rv, rtol=1e-6, atol=1e-9)
+
+
+def test_sm_partial_mll_matches_oracle():
+    M = _mods()
+    d, g, n0 = 2, 10, 25
+    gen = torch.Generator().manual_seed(9)
+    X = torch.rand(n0 + 1, d, generator=gen) * 2 - 1
+    y = torch.sin(3 * X.sum(-1))
+    with warnings.catch_warnings(), M["S"].max_cholesky_size(2048):
+        warnings.simplefilter("ignore")
+        model = M["FixedNoiseOnlineSKIGP"](X[:n0].to(_dev()), y[:n0].to(_dev()).unsqueeze(-1), torch.ones(n0, 1, device=_dev()),
+                                           grid_bounds=[(-1.1, 1.1)] * d, grid_size=[g] * d, learn_additional_noise=True)
+        model.eval()
+        orc = WiskiRef(create_grid([g] * d, [(-1.1, 1.1)] * d), Hypers(d, learn_noise=True), X[:n0], y[:n0], torch.ones(n0))
+        xn = X[n0:].clone().requires_grad_(True)
+        vo = orc.sm_partial_mll(xn, y[n0:], n0)
+        vo.backward()
+        xg = X[n0:].to(_dev()).requires_grad_(True)
+        vg = M["sm_partial_mll"](model, xg, y[n0:].to(_dev()).reshape(1, 1, 1), n0)
+        vg.sum().backward()
+    assert abs(vg.item() - vo.item()) <= 1e-6 * max(1.0, abs(vo.item()))
+    assert torch.allclose(xg.grad.cpu(), xn.grad, rtol=1e-5, atol=1e-8)
