@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — WISKI streaming updates/sec on B200 (BASELINE.json metric), with roofline and CPU baseline.
+
+A "step" is one pass of the reference's streaming loop body (experiments/regression.py:49-54) on one batch of q
+synthetic points:  OnlineSKIRegression.evaluate(x_t, y_t)  (posterior mean + variance at the new points, caches
+rebuilt)  +  OnlineSKIRegression.update(x_t, y_t)  (one Adam step on the Woodbury MLL over lengthscales /
+outputscale / noise  +  condition_on_observations in place).  Default workload = BASELINE.json configs[1]:
+powerplant-shaped 4-D stream, 32^4 inducing grid, batch_size 1, fp32 (reference default dtype), n_init = 430.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` = updates/s with inputs resident in HBM; `e2e` = the same loop fed from
+pinned host memory (H2D copy of every batch and the D2H metric reads inside the timed region).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+WORKLOADS = {
+    # name: (d, g, q, n_init, description)
+    "powerplant_4d_g32": (4, 32, 1, 430, "powerplant-shaped 4-D stream, 32^4 inducing grid, batch_size=1"),
+    "road3d_3d_g128": (3, 128, 8, 19569, "3droad-shaped 3-D stream, 128^3 grid, batch_size=8"),
+    "malaria_2d_g256": (2, 256, 6, 10, "malaria-shaped 2-D stream, 256^2 grid, batch_size=6"),
+    "synthetic_1d_g128": (1, 128, 1, 25, "1-D synthetic regression, 128-point grid, batch_size=1"),
+    "target_2d_g1024": (2, 1024, 1, 430, "2-D stream, 1024^2 grid, batch_size=1"),
+}
+MAX_ROOT, MAX_CHOL, CG_TOL = 512, 2048, 1e-2      # config/regression.yaml:24-27
+
+
+def synth_stream(d, n, seed=0):
+    """x ~ U(-1,1)^d, y = sin(3 sum x) + 0.1 eps, z-scored; torch.Generator().manual_seed(0)."""
+    gen = torch.Generator().manual_seed(seed)
+    x = torch.rand(n, d, generator=gen) * 2 - 1
+    y = torch.sin(3 * x.sum(-1)) + 0.1 * torch.randn(n, generator=gen)
+    y = (y - y.mean()) / y.std()
+    return x, y.unsqueeze(-1)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        z = json.load(open(p))
+        return z["hbm_gbs"], z.get("bf16_tflops_sustained", z["bf16_tflops"]), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, reasons = [], None, set()
+        for line in self.f.read().splitlines():
+            parts = [t.strip() for t in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def build_model(d, g, n_init, dtype, device):
+    from online_gp_b200 import settings as S
+    from online_gp_b200.models import OnlineSKIRegression
+    from online_gp_b200.models.stems import Identity
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        x, y = synth_stream(d, n_init + 4096)
+        x, y = x.to(dtype), y.to(dtype)
+        with S.max_root_decomposition_size(MAX_ROOT), S.max_cholesky_size(MAX_CHOL), S.cg_tolerance(CG_TOL):
+            model = OnlineSKIRegression(Identity(d), x[:n_init].to(device), y[:n_init].to(device), lr=5e-3,
+                                        grid_size=g, grid_bound=1.0)
+            model.set_lr(5e-3)       # base_lr / 10 for powerplant (experiments/regression.py:138)
+    finally:
+        torch.set_default_dtype(prev)
+    return model, x[n_init:], y[n_init:]
+
+
+def one_step(model, xb, yb):
+    from online_gp_b200 import settings as S
+    with S.detach_interp_coeff(True):
+        rmse, nll = model.evaluate(xb, yb)
+    stem_loss, gp_loss = model.update(xb, yb, update_stem=True)
+    return rmse, nll, gp_loss
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    from online_gp_b200 import _lib, ops
+    from online_gp_b200 import settings as S
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    d, g, q, n_init, desc = WORKLOADS[args.workload]
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    lib = _lib.load()
+
+    if world > 1:
+        from online_gp_b200.parallel import ShardedBench
+        return ShardedBench(args, rank, world, device).run()
+
+    model, xs, ys = build_model(d, g, n_init, dtype, device)
+    m = g ** d
+    r = model.gp._kernel_cache["WtW"].root.shape[-1]
+    ctx = (S.max_root_decomposition_size(MAX_ROOT), S.max_cholesky_size(MAX_CHOL), S.cg_tolerance(CG_TOL))
+    for c in ctx:
+        c.__enter__()
+    K, W = args.steps, args.warmup
+    need = (K + W) * 2 * q
+    assert xs.shape[0] >= need, "stream too short"
+    xd, yd = xs.to(device), ys.to(device)
+    xh, yh = xs.pin_memory(), ys.pin_memory()
+
+    def batch_dev(t):
+        return xd[t * q:(t + 1) * q], yd[t * q:(t + 1) * q]
+
+    def batch_host(t):
+        return (xh[t * q:(t + 1) * q].to(device, non_blocking=True), yh[t * q:(t + 1) * q].to(device, non_blocking=True))
+
+    t = 0
+    for _ in range(W):
+        one_step(model, *batch_dev(t))
+        t += 1
+    # ---- device-resident timing (value) with per-op events for the roofline
+    prof_names = {"wiski_kron_toeplitz_mm", "wiski_kron_toeplitz_bwd_cols", "wiski_gram", "wiski_panel_rmul",
+                  "wiski_panel_lowrank_update", "wiski_gather", "wiski_scatter_add", "wiski_interp_fwd"}
+    ops.PROFILE = {"names": prof_names, "events": {}}
+    clocks = ClockSampler(local_rank)
+    launches0 = lib.wiski_launch_count()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        one_step(model, *batch_dev(t))
+        t += 1
+    e1.record()
+    torch.cuda.synchronize()
+    ms_dev = e0.elapsed_time(e1)
+    launches = lib.wiski_launch_count() - launches0
+    prof, ops.PROFILE = ops.PROFILE, None
+    # ---- end-to-end timing from pinned host memory
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(K):
+        one_step(model, *batch_host(t))
+        t += 1
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    clk = clocks.stop()
+
+    # ---- per-op device time -> roofline of the dominant op
+    b = 4 if dtype == torch.float32 else 8
+    per_op = {}
+    for name, evs in prof["events"].items():
+        tot = sum(a.elapsed_time(bb) for a, bb, _ in evs)
+        per_op[name] = {"calls_per_step": len(evs) / K, "ms_per_step": tot / K, "ms_per_call": tot / len(evs)}
+    step_ms = ms_dev / K
+    dom = max(per_op, key=lambda n: per_op[n]["ms_per_step"])
+    hbm_peak, tf_peak, peak_src = peaks()
+    # algorithmic bytes / flops per launch (DESIGN.md "Kernels and rooflines")
+    big = [(a, bb) for a, bb, ar in prof["events"].get("wiski_kron_toeplitz_mm", [])]
+    alg = {
+        "wiski_kron_toeplitz_mm": ("hbm", 2.0 * m * r * b),                  # m x r panel, ideal single pass
+        "wiski_kron_toeplitz_bwd_cols": ("hbm", 2.0 * m * r * b),            # read Z and X once
+        "wiski_panel_lowrank_update": ("hbm", 2.0 * m * r * b),              # read + write the panel
+        "wiski_gram": ("tensor", 2.0 * m * r * r),                           # flops
+        "wiski_panel_rmul": ("tensor", 2.0 * m * r * r),
+    }
+    roof = None
+    if dom in alg:
+        bound, work = alg[dom]
+        # use the slowest-size calls only (panel-sized calls dominate; m x 1 calls of the same op are excluded)
+        evs = prof["events"][dom]
+        times = sorted(a.elapsed_time(bb) for a, bb, _ in evs)
+        big_t = [x for x in times if x >= 0.5 * times[-1]]
+        avg_ms = sum(big_t) / len(big_t)
+        if bound == "hbm":
+            ach = work / (avg_ms * 1e-3) / 1e9
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": avg_ms}
+        else:
+            ach = work / (avg_ms * 1e-3) / 1e12
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src + " (bf16 dense cuBLAS)",
+                    "ms_per_launch": avg_ms}
+    out = {
+        "metric": "wiski_streaming_updates_per_sec", "value": K / (ms_dev * 1e-3), "unit": "updates/s",
+        "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "d": d, "grid": g, "m": m, "q": q, "n_init": n_init,
+                   "root_rank": r, "stencil": 4 ** d, "l2": "panels (m*r*%d B = %.2f GB each) are far larger than L2" % (b, m * r * b / 1e9),
+                   "step": "evaluate + update (Adam step on Woodbury MLL + condition_on_observations)",
+                   "root_update_mode": S.root_update_mode.value()},
+        "clocks": clk,
+        "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": q * (d + 1) * b,
+                "d2h_bytes_per_step": 3 * b + 4},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "per_op_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_op.items())},
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_budget)
+    for c in ctx:
+        c.__exit__(None, None, None)
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def cpu_steps(args, max_steps, budget_s, warm=1):
+    """The reference's algorithm for the same step on host cores: oracle/wiski_matfree.py (literal SVD root update,
+    torch CPU autograd for the hyper gradient), all host threads."""
+    from oracle.gridkernel import Hypers
+    from oracle.interp import create_grid
+    from oracle.wiski_matfree import WiskiMatFree
+
+    d, g, q, n_init, desc = WORKLOADS[args.workload]
+    dtype = torch.float32 if args.dtype == "f32" else torch.float64
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    x, y = synth_stream(d, n_init + 4096)
+    grid = create_grid([g] * d, [(-1.1, 1.1)] * d)
+    hyp = Hypers(d, learn_noise=True, dtype=dtype)
+    t0 = time.time()
+    model = WiskiMatFree(grid, hyp, x[:n_init].to(dtype), y[:n_init, 0].to(dtype), torch.ones(n_init, dtype=dtype),
+                         max_cholesky_size=MAX_CHOL, max_root=MAX_ROOT, dtype=dtype, update_mode="svd")
+    init_s = time.time() - t0
+    opt = torch.optim.Adam(hyp.params(), lr=5e-3)
+    xs, ys = x[n_init:].to(dtype), y[n_init:, 0].to(dtype)
+    times = []
+    t = 0
+    start = time.time()
+    while len(times) < max_steps + warm:
+        s0 = time.time()
+        xb, yb = xs[t * q:(t + 1) * q], ys[t * q:(t + 1) * q]
+        pieces = model.pieces()
+        with torch.no_grad():
+            mean, cov = model.predict(xb, pieces=pieces)                       # evaluate()
+            var = cov.diagonal() + hyp.noise
+            _ = float((mean - yb).pow(2).mean().sqrt())
+            _ = float(-torch.distributions.Normal(mean, var.sqrt()).log_prob(yb).mean())
+        opt.zero_grad()
+        loss = -model.mll(pieces=pieces)                                       # _update_gp()
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            model.condition_on_observations(xb, yb, torch.ones(q, dtype=dtype))   # condition, literal SVD update
+        times.append(time.time() - s0)
+        t += 1
+        if len(times) > warm and time.time() - start > budget_s:
+            break
+    timed = times[warm:] if len(times) > warm else times
+    return timed, cores, init_s, model.L.shape[1]
+
+
+def cpu_baseline(args, budget_s):
+    timed, cores, init_s, r = cpu_steps(args, max_steps=3, budget_s=budget_s, warm=1)
+    per = sum(timed) / len(timed)
+    return {"value": 1.0 / per, "unit": "updates/s", "cores": cores, "kind": "port",
+            "sample": f"{len(timed)} timed step(s) after 1 warm-up of the same workload (m={WORKLOADS[args.workload][1] ** WORKLOADS[args.workload][0]}, r={r}), "
+                      f"oracle/wiski_matfree.py on torch CPU, {per:.2f} s/step"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    d, g, q, n_init, desc = WORKLOADS[args.workload]
+    timed, cores, init_s, r = cpu_steps(args, max_steps=args.steps, budget_s=args.cpu_budget * 4, warm=min(args.warmup, 1))
+    per = sum(timed) / len(timed)
+    val = 1.0 / per
+    out = {
+        "impl": "reference", "metric": "wiski_streaming_updates_per_sec", "value": val, "unit": "updates/s",
+        "n_gpus": args.gpus, "steps": len(timed), "warmup": min(args.warmup, 1), "ms_per_step": per * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": {"workload": args.workload, "description": desc, "d": d, "grid": g, "m": g ** d, "q": q,
+                   "n_init": n_init, "root_rank": r,
+                   "step": "evaluate + update (Adam step on Woodbury MLL + condition_on_observations)"},
+        "cpu_baseline": {"value": val, "unit": "updates/s", "cores": cores, "kind": "port",
+                         "sample": f"{len(timed)} timed step(s) (time-boxed) of the same workload on host cores; the "
+                                   f"reference package itself needs GPyTorch/BoTorch, which cannot be installed "
+                                   f"offline, so this is the oracle port oracle/wiski_matfree.py"},
+        "e2e": {"value": val, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="powerplant_4d_g32", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=30.0, help="seconds of CPU work for the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

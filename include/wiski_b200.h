@@ -26,6 +26,8 @@ extern "C" {
 
 const char* wiski_last_error(void);
 int wiski_abi_version(void);
+/* number of CUDA kernels this library has enqueued so far in this process (bench.py's gpu_launches) */
+long long wiski_launch_count(void);
 
 /* ---- k1: cubic-convolution interpolation stencils.
  * Replaces GPyTorch Interpolation.interpolate (App. A.1) reached from

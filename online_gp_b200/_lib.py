@@ -35,7 +35,7 @@ def _sigs(real, realp):
 
 
 #: every symbol include/wiski_b200.h declares (tests check the .so exports all of them)
-EXPORTED = ["wiski_last_error", "wiski_abi_version", "wiski_gram_work_elems", "wiski_qmv_work_elems",
+EXPORTED = ["wiski_last_error", "wiski_abi_version", "wiski_launch_count", "wiski_gram_work_elems", "wiski_qmv_work_elems",
             "wiski_cg_work_elems", "wiski_kron_toeplitz_bwd_work_elems"] + [
     f"{n}_{sfx}" for n in _sigs(c_float, POINTER(c_float)) for sfx in ("f32", "f64")]
 
@@ -53,6 +53,8 @@ def load():
     lib.wiski_last_error.restype = c_char_p
     lib.wiski_last_error.argtypes = []
     lib.wiski_abi_version.restype = c_int
+    lib.wiski_launch_count.restype = ctypes.c_longlong
+    lib.wiski_launch_count.argtypes = []
     for name in ("wiski_gram_work_elems", "wiski_qmv_work_elems", "wiski_cg_work_elems"):
         fn = getattr(lib, name)
         fn.restype = c_int64

@@ -8,6 +8,7 @@
 namespace wiski {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // kernels enqueued by this library (bench.py reports it as gpu_launches)
 
 #define WISKI_CHECK_ARG(cond, ...)                \
     do {                                          \

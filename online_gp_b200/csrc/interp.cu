@@ -17,6 +17,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+
 template <typename T>
 struct InterpParams {
     int d;
@@ -237,6 +240,7 @@ static int interp_fwd(const T* x, int64_t q, int d, const int64_t* h_g, const T*
     int64_t total = q * s;
     interp_fwd_kernel<T><<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(x, q, s, p, idx, val, oob);
     WISKI_CHECK_LAUNCH("interp_fwd");
+    count_launches(1);
     return 0;
 }
 
@@ -251,6 +255,7 @@ static int interp_bwd(const T* x, int64_t q, int d, const int64_t* h_g, const T*
     int64_t warps = q * d;
     interp_bwd_kernel<T><<<(unsigned)ceil_div(warps * 32, 128), 128, 0, as_stream(stream)>>>(x, q, s, p, gval, gx);
     WISKI_CHECK_LAUNCH("interp_bwd");
+    count_launches(1);
     return 0;
 }
 
@@ -268,6 +273,7 @@ static int gather(const int64_t* idx, const T* val, int64_t q, int64_t s, const 
                                                                                                    src, c, out);
     }
     WISKI_CHECK_LAUNCH("gather");
+    count_launches(1);
     return 0;
 }
 
@@ -279,6 +285,7 @@ static int scatter_add(const int64_t* idx, const T* val, int64_t q, int64_t s, c
     int64_t total = q * s * c;
     scatter_add_kernel<T><<<(unsigned)ceil_div(total, 256), 256, 0, as_stream(stream)>>>(idx, val, q, s, src, c, dst);
     WISKI_CHECK_LAUNCH("scatter_add");
+    count_launches(1);
     return 0;
 }
 
@@ -288,6 +295,7 @@ extern "C" {
 
 const char* wiski_last_error(void) { return wiski::g_err; }
 int wiski_abi_version(void) { return 1; }
+long long wiski_launch_count(void) { return __atomic_load_n(&wiski::g_launches, __ATOMIC_RELAXED); }
 
 int wiski_interp_fwd_f32(const float* x, int64_t q, int d, const int64_t* h_g, const float* h_lo,
                          const float* h_delta, const float* h_first4, const float* h_last4, const float* h_gmin,

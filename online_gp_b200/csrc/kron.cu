@@ -229,6 +229,7 @@ static int launch_axis_apply(const T* X, T* Y, const T* col, int64_t g, int64_t 
 #undef LAUNCH_SMEM
     }
     WISKI_CHECK_LAUNCH("kron_toeplitz_mm");
+    count_launches(1);
     return 0;
 }
 
@@ -268,6 +269,7 @@ static int launch_axis_contract(const T* Z, const T* P, int64_t g, int64_t outer
 #undef LAUNCH_C
     }
     WISKI_CHECK_LAUNCH("kron_toeplitz_bwd_cols");
+    count_launches(1);
     return 0;
 }
 
@@ -360,6 +362,7 @@ static int kron_bwd_cols(const T* cols, int d, const int64_t* h_g, int64_t gmax,
     }
     cvt_f64_kernel<T><<<(unsigned)ceil_div(nacc, 256), 256, 0, st>>>(acc64, grad_cols, nacc);
     WISKI_CHECK_LAUNCH("kron_toeplitz_bwd_cols");
+    count_launches(2);
     return 0;
 }
 

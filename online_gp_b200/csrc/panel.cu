@@ -365,6 +365,7 @@ static int panel_rmul(const T* P, int64_t m, int64_t r, const T* M, int64_t r2, 
         rmul_tile_kernel<T><<<grid, 256, 0, st>>>(P, M, Out, m, r, r2);
     }
     WISKI_CHECK_LAUNCH("panel_rmul");
+    count_launches(1);
     return 0;
 }
 
@@ -385,6 +386,7 @@ static int lowrank_update(T* P, int64_t m, int64_t r, const T* U, const T* Vt, i
     else LR(32);
 #undef LR
     WISKI_CHECK_LAUNCH("panel_lowrank_update");
+    count_launches(1);
     return 0;
 }
 
@@ -425,6 +427,7 @@ static int gram(const T* A, const T* Bm, int64_t m, int64_t r, int64_t r2, T* G,
         reduce_parts_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, ks, n, (const T*)nullptr, G);
     }
     WISKI_CHECK_LAUNCH("gram");
+    count_launches(2);
     return 0;
 }
 
@@ -470,6 +473,7 @@ static int q_matvec(const T* L, const T* KL, int64_t m, int64_t r, const T* v, i
     int64_t n = r * c;
     reduce_parts_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nb, n, v, w);
     WISKI_CHECK_LAUNCH("q_matvec");
+    count_launches(2);
     return 0;
 }
 
@@ -491,6 +495,7 @@ static int cg_solve(const T* L, const T* KL, int64_t m, int64_t r, const T* rhs,
     while (it < max_iter) {
         if (int rc = q_matvec<T>(L, KL, m, r, s.p, c, s.Ap, qwork, stream)) return rc;
         cg_update_kernel<T><<<1, 256, 0, st>>>(r, (int)c, tol, s);
+        count_launches(1);
         ++it;
         if (it % check_every == 0 || it == max_iter) {
             WISKI_CHECK_CUDA(cudaMemcpyAsync(&resid, s.resid, sizeof(T), cudaMemcpyDeviceToHost, st), "cg_solve");
@@ -500,6 +505,7 @@ static int cg_solve(const T* L, const T* KL, int64_t m, int64_t r, const T* rhs,
     }
     cg_finish_kernel<T><<<1, 256, 0, st>>>(r, (int)c, s, x);
     WISKI_CHECK_LAUNCH("cg_solve");
+    count_launches(2);
     if (h_iters) *h_iters = it;
     if (h_resid) *h_resid = resid;
     return 0;

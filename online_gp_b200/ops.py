@@ -38,8 +38,19 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+#: optional per-op device timing (bench.py): {"names": set(...), "events": {name: [(start, end), ...]}}
+PROFILE = None
+
+
 def _call(name, dtype, *args):
     fn = getattr(_lib.load(), f"{name}_{_sfx(dtype)}")
+    if PROFILE is not None and name in PROFILE["names"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(fn(*args), name)
+        e1.record()
+        PROFILE["events"].setdefault(name, []).append((e0, e1, args))
+        return
     _lib.check(fn(*args), name)
 
 
