@@ -14,3 +14,7 @@ for f in interp kron panel gemm_tc; do
 done
 $NVCC -shared -o libwiski_b200.so $OBJS -lcudart -lcuda
 echo "built $(pwd)/libwiski_b200.so"
+# standalone tensor-core GEMM check (run on the GPU box: online_gp_b200/csrc/test_gemm_tc)
+if [ test_gemm_tc.cu -nt test_gemm_tc ] || [ gemm_tc.o -nt test_gemm_tc ]; then
+  $NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a test_gemm_tc.cu gemm_tc.o interp.o -o test_gemm_tc -lcudart -lcuda
+fi

@@ -1,9 +1,422 @@
-// fp32 tensor-core (tcgen05, kind::tf32) versions of the two real contractions: Gram and panel right-multiply.
-// Placeholder until the tcgen05 kernels land: reports "unsupported" (3) so panel.cu falls through to the SIMT path.
+// fp32 tensor-core versions of the two real contractions on the WISKI path (sm_100a: tcgen05 + TMEM + TMA):
+//   Gram        G[r x r2]  = A^T Bm        A [m x r],  Bm [m x r2]   (Q - I = L^T (K L);  k10)
+//   panel rmul  Out[m x r2] = P M          P [m x r],  M [r x r2]    (L <- L (U S~), grad_KL = L grad_Q;  k7)
+//
+// Precision: operands are fp32, tcgen05.mma kind::tf32 keeps 10 mantissa bits, so each operand tile is split in
+// shared memory into big = x with the low 13 mantissa bits cleared and small = x - big (exact), and every k-step
+// issues three MMAs  big*big + big*small + small*big  into the same fp32 TMEM accumulator ("3xTF32"; the dropped
+// small*small term is 2^-22 relative).  K is additionally cut into short slices whose partial tiles are summed in
+// double by reduce_parts_kernel, so accumulator rounding does not grow with m.
+//
+// Structure of one CTA (256 threads, 1 CTA / SM), output tile 128 x BN (BN <= 256, multiple of 32):
+//   warp 0      TMA producer: cp.async.bulk.tensor boxes of 32 floats (128 B, SWIZZLE_128B) -> smem stage ring
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::tf32, tcgen05.commit -> mbarriers
+//   warp 2      TMEM allocator (tcgen05.alloc / dealloc)
+//   warps 4-7   operand split (generic-proxy read/modify/write of the landed tiles + fence.proxy.async), then the
+//               epilogue: tcgen05.ld 32x32b.x32 -> registers -> global
+// Operand layouts in smem follow the canonical UMMA layouts (CUTLASS cute/atom/mma_traits_sm100.hpp):
+//   MN-major tf32 : SWIZZLE_128B_BASE32B (the only MN-major layout the hardware accepts for 32-bit operands; TMA
+//                   CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): atoms of 32 floats (MN, contiguous) x 4 K rows of 128 B;
+//                   LBO = stride between MN atoms, SBO = stride between 4-row K groups (512 B).
+//   K-major  SW128: rows of 32 floats (K), 8-row groups of 1024 B (SBO); K advances by 32 B inside the row.
+#include <cuda.h>
 #include "common.cuh"
 
 namespace wiski {
-int tc_gram_f32(const float*, const float*, int64_t, int64_t, int64_t, float*, float*, cudaStream_t) { return 3; }
-int tc_panel_rmul_f32(const float*, int64_t, int64_t, const float*, int64_t, float*, cudaStream_t) { return 3; }
-int64_t tc_gram_work_elems(int64_t, int64_t, int64_t) { return 0; }
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): SWIZZLE_128B, version 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                             uint32_t layout_type = 2) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
+    d |= (uint64_t)layout_type << 61;   // 2 = SWIZZLE_128B (K-major), 1 = SWIZZLE_128B_BASE32B (MN-major tf32)
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, M = 128, N = n.
+__host__ __device__ inline uint32_t make_idesc(bool a_mn_major, bool b_mn_major, int n) {
+    uint32_t d = 0;
+    d |= 1u << 4;                          // c_format = F32
+    d |= 2u << 7;                          // a_format = TF32
+    d |= 2u << 10;                         // b_format = TF32
+    d |= (a_mn_major ? 1u : 0u) << 15;     // a_major
+    d |= (b_mn_major ? 1u : 0u) << 16;     // b_major
+    d |= (uint32_t)(n >> 3) << 17;         // n_dim
+    d |= (uint32_t)(128 >> 4) << 24;       // m_dim
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+// D[128 x BN] (+)= sum_k opA[k][m] * opB[k][n] over this CTA's K slice.
+//   A_KMAJOR = false: A global [Kdim rows][Mdim cols] (MN-major; Gram).   true: A global [Mdim rows][Kdim cols] (rmul).
+//   B global [Kdim rows][Ndim cols] (MN-major) in both modes.
+// out: slice z writes out + z * slice_stride, row-major with leading dimension ld_out.
+template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
+__global__ void __launch_bounds__(256, 1)
+tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ out,
+                 int64_t Mdim, int64_t Ndim, int64_t Kdim, int BN, int64_t k_per_slice, int64_t ld_out,
+                 int64_t slice_stride, float* __restrict__ dbg) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is at least 16-byte aligned -> realign.
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int A_BYTES = 128 * BK * 4;
+    const int B_BYTES = BN * BK * 4;
+    const int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t* full_bar = bars;                  // [STAGES] TMA landed
+    uint64_t* ready_bar = bars + STAGES;        // [STAGES] operands split
+    uint64_t* empty_bar = bars + 2 * STAGES;    // [STAGES] MMAs retired
+    uint64_t* tmem_full_bar = bars + 3 * STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t m0 = (int64_t)blockIdx.x * 128;
+    const int64_t n0 = (int64_t)blockIdx.y * BN;
+    const int64_t k_begin = (int64_t)blockIdx.z * k_per_slice;
+    int64_t k_end = k_begin + k_per_slice;
+    if (k_end > Kdim) k_end = Kdim;
+    const int num_kb = (int)((k_end - k_begin + BK - 1) / BK);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&ready_bar[s], 128);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 2) tmem_alloc(tmem_ptr, 256);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+                uint8_t* sB = sA + 2 * A_BYTES;
+                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + B_BYTES));
+                const int k = (int)(k_begin + (int64_t)kb * BK);
+                if (A_KMAJOR) {
+                    tma_load_2d(sA, &tmA, &full_bar[stage], k, (int)m0);                 // box {32 k, 128 rows}
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)                                         // boxes {32 cols, BK rows}
+                        tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], (int)m0 + 32 * j, k);
+                }
+                if (B_KMAJOR) {
+                    tma_load_2d(sB, &tmB, &full_bar[stage], k, (int)n0);                 // box {32 k, BN rows}
+                } else {
+                    for (int j = 0; j < BN / 32; ++j)
+                        tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], (int)n0 + 32 * j, k);
+                }
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(!A_KMAJOR, !B_KMAJOR, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(&ready_bar[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t aB = smem_u32(smem + (size_t)stage * STAGE_BYTES);   // A big
+                const uint32_t aS = aB + A_BYTES;                                     // A small
+                const uint32_t bB = aB + 2 * A_BYTES;                                 // B big
+                const uint32_t bS = bB + B_BYTES;                                     // B small
+#pragma unroll
+                for (int ks = 0; ks < BK / 8; ++ks) {
+                    uint64_t dAb, dAs;
+                    if (A_KMAJOR) {
+                        dAb = make_desc(aB + ks * 32, 0, 1024);
+                        dAs = make_desc(aS + ks * 32, 0, 1024);
+                    } else {
+                        dAb = make_desc(aB + ks * 1024, BK * 128, 512, 1);
+                        dAs = make_desc(aS + ks * 1024, BK * 128, 512, 1);
+                    }
+                    const uint64_t dBb = B_KMAJOR ? make_desc(bB + ks * 32, 0, 1024) : make_desc(bB + ks * 1024, BK * 128, 512, 1);
+                    const uint64_t dBs = B_KMAJOR ? make_desc(bS + ks * 32, 0, 1024) : make_desc(bS + ks * 1024, BK * 128, 512, 1);
+                    umma_tf32(tmem_base, dAs, dBb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
+                    umma_tf32(tmem_base, dAb, dBs, idesc, 1u);
+                    umma_tf32(tmem_base, dAb, dBb, idesc, 1u);
+                }
+                umma_commit(&empty_bar[stage]);
+                if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ operand split, then epilogue
+        const int t = threadIdx.x - 128;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int nvec = (A_BYTES + B_BYTES) / 16;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+            for (int i = t; i < nvec; i += 128) {
+                // vectors [0, A_BYTES/16) belong to A (big at sA, small at sA + A_BYTES), the rest to B
+                const bool isA = i < A_BYTES / 16;
+                uint4* big = reinterpret_cast<uint4*>(isA ? sA : sA + 2 * A_BYTES) + (isA ? i : i - A_BYTES / 16);
+                uint4* sml = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(big) + (isA ? A_BYTES : B_BYTES));
+                uint4 v = *big;
+                uint4 b, s;
+                b.x = v.x & 0xffffe000u; b.y = v.y & 0xffffe000u; b.z = v.z & 0xffffe000u; b.w = v.w & 0xffffe000u;
+                s.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(b.x));
+                s.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(b.y));
+                s.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(b.z));
+                s.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(b.w));
+                *big = b;
+                *sml = s;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (dbg != nullptr && kb == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (t < 64) {
+                    dbg[t] = reinterpret_cast<float*>(sA)[t];
+                    dbg[64 + t] = reinterpret_cast<float*>(sA + A_BYTES)[t];
+                    dbg[128 + t] = reinterpret_cast<float*>(sA + 2 * A_BYTES)[t];
+                    dbg[192 + t] = reinterpret_cast<float*>(sA + 2 * A_BYTES + B_BYTES)[t];
+                }
+            }
+            mbar_arrive(&ready_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 ; thread = output row
+        if (num_kb > 0) {
+            mbar_wait(tmem_full_bar, 0);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const int wq = warp & 3;
+        const int64_t row = m0 + wq * 32 + lane;
+        float* orow = out + (int64_t)blockIdx.z * slice_stride + row * ld_out;
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            if (num_kb > 0) {
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0u;
+            }
+            if (dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && c0 == 0 && wq == 0 && lane < 2) {
+                for (int j = 0; j < 32; ++j) dbg[256 + lane * 32 + j] = __uint_as_float(v[j]);
+                dbg[320] = (float)num_kb; dbg[321] = __uint_as_float(tmem_base);
+            }
+            if (row < Mdim) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int64_t col = n0 + c0 + j;
+                    if (col < Ndim) orow[col] = __uint_as_float(v[j]);
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D fp32 row-major tensor [rows][cols], box {32 cols, box_rows}, SWIZZLE_128B, OOB -> zeros.
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, bool mn_major) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (enc == nullptr) {
+        set_error("tc gemm: cuTensorMapEncodeTiled unavailable");
+        return 2;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) {
+        set_error("tc gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld", (int)rc, (long long)rows,
+                  (long long)cols);
+        return 2;
+    }
+    return 0;
+}
+
+static inline int pick_bn(int64_t n, int* ntiles) {
+    int64_t npad = ceil_div(n, 32) * 32;
+    int nt = (int)ceil_div(npad, 256);
+    int bn = (int)(ceil_div(ceil_div(npad, nt), 32) * 32);
+    *ntiles = (int)ceil_div(npad, bn);
+    return bn;
+}
+
+constexpr int kGramBK = 16, kGramStages = 4;
+constexpr int kRmulBK = 32, kRmulStages = 2;
+constexpr int64_t kGramSliceRows = 2048;
+
+static inline bool tc_shape_ok(int64_t m, int64_t r, int64_t r2) {
+    return m >= 2048 && r >= 64 && r2 >= 64 && (r % 4) == 0 && (r2 % 4) == 0 && r <= 65536 && r2 <= 65536;
+}
+
+template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, int64_t Mdim, int64_t Ndim, int64_t Kdim,
+                  int bn, int ntiles, int64_t k_per_slice, int64_t nslices, int64_t ld_out, int64_t slice_stride,
+                  cudaStream_t st, const char* name, float* dbg = nullptr) {
+    size_t smem = (size_t)STAGES * 2 * ((size_t)128 * BK * 4 + (size_t)bn * BK * 4) + (3 * STAGES + 2) * 8 + 1024;
+    auto kfn = tc_gemm3x_kernel<A_KMAJOR, B_KMAJOR, BK, STAGES>;
+    WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
+    dim3 grid((unsigned)ceil_div(Mdim, 128), (unsigned)ntiles, (unsigned)nslices);
+    kfn<<<grid, 256, smem, st>>>(tmA, tmB, out, Mdim, Ndim, Kdim, bn, k_per_slice, ld_out, slice_stride, dbg);
+    WISKI_CHECK_LAUNCH(name);
+    count_launches(1);
+    return 0;
+}
+
+template <typename T>
+__global__ void reduce_slices_kernel(const T* __restrict__ part, int64_t nparts, int64_t n, T* __restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    double s = 0.0;
+    for (int64_t p = 0; p < nparts; ++p) s += (double)part[p * n + e];
+    out[e] = (T)s;
+}
+
+int64_t tc_gram_work_elems(int64_t m, int64_t r, int64_t r2) {
+    if (!tc_shape_ok(m, r, r2)) return 0;
+    return ceil_div(m, kGramSliceRows) * r * r2;
+}
+
+float* g_tc_dbg = nullptr;   // debug dump buffer (device), set by the standalone test only
+
+int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
+                cudaStream_t st) {
+    if (!tc_shape_ok(m, r, r2)) return 3;
+    CUtensorMap tmA, tmB;
+    if (int rc = make_map(&tmA, A, m, r, kGramBK, true)) return rc;
+    if (int rc = make_map(&tmB, Bm, m, r2, kGramBK, true)) return rc;
+    int ntiles;
+    int bn = pick_bn(r2, &ntiles);
+    int64_t nslices = ceil_div(m, kGramSliceRows);
+    if (int rc = launch<false, false, kGramBK, kGramStages>(tmA, tmB, work, r, r2, m, bn, ntiles, kGramSliceRows, nslices, r2,
+                                                     r * r2, st, "tc_gram", g_tc_dbg))
+        return rc;
+    int64_t n = r * r2;
+    reduce_slices_kernel<float><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nslices, n, G);
+    WISKI_CHECK_LAUNCH("tc_gram(reduce)");
+    count_launches(1);
+    return 0;
+}
+
+int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st) {
+    if (!tc_shape_ok(m, r, r2)) return 3;
+    CUtensorMap tmA, tmB;
+    if (int rc = make_map(&tmA, P, m, r, 128, false)) return rc;   // K-major A: box {32 k, 128 rows}
+    if (int rc = make_map(&tmB, M, r, r2, kRmulBK, true)) return rc;   // MN-major B: box {32 cols, BK rows}
+    int ntiles;
+    int bn = pick_bn(r2, &ntiles);
+    return launch<true, false, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, r2, 0, st, "tc_panel_rmul");
+}
+
+// debug: Out = P @ Mt^T with Mt [r2 x r] row-major (both operands K-major)
+int tc_panel_rmul_nt_f32(const float* P, int64_t m, int64_t r, const float* Mt, int64_t r2, float* Out, cudaStream_t st) {
+    CUtensorMap tmA, tmB;
+    int ntiles;
+    int bn = pick_bn(r2, &ntiles);
+    if (int rc = make_map(&tmA, P, m, r, 128, false)) return rc;
+    if (int rc = make_map(&tmB, Mt, r2, r, bn, false)) return rc;
+    return launch<true, true, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, r2, 0, st, "tc_panel_rmul_nt", g_tc_dbg);
+}
+
 }  // namespace wiski

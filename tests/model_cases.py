@@ -201,6 +201,7 @@ CASES = [
     (4, 8, 60, 0, "rbf"),
     (1, 128, 25, 2048, "rbf"),
     (2, 40, 30, 0, "matern0.5"),
+    (3, 16, 100, 0, "rbf"),          # m = 4096, r = 112: large enough for the tcgen05 Gram / panel-rmul path in fp32
 ]
 
 
