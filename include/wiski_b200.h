@@ -85,6 +85,19 @@ int wiski_kron_toeplitz_bwd_cols_f32(const float* cols, int d, const int64_t* h_
 int wiski_kron_toeplitz_bwd_cols_f64(const double* cols, int d, const int64_t* h_g, int64_t gmax, const double* Z,
                                      const double* X, int64_t c, double* grad_cols, double* work, void* stream);
 
+/* Single-axis building blocks of the two entry points above, exported for the row-sharded multi-GPU path
+ * (each rank applies the local grid axes to its slab and the sharded axis in a column-sharded layout).
+ * View X as [outer, g, inner]: Y[o,a,w] = sum_b col[|a-b|] X[o,b,w];  X != Y.
+ * contract: acc64[k] += sum_{o,w} sum_{|a-b|=k} Z[o,a,w] P[o,b,w]   (acc64: g doubles, accumulated, caller zeroes). */
+int wiski_kron_axis_apply_f32(const float* X, float* Y, const float* col, int64_t g, int64_t outer, int64_t inner,
+                              void* stream);
+int wiski_kron_axis_apply_f64(const double* X, double* Y, const double* col, int64_t g, int64_t outer, int64_t inner,
+                              void* stream);
+int wiski_kron_axis_contract_f32(const float* Z, const float* P, int64_t g, int64_t outer, int64_t inner, double* acc64,
+                                 void* stream);
+int wiski_kron_axis_contract_f64(const double* Z, const double* P, int64_t g, int64_t outer, int64_t inner,
+                                 double* acc64, void* stream);
+
 /* ---- k7: panel right-multiply  Out = P @ M,  P,Out [m,r], M [r,r2], Out [m,r2]  (Out must not alias P)
  * (replaces current_root.matmul(inner_root) / current_inv_root^T.matmul(inner_inv_root),
  * updated_root_lazy_tensor.py:97-100,115-117, and Kuu_Lmat @ qmat_solve, batched_fixed_noise_online_gp.py:376). */

@@ -26,6 +26,8 @@ def _sigs(real, realp):
         "wiski_scatter_add": [_P, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, _S],
         "wiski_kron_toeplitz_mm": [_P, c_int, _I64P, c_int64, _P, c_int64, _P, _P, _S],
         "wiski_kron_toeplitz_bwd_cols": [_P, c_int, _I64P, c_int64, _P, _P, c_int64, _P, _P, _S],
+        "wiski_kron_axis_apply": [_P, _P, _P, c_int64, c_int64, c_int64, _S],
+        "wiski_kron_axis_contract": [_P, _P, c_int64, c_int64, c_int64, _P, _S],
         "wiski_panel_rmul": [_P, c_int64, c_int64, _P, c_int64, _P, _S],
         "wiski_panel_lowrank_update": [_P, c_int64, c_int64, _P, _P, c_int64, _S],
         "wiski_gram": [_P, _P, c_int64, c_int64, c_int64, _P, _P, _S],

@@ -369,6 +369,27 @@ static int kron_bwd_cols(const T* cols, int d, const int64_t* h_g, int64_t gmax,
 }  // namespace wiski
 
 extern "C" {
+// single-axis building blocks (used by the row-sharded multi-GPU path, online_gp_b200/parallel.py)
+int wiski_kron_axis_apply_f32(const float* X, float* Y, const float* col, int64_t g, int64_t outer, int64_t inner,
+                              void* stream) {
+    WISKI_CHECK_ARG(X != Y && g >= 1 && outer >= 0 && inner >= 1, "kron_axis_apply: bad arguments");
+    return wiski::launch_axis_apply<float>(X, Y, col, g, outer, inner, wiski::as_stream(stream));
+}
+int wiski_kron_axis_apply_f64(const double* X, double* Y, const double* col, int64_t g, int64_t outer, int64_t inner,
+                              void* stream) {
+    WISKI_CHECK_ARG(X != Y && g >= 1 && outer >= 0 && inner >= 1, "kron_axis_apply: bad arguments");
+    return wiski::launch_axis_apply<double>(X, Y, col, g, outer, inner, wiski::as_stream(stream));
+}
+int wiski_kron_axis_contract_f32(const float* Z, const float* P, int64_t g, int64_t outer, int64_t inner, double* acc64,
+                                 void* stream) {
+    WISKI_CHECK_ARG(g >= 1 && outer >= 0 && inner >= 1 && acc64 != nullptr, "kron_axis_contract: bad arguments");
+    return wiski::launch_axis_contract<float>(Z, P, g, outer, inner, acc64, wiski::as_stream(stream));
+}
+int wiski_kron_axis_contract_f64(const double* Z, const double* P, int64_t g, int64_t outer, int64_t inner,
+                                 double* acc64, void* stream) {
+    WISKI_CHECK_ARG(g >= 1 && outer >= 0 && inner >= 1 && acc64 != nullptr, "kron_axis_contract: bad arguments");
+    return wiski::launch_axis_contract<double>(Z, P, g, outer, inner, acc64, wiski::as_stream(stream));
+}
 int wiski_kron_toeplitz_mm_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, const float* X, int64_t c,
                                float* Y, float* work, void* stream) {
     return wiski::kron_mm<float>(cols, d, h_g, gmax, X, c, Y, work, stream);

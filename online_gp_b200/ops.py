@@ -254,6 +254,24 @@ def kron_toeplitz_matmul(cols, sizes, X):
     return _kron_mm(cols.detach().contiguous(), tuple(sizes), X.detach())
 
 
+def kron_axis_apply(X, col, g, outer, inner):
+    """One Kronecker axis: view X as [outer, g, inner]; Y[o,a,w] = sum_b col[|a-b|] X[o,b,w]. (no autograd)"""
+    _require_cuda(X, col)
+    X = X.contiguous()
+    Y = torch.empty_like(X)
+    _call("wiski_kron_axis_apply", X.dtype, _ptr(X), _ptr(Y), _ptr(col.contiguous()), int(g), int(outer), int(inner),
+          _stream())
+    return Y
+
+
+def kron_axis_contract(Z, P, g, outer, inner, acc64):
+    """acc64[k] += sum over lines of sum_{|a-b|=k} Z[o,a,w] P[o,b,w]  (acc64: float64 [g], accumulated in place)."""
+    _require_cuda(Z, P, acc64)
+    _call("wiski_kron_axis_contract", Z.dtype, _ptr(Z.contiguous()), _ptr(P.contiguous()), int(g), int(outer), int(inner),
+          _ptr(acc64), _stream())
+    return acc64
+
+
 # ---------------------------------------------------------------------------------------------- panels
 def _rmul(P, M):
     _require_cuda(P, M)

@@ -1,0 +1,348 @@
+"""Row-sharded multi-GPU WISKI: the inducing grid is partitioned across ranks along its slowest axis.
+
+One process per GPU (``torch.distributed``; NCCL over NVLink on B200, gloo in the CPU tests).  Rank ``g`` of ``G``
+owns the contiguous slab of rows ``[g m/G, (g+1) m/G)`` (``g_0 / G`` hyper-planes of grid axis 0) of the root panel
+``L``, the inverse-root panel ``B``, ``K L`` and ``interpolation_cache``.  Replicated on every rank: the
+hyper-parameters, the Toeplitz columns and every r x r object (``Q``, its Cholesky factor, the rank-q update
+factors), so the small dense algebra and its autograd run identically everywhere.
+
+Exchange steps per streaming step
+  * projection ``p = B^T v`` (r x q), ``c = L^T K b`` (r), predictive gathers: all-reduce of partial sums;
+  * ``Q - I = L^T (K L)``: all-reduce of the r x r Gram partials;
+  * ``K L``: grid axes 1..d-1 are slab-local; the axis-0 Toeplitz factor mixes slabs and is applied in a
+    *column-sharded* layout reached by one all-to-all each way (m r b / G bytes per rank each);
+  * hyper-gradient (column gradient of the Kronecker operator): the same exchange for the prefix chain and for the
+    axis-0 contraction, then one all-reduce of the d x g column gradient;
+  * ``K b`` for the m-vector ``b``: all-gather of b (m b bytes), replicated MVM.
+Every autograd Function below returns *complete* (replicated) gradients for replicated inputs, so hyper-parameter
+updates need no extra synchronisation.
+
+Mirrors, for one output and an Identity stem, ``OnlineSKIRegression.evaluate`` / ``.update``
+(``online_gp/models/online_ski_regression.py:64-78,113-146``) on top of the same kernels as the single-GPU path.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops, settings
+from .kernels import GridInterpolationKernel, RBFKernel, ScaleKernel
+from .lazy.updated_root_lazy_tensor import _sym_factors
+from .likelihoods import FNMGLikelihood
+
+
+# ---------------------------------------------------------------------------------------------- communication
+class Comm:
+    """Thin wrapper over a torch.distributed process group (None => single process, every collective a no-op)."""
+
+    def __init__(self, group=None):
+        self.enabled = dist.is_available() and dist.is_initialized()
+        self.group = group
+        self.world = dist.get_world_size(group) if self.enabled else 1
+        self.rank = dist.get_rank(group) if self.enabled else 0
+        self._a2a_ok = self.enabled and dist.get_backend(group) != "gloo"
+
+    def allreduce_(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def allgather(self, t):
+        """[world, *t.shape]"""
+        if self.world == 1:
+            return t.unsqueeze(0)
+        out = torch.empty(self.world, *t.shape, dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group) if self._a2a_ok else \
+            dist.all_gather(list(out.unbind(0)), t.contiguous(), group=self.group)
+        return out
+
+    def all_to_all(self, send):
+        """send [world, ...] (chunk j goes to rank j) -> recv [world, ...] (chunk i came from rank i)."""
+        if self.world == 1:
+            return send
+        send = send.contiguous()
+        if self._a2a_ok:
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(recv, send, group=self.group)
+            return recv
+        # gloo (CPU tests) has no all_to_all: emulate with an all-gather
+        return self.allgather(send)[:, self.rank].contiguous()
+
+
+class ShardPlan:
+    """Partition of the m = prod(sizes) grid rows along grid axis 0."""
+
+    def __init__(self, sizes, world, rank):
+        self.sizes = [int(s) for s in sizes]
+        self.world, self.rank = world, rank
+        if self.sizes[0] % world != 0:
+            raise ValueError(f"grid axis 0 ({self.sizes[0]} points) must be divisible by the number of ranks ({world})")
+        self.d = len(self.sizes)
+        self.m = 1
+        for s in self.sizes:
+            self.m *= s
+        self.g0_loc = self.sizes[0] // world
+        self.rest = self.m // self.sizes[0]
+        self.m_loc = self.g0_loc * self.rest
+        self.row0 = rank * self.m_loc
+
+    def localize(self, idx, val):
+        """Global stencils -> slab-local stencils (entries owned by other ranks get weight 0)."""
+        mask = (idx >= self.row0) & (idx < self.row0 + self.m_loc)
+        return torch.where(mask, idx - self.row0, torch.zeros_like(idx)), torch.where(mask, val, torch.zeros_like(val))
+
+    def local_axes(self, c):
+        """(axis, g, outer, inner) for the slab-local grid axes 1..d-1 of a [m_loc, c] panel."""
+        out = []
+        outer = self.g0_loc
+        for i in range(1, self.d):
+            inner = (self.m_loc // (outer * self.sizes[i])) * c
+            out.append((i, self.sizes[i], outer, inner))
+            outer *= self.sizes[i]
+        return out
+
+
+def _to_cols(X, plan, comm):
+    """[m_loc, c] row slab -> [g0 * rest, c / world] column block (all rows of my columns)."""
+    W = plan.world
+    if W == 1:
+        return X
+    m_loc, c = X.shape
+    send = X.view(m_loc, W, c // W).permute(1, 0, 2)
+    return comm.all_to_all(send).reshape(W * m_loc, c // W)
+
+
+def _to_rows(Xc, plan, comm):
+    """inverse of _to_cols."""
+    W = plan.world
+    if W == 1:
+        return Xc
+    cw = Xc.shape[1]
+    recv = comm.all_to_all(Xc.view(W, plan.m_loc, cw))
+    return recv.permute(1, 0, 2).reshape(plan.m_loc, W * cw)
+
+
+def _apply_local_axes(X, cols, plan):
+    for i, g, outer, inner in plan.local_axes(X.shape[1]):
+        X = ops.kron_axis_apply(X, cols[i], g, outer, inner)
+    return X
+
+
+class _ShardedKronFn(torch.autograd.Function):
+    """Y_loc = (K X)_loc for a row-sharded panel X (c divisible by world); complete gradient w.r.t. cols."""
+
+    @staticmethod
+    def forward(ctx, cols, X, plan, comm):
+        cols = cols.contiguous()
+        ctx.save_for_backward(cols, X)
+        ctx.plan, ctx.comm = plan, comm
+        Y = _apply_local_axes(X, cols, plan)
+        Yc = _to_cols(Y, plan, comm)
+        Yc = ops.kron_axis_apply(Yc, cols[0], plan.sizes[0], 1, Yc.numel() // plan.sizes[0])
+        return _to_rows(Yc, plan, comm)
+
+    @staticmethod
+    def backward(ctx, gY):
+        cols, X = ctx.saved_tensors
+        plan, comm = ctx.plan, ctx.comm
+        d, gmax = cols.shape
+        c = X.shape[1]
+        acc = torch.zeros(d, gmax, dtype=torch.float64, device=X.device)
+        axes = plan.local_axes(c)
+        # suffix chain on X: S_i = T_{i+1} .. T_{d-1} X  (all slab-local)
+        S = [None] * d
+        S[d - 1] = X
+        for (i, g, outer, inner) in reversed(axes):            # i = d-1 .. 1 -> S_{i-1} = T_i S_i
+            S[i - 1] = ops.kron_axis_apply(S[i], cols[i], g, outer, inner)
+        # axis 0 in the column-sharded layout: contraction, then the first step of the prefix chain on Z
+        Zc = _to_cols(gY.contiguous(), plan, comm)
+        S0c = _to_cols(S[0], plan, comm)
+        inner0 = Zc.numel() // plan.sizes[0]
+        ops.kron_axis_contract(Zc, S0c, plan.sizes[0], 1, inner0, acc[0])
+        Pz = _to_rows(ops.kron_axis_apply(Zc, cols[0], plan.sizes[0], 1, inner0), plan, comm) if d > 1 else None
+        for (i, g, outer, inner) in axes:
+            ops.kron_axis_contract(Pz, S[i], g, outer, inner, acc[i])
+            if i < d - 1:
+                Pz = ops.kron_axis_apply(Pz, cols[i], g, outer, inner)
+        comm.allreduce_(acc)
+        return acc.to(cols.dtype), None, None, None
+
+
+class _ShardedGramFn(torch.autograd.Function):
+    """A_loc^T B_loc summed over ranks (replicated result); gradient w.r.t. the sharded B_loc only."""
+
+    @staticmethod
+    def forward(ctx, A, B, comm):
+        ctx.save_for_backward(A)
+        return comm.allreduce_(ops.gram(A, B))
+
+    @staticmethod
+    def backward(ctx, gG):
+        (A,) = ctx.saved_tensors
+        return None, ops.panel_rmul(A, gG.contiguous()), None
+
+
+class _ShardSliceFn(torch.autograd.Function):
+    """Replicated full vector -> my slab; backward all-gathers the slab gradients so the replicated graph upstream
+    receives the complete gradient on every rank."""
+
+    @staticmethod
+    def forward(ctx, full, plan, comm):
+        ctx.plan, ctx.comm = plan, comm
+        return full[plan.row0:plan.row0 + plan.m_loc].contiguous()
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.comm.allgather(g.contiguous()).reshape(-1, g.shape[-1]), None, None
+
+
+# ---------------------------------------------------------------------------------------------- the sharded model
+class ShardedOnlineSKIRegression(torch.nn.Module):
+    """Row-sharded counterpart of ``OnlineSKIRegression`` (Identity stem, one output, learnable noise)."""
+
+    def __init__(self, init_x, init_y, lr, grid_size, grid_bound, comm=None, covar_module=None):
+        super().__init__()
+        self.comm = comm if comm is not None else Comm()
+        d = init_x.shape[-1]
+        assert init_y.ndim == 2 and init_y.shape[-1] == 1, "sharded path: one output"
+        grid_bound = grid_bound + 1e-1                                           # online_ski_regression.py:26
+        sizes = [grid_size] * d if isinstance(grid_size, int) else list(grid_size)
+        base = covar_module if covar_module is not None else ScaleKernel(RBFKernel(ard_num_dims=d))
+        self.covar_module = GridInterpolationKernel(base, grid_size=sizes, num_dims=d,
+                                                    grid_bounds=torch.tensor([[-grid_bound, grid_bound]] * d)).to(init_x.device)
+        self.likelihood = FNMGLikelihood(noise=torch.ones_like(init_y).t(), learn_additional_noise=True,
+                                         batch_shape=torch.Size([1])).to(init_x.device)
+        self.plan = ShardPlan(sizes, self.comm.world, self.comm.rank)
+        self.dtype = init_y.dtype
+        self.gp_optimizer = torch.optim.Adam(self.parameters(), lr=lr)
+        self._init_caches(init_x, init_y[:, 0], torch.ones_like(init_y[:, 0]))
+        self._pieces = None
+
+    # ---- state
+    def _stencils(self, x):
+        idx, val = self.covar_module._compute_grid(x)
+        return self.plan.localize(idx, val.detach())
+
+    def _init_caches(self, X, y, D):
+        plan, comm = self.plan, self.comm
+        idx, val = self._stencils(X)
+        n0 = X.shape[0]
+        self.response_cache = (y * y / D).sum()
+        self.D_logdet = D.log().sum()
+        self.num_data = n0
+        self.b_loc = ops.left_t_interp(idx, val, (y / D).unsqueeze(-1), plan.m_loc)
+        vval = val / D.clamp_min(1e-7).sqrt().unsqueeze(-1)
+        max_rank = settings.max_root_decomposition_size.value()
+        n1 = min(n0, max_rank)
+        eye = torch.eye(n1, dtype=self.dtype, device=X.device)
+        V1 = ops.left_t_interp(idx[:n1], vval[:n1], eye, plan.m_loc)
+        lam, U = torch.linalg.eigh(comm.allreduce_(ops.gram(V1, V1)))
+        tol = 1e-10 if self.dtype == torch.float64 else 1e-5
+        keep = lam > tol * lam.max()
+        lam, U = lam[keep].flip(0), U[:, keep].flip(1)
+        r_eff = lam.numel()
+        mult = 16 * comm.world // math.gcd(16, comm.world)
+        r = ((r_eff + mult - 1) // mult) * mult          # multiple of 16 and of the number of ranks
+        Upad = torch.zeros(n1, r, dtype=self.dtype, device=X.device)
+        Upad[:, :r_eff] = U
+        scale = torch.zeros(r, dtype=self.dtype, device=X.device)
+        scale[:r_eff] = 1.0 / lam
+        self.L_loc = ops.panel_rmul(V1, Upad)
+        self.B_loc = (self.L_loc * scale).contiguous()
+        for s0 in range(n1, n0, 32):
+            self._root_update(idx[s0:s0 + 32], vval[s0:s0 + 32])
+
+    def _root_update(self, idx_l, vval_l):
+        """collect_vector (updated_root_lazy_tensor.py:69-119), symmetric-square-root form, panels updated in place."""
+        for s0 in range(0, idx_l.shape[0], 32):
+            pT = self.comm.allreduce_(ops.left_interp(idx_l[s0:s0 + 32], vval_l[s0:s0 + 32], self.B_loc))
+            p = pT.t().contiguous()
+            C, Cp = _sym_factors(p)
+            ops.panel_lowrank_update_(self.L_loc, p, C @ p.t())
+            ops.panel_lowrank_update_(self.B_loc, p, Cp @ p.t())
+
+    # ---- pieces with grad (Kuu / sigma^2, K L, Q, K b, c)  — batched_fixed_noise_online_gp.py:334-366
+    def _noise(self):
+        return self.likelihood.second_noise_covar.noise.to(self.dtype).reshape(())
+
+    def _build_pieces(self):
+        plan, comm = self.plan, self.comm
+        cols = self.covar_module.base_kernel.grid_columns(self.covar_module.grid).to(self.dtype)
+        noise = self._noise()
+        scale = torch.cat([(1.0 / noise).reshape(1, 1), torch.ones(plan.d - 1, 1, dtype=self.dtype, device=cols.device)])
+        cols = cols * scale                                                       # Kuu / sigma^2 (:340)
+        KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm)                   # :348
+        r = self.L_loc.shape[1]
+        Q = _ShardedGramFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355
+        b_full = comm.allgather(self.b_loc).reshape(plan.m, 1)
+        Kb_full = ops.kron_toeplitz_matmul(cols, plan.sizes, b_full)              # :366
+        Kb = _ShardSliceFn.apply(Kb_full, plan, comm)
+        c = _ShardedGramFn.apply(self.L_loc, Kb, comm)                            # :360-361
+        Lq = torch.linalg.cholesky(Q)
+        self._pieces = dict(cols=cols, KL=KL, Q=Q, Lq=Lq, Kb_full=Kb_full, Kb=Kb, c=c, b_full=b_full, noise=noise)
+        return self._pieces
+
+    def pieces(self):
+        return self._pieces if self._pieces is not None else self._build_pieces()
+
+    # ---- evaluate / predict  (online_ski_regression.py:56-78)
+    def predict(self, x):
+        P = self.pieces()
+        plan, comm = self.plan, self.comm
+        with torch.no_grad():
+            idx, val = self.covar_module._compute_grid(x)
+            val = val.detach()
+            idx_l, val_l = plan.localize(idx, val)
+            a = torch.cholesky_solve(P["c"], P["Lq"])
+            mu_loc = P["Kb"] - ops.panel_rmul(P["KL"].detach(), a)                # :376
+            mean = comm.allreduce_(ops.left_interp(idx_l, val_l, mu_loc))         # :206-210
+            q = x.shape[0]
+            Wt = ops.left_t_interp(idx, val, torch.eye(q, dtype=self.dtype, device=x.device), plan.m)
+            c1 = ops.left_interp(idx, val, ops.kron_toeplitz_matmul(P["cols"].detach(), plan.sizes, Wt))
+            T = comm.allreduce_(ops.left_interp(idx_l, val_l, P["KL"].detach())).t()
+            cov = (c1 - T.t() @ torch.cholesky_solve(T, P["Lq"])) * P["noise"]    # :222-228
+            var = cov.diagonal().unsqueeze(-1) + P["noise"]                        # predict(): + second_noise
+        return mean, var
+
+    def evaluate(self, x, y):
+        mean, var = self.predict(x)
+        rmse = (mean - y).pow(2).mean().sqrt().item()
+        nll = -torch.distributions.Normal(mean, var.sqrt()).log_prob(y).mean().item()
+        return rmse, nll
+
+    # ---- Woodbury MLL (batched_woodbury_marginal_log_likelihood.py:19-52)
+    def mll(self):
+        P = self.pieces()
+        Lq = P["Lq"]
+        half = torch.linalg.solve_triangular(Lq, P["c"], upper=False)
+        inner_qform = (half * half).sum()
+        logdet = 2.0 * Lq.diagonal().log().sum()
+        if settings.skip_logdet_forward.on():
+            logdet = logdet - logdet.detach()
+        inducing_qform = (P["b_full"] * P["Kb_full"]).sum()
+        inv_quad = (self.response_cache - inducing_qform + inner_qform) / P["noise"]
+        n = self.num_data
+        final = n * math.log(2 * math.pi) + n * P["noise"].log()
+        return -0.5 * (inv_quad + logdet + self.D_logdet + final) / n
+
+    # ---- update (online_ski_regression.py:113-146)
+    def update(self, x, y):
+        self.gp_optimizer.zero_grad()
+        with settings.skip_logdet_forward(True):
+            loss = -self.mll()
+        loss.backward()
+        self.gp_optimizer.step()
+        self._pieces = None
+        gp_loss = loss.item()
+        with torch.no_grad():
+            self.condition_on_observations(x, y[:, 0], torch.ones_like(y[:, 0]))
+        return 0.0, gp_loss
+
+    def condition_on_observations(self, x, y, D):
+        idx_l, val_l = self._stencils(x)
+        self.response_cache = self.response_cache + (y * y / D).sum()
+        self.D_logdet = self.D_logdet + D.log().sum()
+        ops.scatter_add_(self.b_loc, idx_l, val_l, (y / D).unsqueeze(-1))
+        self._root_update(idx_l, val_l / D.clamp_min(1e-7).sqrt().unsqueeze(-1))
+        self.num_data += x.shape[0]
+        self._pieces = None

@@ -22,7 +22,7 @@ def install():
 
     saved = {k: getattr(ops, k) for k in ("_require_cuda", "_interp_fwd", "_gather", "_scatter_add", "_kron_mm",
                                           "_kron_bwd_cols", "_rmul", "_gram", "panel_lowrank_update_", "q_matvec",
-                                          "cg_solve")}
+                                          "cg_solve", "kron_axis_apply", "kron_axis_contract")}
     orig_init = ops.GridSpec.__init__
     orig_bwd = ops._InterpFn.backward
 
@@ -73,6 +73,19 @@ def install():
         Q = torch.eye(L.shape[1], dtype=L.dtype) + L.t() @ KL
         return torch.linalg.solve(Q, rhs), 1, 0.0
 
+    def axis_apply(X, col, g, outer, inner):
+        T = ogk.toeplitz_dense(col[:g])
+        return torch.einsum("ab,obw->oaw", T, X.reshape(outer, g, inner)).reshape(X.shape).contiguous()
+
+    def axis_contract(Z, P, g, outer, inner, acc64):
+        G = torch.einsum("oaw,obw->ab", Z.reshape(outer, g, inner).double(), P.reshape(outer, g, inner).double())
+        ar = torch.arange(g)
+        off = (ar.unsqueeze(0) - ar.unsqueeze(1)).abs()
+        acc64[:g] += torch.zeros(g, dtype=torch.float64).index_add_(0, off.reshape(-1), G.reshape(-1))
+        return acc64
+
+    ops.kron_axis_apply = axis_apply
+    ops.kron_axis_contract = axis_contract
     ops.GridSpec.__init__ = spec_init
     ops._InterpFn.backward = staticmethod(interp_bwd)
     ops._require_cuda = lambda *a: None

@@ -324,3 +324,32 @@ def test_sm_partial_mll_matches_oracle():
         vg.sum().backward()
     assert abs(vg.item() - vo.item()) <= 1e-6 * max(1.0, abs(vo.item()))
     assert torch.allclose(xg.grad.cpu(), xn.grad, rtol=1e-5, atol=1e-8)
+
+
+def test_sharded_world1_matches_single_device():
+    """The row-sharded model with one rank (all collectives no-ops) runs the exported single-axis kernels and must
+    reproduce OnlineSKIRegression on the same stream."""
+    M = _mods()
+    from online_gp_b200.parallel import Comm, ShardedOnlineSKIRegression
+    d, g, n0, steps = 3, 8, 40, 4
+    gen = torch.Generator().manual_seed(11)
+    X = torch.rand(n0 + steps, d, generator=gen) * 2 - 1
+    y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen)).unsqueeze(-1)
+    with warnings.catch_warnings(), M["S"].max_cholesky_size(0), M["S"].max_root_decomposition_size(64):
+        warnings.simplefilter("ignore")
+        with M["S"].max_cholesky_size(0):
+            reg = M["OnlineSKIRegression"](M["Identity"](d), X[:n0].to(_dev()), y[:n0].to(_dev()), lr=1e-2, grid_size=g,
+                                           grid_bound=1.0)
+            shd = ShardedOnlineSKIRegression(X[:n0].to(_dev()), y[:n0].to(_dev()), lr=1e-2, grid_size=g, grid_bound=1.0,
+                                             comm=Comm())
+        with M["S"].max_cholesky_size(2048):
+            for t in range(steps):
+                xt, yt = X[n0 + t:n0 + t + 1].to(_dev()), y[n0 + t:n0 + t + 1].to(_dev())
+                with M["S"].detach_interp_coeff(True):
+                    r1 = reg.evaluate(xt, yt)
+                r2 = shd.evaluate(xt, yt)
+                assert abs(r1[0] - r2[0]) <= 1e-7 * max(1, abs(r1[0])) and abs(r1[1] - r2[1]) <= 1e-7 * max(1, abs(r1[1]))
+                l1 = reg.update(xt, yt)[1]
+                l2 = shd.update(xt, yt)[1]
+                assert abs(l1 - l2) <= 1e-7 * max(1, abs(l1))
+                assert abs(float(reg.noise.mean()) - float(shd._noise())) <= 1e-9

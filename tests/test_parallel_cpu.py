@@ -1,0 +1,108 @@
+"""CPU, world_size 2, gloo: host-side logic of the row-sharded path (partition, exchanges, autograd completeness)
+against the unsharded oracle loop.  CUDA entry points are mocked by the oracle (tests/cpu_ops_mock.py); the sharded
+kernels themselves run in the -m gpu suite / bench.py --gpus N."""
+import os
+import sys
+import warnings
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, d, g, n0, steps, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_default_dtype(torch.float64)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cpu_ops_mock
+    from online_gp_b200 import settings as S
+    from online_gp_b200.parallel import Comm, ShardedOnlineSKIRegression
+    warnings.simplefilter("ignore")
+    gen = torch.Generator().manual_seed(7)
+    X = torch.rand(n0 + steps * 2, d, generator=gen) * 2 - 1
+    y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps * 2, generator=gen)).unsqueeze(-1)
+    out = []
+    with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64):
+        model = ShardedOnlineSKIRegression(X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0, comm=Comm())
+        for t in range(steps):
+            xt, yt = X[n0 + 2 * t:n0 + 2 * t + 2], y[n0 + 2 * t:n0 + 2 * t + 2]
+            rmse, nll = model.evaluate(xt, yt)
+            _, loss = model.update(xt, yt)
+            out.append((rmse, nll, loss, float(model._noise())))
+        ls = model.covar_module.base_kernel.base_kernel.lengthscale.detach().reshape(-1).tolist()
+    ret[rank] = (out, ls, model.L_loc.shape)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _oracle_loop(d, g, n0, steps):
+    from oracle.gridkernel import Hypers
+    from oracle.interp import create_grid
+    from oracle.wiski_matfree import WiskiMatFree
+    torch.set_default_dtype(torch.float64)
+    gen = torch.Generator().manual_seed(7)
+    X = torch.rand(n0 + steps * 2, d, generator=gen) * 2 - 1
+    y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps * 2, generator=gen)).unsqueeze(-1)
+    grid = create_grid([g] * d, [(-1.1, 1.1)] * d)
+    hyp = Hypers(d, learn_noise=True)
+    orc = WiskiMatFree(grid, hyp, X[:n0], y[:n0, 0], torch.ones(n0), max_cholesky_size=0, max_root=64, update_mode="svd")
+    opt = torch.optim.Adam(hyp.params(), lr=1e-2)
+    out = []
+    for t in range(steps):
+        xt, yt = X[n0 + 2 * t:n0 + 2 * t + 2], y[n0 + 2 * t:n0 + 2 * t + 2, 0]
+        with torch.no_grad():
+            mo, co = orc.predict(xt)
+            var = co.diagonal() + hyp.noise
+            rmse = float((mo - yt).pow(2).mean().sqrt())
+            nll = float(-torch.distributions.Normal(mo, var.sqrt()).log_prob(yt).mean())
+        opt.zero_grad()
+        mll = orc.mll()
+        (-mll).backward()
+        opt.step()
+        orc.condition_on_observations(xt, yt, torch.ones(2))
+        out.append((rmse, nll, float(hyp.noise)))
+    torch.set_default_dtype(torch.float32)
+    return out, hyp.lengthscale.detach().tolist()
+
+
+@pytest.mark.parametrize("d,g,n0", [(2, 8, 20), (3, 6, 30)])
+def test_sharded_stream_matches_unsharded_oracle(d, g, n0):
+    world, steps = 2, 3
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, d, g, n0, steps, ret), nprocs=world, join=True)
+    ref, ls_ref = _oracle_loop(d, g, n0, steps)
+    for rank in range(world):
+        out, ls, shape = ret[rank]
+        assert shape[0] == g ** d // world                      # each rank holds half of the grid rows
+        for (rmse, nll, loss, noise), (rmse_o, nll_o, noise_o) in zip(out, ref):
+            assert abs(rmse - rmse_o) <= 1e-6 * max(1.0, abs(rmse_o))
+            assert abs(nll - nll_o) <= 1e-6 * max(1.0, abs(nll_o))
+            assert abs(noise - noise_o) <= 1e-8                  # identical Adam trajectory => complete gradients
+        assert all(abs(a - b) <= 1e-8 for a, b in zip(ls, ls_ref))
+    assert ret[0][0] == ret[1][0]                               # replicas agree exactly
+
+
+def test_shard_plan_and_layout_roundtrip():
+    sys.path.insert(0, ROOT)
+    from online_gp_b200.parallel import Comm, ShardPlan, _to_cols, _to_rows
+    plan = ShardPlan([8, 4, 6], world=4, rank=2)
+    assert (plan.m, plan.m_loc, plan.row0, plan.g0_loc, plan.rest) == (192, 48, 96, 2, 24)
+    idx = torch.tensor([[0, 95, 96, 143, 144]])
+    il, vl = plan.localize(idx, torch.ones(1, 5))
+    assert il.tolist() == [[0, 0, 0, 47, 0]] and vl.tolist() == [[0, 0, 1, 1, 0]]
+    assert plan.local_axes(5) == [(1, 4, 2, 30), (2, 6, 8, 5)]
+    with pytest.raises(ValueError):
+        ShardPlan([6, 4], world=4, rank=0)
+    one = ShardPlan([4, 4], world=1, rank=0)
+    X = torch.randn(16, 3)
+    assert torch.equal(_to_rows(_to_cols(X, one, Comm()), one, Comm()), X)
