@@ -137,8 +137,8 @@ class WoodburyInnerCovar(LazyTensor):
 class PredictiveCovar(LazyTensor):
     """W* M W*^T * scale for q* test points (eval ``forward``, ``:222-228``): only q* x q* is ever formed."""
 
-    def __init__(self, idx, val, inner, scale=None):
-        self.idx, self.val, self.inner, self.scale = idx, val, inner, scale
+    def __init__(self, idx, val, inner, scale=None, T=None):
+        self.idx, self.val, self.inner, self.scale, self.T = idx, val, inner, scale, T
 
     def _size(self):
         q = self.idx.shape[0]
@@ -150,7 +150,10 @@ class PredictiveCovar(LazyTensor):
         eye = torch.eye(idx.shape[0], dtype=val.dtype, device=val.device)
         Wt = _scatter_dense(idx, val, eye, m) if val.requires_grad else ops.left_t_interp(idx, val, eye, m)
         c1 = ops.left_interp(idx, val, self.inner.Kuu._matmul(Wt))
-        T = ops.left_interp(idx, val, self.inner.KL).transpose(-1, -2)       # (K L)^T W*^T : r x q by row gather
+        if self.T is not None and sl == slice(None):
+            T = self.T
+        else:
+            T = ops.left_interp(idx, val, self.inner.KL).transpose(-1, -2)   # (K L)^T W*^T : r x q by row gather
         c2 = T.transpose(-1, -2) @ self.inner.qmatrix.inv_matmul(T)
         cov = c1 - c2
         return cov if self.scale is None else cov * self.scale
@@ -174,6 +177,32 @@ class PredictiveCovar(LazyTensor):
 
     dtype = property(lambda self: self.val.dtype)
     device = property(lambda self: self.val.device)
+
+
+class _PredictionCache(dict):
+    """``prediction_cache`` dict (``:368-383``) whose "pred_mean" entry — the m-vector K b - K L Q^-1 c — is only
+    materialised when somebody asks for it (one pass over the K L panel)."""
+
+    def __init__(self, Kuu_response, KLs, qmat_solve):
+        super().__init__()
+        dict.__setitem__(self, "KL", KLs)
+        dict.__setitem__(self, "qmat_solve", qmat_solve)
+        self._Kuu_response = Kuu_response
+
+    def has_pred_mean(self):
+        return dict.__contains__(self, "pred_mean")
+
+    def __getitem__(self, key):
+        if key == "pred_mean" and not dict.__contains__(self, key):
+            dict.__setitem__(self, key, self._Kuu_response - torch.stack(
+                [ops.panel_rmul(KL, s) for KL, s in zip(dict.__getitem__(self, "KL"), dict.__getitem__(self, "qmat_solve"))]))
+        return dict.__getitem__(self, key)
+
+    def __contains__(self, key):
+        return key == "pred_mean" or dict.__contains__(self, key)
+
+    def keys(self):
+        return list(dict.keys(self)) + ([] if self.has_pred_mean() else ["pred_mean"])
 
 
 class GP(nn.Module, _PriorMixin):
@@ -338,7 +367,18 @@ class FixedNoiseOnlineSKIGP(GP):
         idx2, val2 = idx.reshape(-1, idx.shape[-1]), val.reshape(-1, val.shape[-1])
         cache = self.prediction_cache
         t = self._num_models
-        pred_mean = torch.stack([ops.left_interp(idx2, val2, cache["pred_mean"][o]) for o in range(t)])   # :206-210
+        # W* (K b - K L Q^-1 c)  (:206-210).  For few test points the m-vector pred_mean is never materialised:
+        # W* K b - (W* K L) (Q^-1 c) only gathers the stencil rows of K L (shared with the covariance below).
+        gather_form = (not cache.has_pred_mean()) and idx2.numel() * 2 < self.covar_module.num_inducing
+        Ts = [None] * t
+        if gather_form:
+            means = []
+            for o in range(t):
+                Ts[o] = ops.left_interp(idx2, val2, cache["KL"][o]).transpose(-1, -2)          # r x q*
+                means.append(ops.left_interp(idx2, val2, self.Kuu_response[o]) - Ts[o].transpose(-1, -2) @ cache["qmat_solve"][o])
+            pred_mean = torch.stack(means)
+        else:
+            pred_mean = torch.stack([ops.left_interp(idx2, val2, cache["pred_mean"][o]) for o in range(t)])
         pred_mean = pred_mean.reshape(t, *xb, idx.shape[-2], 1)
 
         if skip_posterior_variances.off():
@@ -350,7 +390,7 @@ class FixedNoiseOnlineSKIGP(GP):
                 for o in range(t):
                     scale = self._second_noise(o) if self.has_learnable_noise else None                   # :227-228
                     if len(xb) == 0:
-                        covs.append(PredictiveCovar(idx2, val2, inner[o], scale))
+                        covs.append(PredictiveCovar(idx2, val2, inner[o], scale, T=Ts[o]))
                     else:
                         n = idx.shape[-2]
                         covs.append(BatchLazyTensor([PredictiveCovar(idx2[b * n:(b + 1) * n], val2[b * n:(b + 1) * n],
@@ -459,11 +499,9 @@ class FixedNoiseOnlineSKIGP(GP):
     @property
     @cached(name="prediction_cache")
     def prediction_cache(self):
-        prediction_cache = {}
         KLs = [kl.evaluate() for kl in self.current_inducing_compression_matrix.items]
         qmat_solve = self.current_qmatrix.inv_matmul(self.root_space_projection)
-        prediction_cache["pred_mean"] = self.Kuu_response - torch.stack(
-            [ops.panel_rmul(KL, s) for KL, s in zip(KLs, qmat_solve)])
+        prediction_cache = _PredictionCache(self.Kuu_response, KLs, qmat_solve)
         if skip_posterior_variances.off():
             prediction_cache["pred_cov"] = self._make_predictive_covar(self.current_qmatrix, self.Kuu, KLs)
         return prediction_cache

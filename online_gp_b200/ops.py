@@ -222,24 +222,62 @@ def _kron_bwd_cols(cols, sizes, Z, X):
     return g
 
 
+def _axis_geometry(sizes, c):
+    """[(g_i, outer_i, inner_i)] for a [prod(sizes), c] panel viewed as [outer, g_i, inner]."""
+    m = 1
+    for g in sizes:
+        m *= g
+    out, outer = [], 1
+    for g in sizes:
+        out.append((g, outer, (m // (outer * g)) * c))
+        outer *= g
+    return out
+
+
 class _KronFn(torch.autograd.Function):
+    """K X with the column gradient.  When cols needs grad the forward applies the axes in the order d-1, ..., 0 and
+    keeps the suffix products S_i = T_{i+1} .. T_{d-1} X, so the backward only runs the prefix chain on the incoming
+    gradient plus one contraction per axis (d-1 axis passes instead of 2(d-1))."""
+
     @staticmethod
     def forward(ctx, cols, X, sizes):
         cols = cols.contiguous()
-        ctx.save_for_backward(cols, X)
         ctx.sizes = sizes
-        return _kron_mm(cols, sizes, X)
+        if not ctx.needs_input_grad[0]:
+            ctx.save_for_backward(cols, X)
+            ctx.suffix = None
+            return _kron_mm(cols, sizes, X)
+        geo = _axis_geometry(sizes, X.shape[1])
+        S = [None] * len(sizes)
+        S[-1] = X.contiguous()
+        for i in range(len(sizes) - 1, 0, -1):
+            g, outer, inner = geo[i]
+            S[i - 1] = kron_axis_apply(S[i], cols[i], g, outer, inner)
+        g, outer, inner = geo[0]
+        Y = kron_axis_apply(S[0], cols[0], g, outer, inner)
+        ctx.save_for_backward(cols, *S)
+        ctx.suffix = True
+        return Y
 
     @staticmethod
     def backward(ctx, gY):
-        cols, X = ctx.saved_tensors
         gY = gY.contiguous()
-        gcols = gX = None
-        if ctx.needs_input_grad[0]:
-            gcols = _kron_bwd_cols(cols, ctx.sizes, gY, X)
-        if ctx.needs_input_grad[1]:
-            gX = _kron_mm(cols, ctx.sizes, gY)
-        return gcols, gX, None
+        if ctx.suffix is None:
+            cols, X = ctx.saved_tensors
+            return None, (_kron_mm(cols, ctx.sizes, gY) if ctx.needs_input_grad[1] else None), None
+        cols, *S = ctx.saved_tensors
+        sizes = ctx.sizes
+        d, gmax = cols.shape
+        geo = _axis_geometry(sizes, gY.shape[1])
+        acc = torch.zeros(d, gmax, dtype=torch.float64, device=gY.device)
+        Pz = gY
+        for i in range(d):
+            g, outer, inner = geo[i]
+            kron_axis_contract(Pz, S[i], g, outer, inner, acc[i])
+            if i < d - 1 or ctx.needs_input_grad[1]:
+                Pz = kron_axis_apply(Pz, cols[i], g, outer, inner)
+        gX = Pz if ctx.needs_input_grad[1] else None      # K symmetric: after all d axes Pz = K gY
+        return acc.to(cols.dtype), gX, None
 
 
 def kron_toeplitz_matmul(cols, sizes, X):
