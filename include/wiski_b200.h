@@ -98,6 +98,19 @@ int wiski_kron_axis_contract_f32(const float* Z, const float* P, int64_t g, int6
 int wiski_kron_axis_contract_f64(const double* Z, const double* P, int64_t g, int64_t outer, int64_t inner,
                                  double* acc64, void* stream);
 
+/* Fused fast path of k9 / k15 for grids whose axes all have 32 points (fp32, d even, c % 16 == 0; BASELINE config 2):
+ * two axes per pass, grid tiles staged in shared memory.  wiski_kron_toeplitz_mm_f32 dispatches to it by itself;
+ * the pair-level entry points let the autograd layer keep the intermediate panel of the forward pass.
+ *   pair p covers grid axes (2p, 2p+1);   pair_apply: Y = (T_2p x T_2p+1) X;
+ *   pair_grad: acc_u += contract_{2p}(Z, T_2p+1 P), acc_v += contract_{2p+1}(T_2p Z, P), Zout = T_2p+1 T_2p Z (or NULL).
+ * Not re-entrant across streams (coefficients live in __constant__ memory). */
+int wiski_kron_fused_supported(int d, const int64_t* h_g, int64_t c);
+int wiski_kron_fused_pair_apply_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X,
+                                    float* Y, int64_t c, void* stream);
+int wiski_kron_fused_pair_grad_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,
+                                   const float* P, float* Zout, int64_t c, double* acc_u64, double* acc_v64,
+                                   void* stream);
+
 /* ---- k7: panel right-multiply  Out = P @ M,  P,Out [m,r], M [r,r2], Out [m,r2]  (Out must not alias P)
  * (replaces current_root.matmul(inner_root) / current_inv_root^T.matmul(inner_inv_root),
  * updated_root_lazy_tensor.py:97-100,115-117, and Kuu_Lmat @ qmat_solve, batched_fixed_noise_online_gp.py:376). */

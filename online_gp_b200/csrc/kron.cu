@@ -16,6 +16,11 @@
 
 namespace wiski {
 
+// kron_fused.cu: two axes per pass for 32-point axes (fp32)
+bool fused_supported(int d, const int64_t* h_g, int64_t c);
+int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, const float* X, int64_t c, float* Y,
+                  float* work, cudaStream_t st);
+
 // ------------------------------------------------------------------ register kernels (g <= G, G in {8,16,32})
 template <typename T, int G>
 __global__ void __launch_bounds__(128) axis_apply_reg_kernel(const T* __restrict__ X, T* __restrict__ Y,
@@ -392,6 +397,9 @@ int wiski_kron_axis_contract_f64(const double* Z, const double* P, int64_t g, in
 }
 int wiski_kron_toeplitz_mm_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, const float* X, int64_t c,
                                float* Y, float* work, void* stream) {
+    if (d >= 1 && d <= WISKI_MAX_DIMS && wiski::fused_supported(d, h_g, c) && X != Y && work != nullptr && work != X &&
+        work != Y)
+        return wiski::fused_kron_mm(cols, d, h_g, gmax, X, c, Y, work, wiski::as_stream(stream));
     return wiski::kron_mm<float>(cols, d, h_g, gmax, X, c, Y, work, stream);
 }
 int wiski_kron_toeplitz_mm_f64(const double* cols, int d, const int64_t* h_g, int64_t gmax, const double* X,

@@ -1,0 +1,365 @@
+// k9 / k15 fast path: two Kronecker axes per pass over an m x c fp32 panel, for grids whose axes have 32 points
+// (BASELINE config 2: 32^4).  A CTA stages a [32 x 32 x 16-column] grid tile in shared memory (cp.async, padded so
+// that both axis orientations are bank-conflict free), applies both symmetric-Toeplitz factors there and streams
+// the result back, so K X costs d/2 panel passes instead of d and the column gradient 2.5 instead of 2d.
+//
+// Symmetric Toeplitz trick: T is centro-symmetric, so with s = x + Jx, a = x - Jx (J = reversal) the product splits
+// into two half-size products  (T x)[i] = (P s)[i] + (M a)[i],  (T x)[31-i] = (P s)[i] - (M a)[i],  i < 16, with
+// P[i][j] = (t|i-j| + t(31-i-j)) / 2, M[i][j] = (t|i-j| - t(31-i-j)) / 2: 512 FMA per line instead of 1024.
+// P and M live in __constant__ memory (filled on the stream from the device-resident Toeplitz columns), so every
+// FFMA takes its coefficient as a uniform constant-bank operand: no register or shared-memory traffic for them.
+//
+// Reference operations replaced: KroneckerProductLazyTensor._matmul / ToeplitzLazyTensor._matmul and their autograd
+//  reached from online_gp/models/batched_fixed_noise_online_gp.py:348.
+//
+// NOTE: the constant coefficient slots are process-global; calls must be issued on one stream at a time (the host
+// layer uses torch's current stream, like the reference's single default stream).
+#include "common.cuh"
+
+namespace wiski {
+
+constexpr int G = 32;          // grid points per fused axis
+constexpr int H = 16;          // half
+constexpr int CB = 16;         // panel columns per tile
+constexpr int UP = G * CB + 16;   // pitch (floats) of one u-group in shared memory: 32 rows of 16 + 16 pad
+constexpr int TILE_FLOATS = G * UP;   // 16896 floats = 67584 B
+
+__constant__ float c_coef[2][2][H][H];          // [slot][P|M][i][j]
+__device__ float g_coef_stage[2 * 2 * H * H];
+
+__global__ void prep_coef_kernel(const float* __restrict__ col0, const float* __restrict__ col1) {
+    int t = threadIdx.x;            // 256 threads: (i, j)
+    int i = t / H, j = t % H;
+    int d = i - j;
+    d = d < 0 ? -d : d;
+    const float* cols[2] = {col0, col1};
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        if (cols[s] == nullptr) continue;
+        float a = cols[s][d], b = cols[s][G - 1 - i - j];
+        g_coef_stage[((s * 2 + 0) * H + i) * H + j] = 0.5f * (a + b);
+        g_coef_stage[((s * 2 + 1) * H + i) * H + j] = 0.5f * (a - b);
+    }
+}
+
+static int set_coefficients(const float* col0, const float* col1, cudaStream_t st) {
+    prep_coef_kernel<<<1, 256, 0, st>>>(col0, col1);
+    void* stage = nullptr;
+    WISKI_CHECK_CUDA(cudaGetSymbolAddress(&stage, g_coef_stage), "kron_fused(symbol)");
+    WISKI_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_coef, stage, sizeof(float) * 2 * 2 * H * H, 0, cudaMemcpyDeviceToDevice, st),
+                     "kron_fused(coef)");
+    count_launches(1);
+    return 0;
+}
+
+// x <- T x for the symmetric Toeplitz factor in constant slot SLOT (in registers, fully unrolled)
+template <int SLOT>
+__device__ __forceinline__ void sym_apply32(float (&x)[G]) {
+    float s[H], a[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        s[j] = x[j] + x[G - 1 - j];
+        a[j] = x[j] - x[G - 1 - j];
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        float ys = 0.f, ya = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            ys = fmaf(c_coef[SLOT][0][i][j], s[j], ys);
+            ya = fmaf(c_coef[SLOT][1][i][j], a[j], ya);
+        }
+        x[i] = ys + ya;
+        x[G - 1 - i] = ys - ya;
+    }
+}
+
+// acc[k] += sum_{|a-b|=k} z[a] p[b]
+__device__ __forceinline__ void contract32(const float (&z)[G], const float (&p)[G], float (&acc)[G]) {
+#pragma unroll
+    for (int a = 0; a < G; ++a)
+#pragma unroll
+        for (int b = 0; b < G; ++b) {
+            int k = a - b;
+            k = k < 0 ? -k : k;
+            acc[k] = fmaf(z[a], p[b], acc[k]);
+        }
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Geometry of one axis pair (u slower, v faster; both of size 32):  row(u, v) = base + u*32*sv + v*sv,
+// base = ob * (1024 * sv) + oa,  ob in [0, n_before), oa in [0, sv).  Tile id -> (ob, oa, column chunk), chunk fastest.
+struct PairGeom {
+    int64_t sv;          // row stride of v (product of the grid sizes after the pair)
+    int64_t n_before;    // product of the grid sizes before the pair
+    int64_t c;           // panel columns
+    int64_t n_chunks;    // c / CB
+    int64_t n_tiles;     // n_before * sv * n_chunks
+};
+
+__device__ __forceinline__ void tile_coords(const PairGeom& g, int64_t tile, int64_t& rowbase, int64_t& col0) {
+    int64_t cc = tile % g.n_chunks;
+    int64_t o = tile / g.n_chunks;
+    int64_t oa = o % g.sv, ob = o / g.sv;
+    rowbase = ob * (1024 * g.sv) + oa;
+    col0 = cc * CB;
+}
+
+// stage one [32][32][16] tile: 4096 16-byte pieces
+template <int NT>
+__device__ __forceinline__ void load_tile_async(float* buf, const float* __restrict__ X, const PairGeom& g,
+                                                int64_t rowbase, int64_t col0) {
+#pragma unroll
+    for (int q = threadIdx.x; q < G * G * 4; q += NT) {
+        int part = q & 3, v = (q >> 2) & 31, u = q >> 7;
+        int64_t row = rowbase + ((int64_t)u * G + v) * g.sv;
+        cp_async16(buf + u * UP + v * CB + part * 4, X + row * g.c + col0 + part * 4);
+    }
+}
+
+// ------------------------------------------------------------------ Y = (T_u x T_v) X   (forward pair apply)
+// slot 0 = factor of axis u, slot 1 = factor of axis v.
+template <int NT>
+__global__ void __launch_bounds__(NT, 1) pair_apply_kernel(const float* __restrict__ X, float* __restrict__ Y, PairGeom g) {
+    extern __shared__ __align__(16) float smem[];
+    float* bufs[2] = {smem, smem + TILE_FLOATS};
+    int64_t tile = blockIdx.x;
+    int it = 0;
+    if (tile < g.n_tiles) {
+        int64_t rb, c0;
+        tile_coords(g, tile, rb, c0);
+        load_tile_async<NT>(bufs[0], X, g, rb, c0);
+    }
+    cp_async_commit();
+    for (; tile < g.n_tiles; tile += gridDim.x, ++it) {
+        float* buf = bufs[it & 1];
+        int64_t next = tile + gridDim.x;
+        if (next < g.n_tiles) {
+            int64_t rb, c0;
+            tile_coords(g, next, rb, c0);
+            load_tile_async<NT>(bufs[(it + 1) & 1], X, g, rb, c0);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        // phase 1: along v; line (u, w)
+        for (int l = threadIdx.x; l < G * CB; l += NT) {
+            int w = l & (CB - 1), u = l / CB;
+            float* p = buf + u * UP + w;
+            float x[G];
+#pragma unroll
+            for (int v = 0; v < G; ++v) x[v] = p[v * CB];
+            sym_apply32<1>(x);
+#pragma unroll
+            for (int v = 0; v < G; ++v) p[v * CB] = x[v];
+        }
+        __syncthreads();
+        // phase 2: along u; line (v, w); results go straight to global memory
+        int64_t rb, c0;
+        tile_coords(g, tile, rb, c0);
+        for (int l = threadIdx.x; l < G * CB; l += NT) {
+            int w = l & (CB - 1), v = l / CB;
+            const float* p = buf + v * CB + w;
+            float x[G];
+#pragma unroll
+            for (int u = 0; u < G; ++u) x[u] = p[u * UP];
+            sym_apply32<0>(x);
+            float* yp = Y + (rb + (int64_t)v * g.sv) * g.c + c0 + w;
+#pragma unroll
+            for (int u = 0; u < G; ++u) yp[(int64_t)u * G * g.sv * g.c] = x[u];
+        }
+        __syncthreads();   // buffer may be refilled by the prefetch of the next iteration
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------ backward pair kernel
+// Inputs: Z (incoming gradient side) and P (operand side), both m x c.  Per tile:
+//   acc_u += contract_u(Z, T_v P);   acc_v += contract_v(T_u Z, P);   if STORE: Zout = T_v T_u Z.
+template <bool STORE>
+__global__ void __launch_bounds__(256, 1)
+pair_grad_kernel(const float* __restrict__ Z, const float* __restrict__ P, float* __restrict__ Zout, PairGeom g,
+                 double* __restrict__ acc_u64, double* __restrict__ acc_v64) {
+    constexpr int NT = 256;
+    extern __shared__ __align__(16) float smem[];
+    float* zt = smem;
+    float* pt = smem + TILE_FLOATS;
+    float* st = smem + 2 * TILE_FLOATS;      // scratch: T_v P
+    float acc_u[G], acc_v[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) { acc_u[k] = 0.f; acc_v[k] = 0.f; }
+    for (int64_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        int64_t rb, c0;
+        tile_coords(g, tile, rb, c0);
+        load_tile_async<NT>(zt, Z, g, rb, c0);
+        load_tile_async<NT>(pt, P, g, rb, c0);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        // A: st = T_v P  (lines along v)
+        for (int l = threadIdx.x; l < G * CB; l += NT) {
+            int w = l & (CB - 1), u = l / CB;
+            float x[G];
+#pragma unroll
+            for (int v = 0; v < G; ++v) x[v] = pt[u * UP + v * CB + w];
+            sym_apply32<1>(x);
+#pragma unroll
+            for (int v = 0; v < G; ++v) st[u * UP + v * CB + w] = x[v];
+        }
+        __syncthreads();
+        // B: acc_u += contract_u(Z, st);  then Z <- T_u Z in place  (lines along u)
+        for (int l = threadIdx.x; l < G * CB; l += NT) {
+            int w = l & (CB - 1), v = l / CB;
+            float z[G], p[G];
+#pragma unroll
+            for (int u = 0; u < G; ++u) { z[u] = zt[u * UP + v * CB + w]; p[u] = st[u * UP + v * CB + w]; }
+            contract32(z, p, acc_u);
+            sym_apply32<0>(z);
+#pragma unroll
+            for (int u = 0; u < G; ++u) zt[u * UP + v * CB + w] = z[u];
+        }
+        __syncthreads();
+        // C: acc_v += contract_v(T_u Z, P);  STORE: Zout = T_v (T_u Z)   (lines along v)
+        for (int l = threadIdx.x; l < G * CB; l += NT) {
+            int w = l & (CB - 1), u = l / CB;
+            float z[G], p[G];
+#pragma unroll
+            for (int v = 0; v < G; ++v) { z[v] = zt[u * UP + v * CB + w]; p[v] = pt[u * UP + v * CB + w]; }
+            contract32(z, p, acc_v);
+            if (STORE) {
+                sym_apply32<1>(z);
+                float* yp = Zout + (rb + (int64_t)u * G * g.sv) * g.c + c0 + w;
+#pragma unroll
+                for (int v = 0; v < G; ++v) yp[(int64_t)v * g.sv * g.c] = z[v];
+            }
+        }
+        __syncthreads();
+    }
+    // block reduction of the two column-gradient accumulators -> double atomics
+    __shared__ float red[2][8][G];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        float a = warp_sum(acc_u[k]), b = warp_sum(acc_v[k]);
+        if (lane == 0) { red[0][warp][k] = a; red[1][warp][k] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * G) {
+        int which = threadIdx.x / G, k = threadIdx.x % G;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += (double)red[which][w][k];
+        atomicAdd(which == 0 ? &acc_u64[k] : &acc_v64[k], s);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static bool make_geom(PairGeom& g, int d, const int64_t* h_g, int pair, int64_t c) {
+    int u = 2 * pair, v = u + 1;
+    if (v >= d || h_g[u] != G || h_g[v] != G || c % CB != 0) return false;
+    g.sv = 1;
+    for (int j = v + 1; j < d; ++j) g.sv *= h_g[j];
+    g.n_before = 1;
+    for (int j = 0; j < u; ++j) g.n_before *= h_g[j];
+    g.c = c;
+    g.n_chunks = c / CB;
+    g.n_tiles = g.n_before * g.sv * g.n_chunks;
+    return true;
+}
+
+bool fused_supported(int d, const int64_t* h_g, int64_t c) {
+    if (d < 2 || (d % 2) != 0 || c % CB != 0 || c < CB) return false;
+    for (int i = 0; i < d; ++i)
+        if (h_g[i] != G) return false;
+    return true;
+}
+
+// Y = K X via d/2 fused pair passes (pairs applied last to first); `mid` receives the panel after every pair but the
+// last one when d == 4 it is exactly X23 = (T_2 x T_3) X, which the backward pass reuses.
+int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, const float* X, int64_t c, float* Y,
+                  float* work, cudaStream_t st) {
+    const int npairs = d / 2;
+    const float* src = X;
+    size_t smem = 2 * TILE_FLOATS * sizeof(float);
+    auto kfn = pair_apply_kernel<512>;
+    WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
+    for (int p = npairs - 1; p >= 0; --p) {
+        PairGeom g;
+        if (!make_geom(g, d, h_g, p, c)) { set_error("kron_fused: unsupported shape"); return 3; }
+        // passes remaining after this one: p ; the last pass (p == 0) must write Y
+        float* dst = (p % 2 == 0) ? Y : work;
+        if (int rc = set_coefficients(cols + (int64_t)(2 * p) * gmax, cols + (int64_t)(2 * p + 1) * gmax, st)) return rc;
+        int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
+        kfn<<<(unsigned)grid, 512, smem, st>>>(src, dst, g);
+        WISKI_CHECK_LAUNCH("kron_fused(pair_apply)");
+        count_launches(1);
+        src = dst;
+    }
+    return 0;
+}
+
+// One forward pair pass: Y = (T_{2 pair} x T_{2 pair + 1}) X.
+int fused_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X, float* Y,
+                     int64_t c, cudaStream_t st) {
+    PairGeom g;
+    if (!make_geom(g, d, h_g, pair, c)) { set_error("kron_fused: unsupported shape"); return 3; }
+    if (int rc = set_coefficients(cols + (int64_t)(2 * pair) * gmax, cols + (int64_t)(2 * pair + 1) * gmax, st)) return rc;
+    size_t smem = 2 * TILE_FLOATS * sizeof(float);
+    auto kfn = pair_apply_kernel<512>;
+    WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
+    int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
+    kfn<<<(unsigned)grid, 512, smem, st>>>(X, Y, g);
+    WISKI_CHECK_LAUNCH("kron_fused(pair_apply)");
+    count_launches(1);
+    return 0;
+}
+
+// One backward pair pass (see pair_grad_kernel).  acc_u64 / acc_v64: g doubles each, accumulated.
+int fused_pair_grad(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z, const float* P,
+                    float* Zout, int64_t c, double* acc_u64, double* acc_v64, cudaStream_t st) {
+    PairGeom g;
+    if (!make_geom(g, d, h_g, pair, c)) { set_error("kron_fused: unsupported shape"); return 3; }
+    if (int rc = set_coefficients(cols + (int64_t)(2 * pair) * gmax, cols + (int64_t)(2 * pair + 1) * gmax, st)) return rc;
+    size_t smem = 3 * TILE_FLOATS * sizeof(float);
+    int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
+    if (Zout != nullptr) {
+        auto kfn = pair_grad_kernel<true>;
+        WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
+        kfn<<<(unsigned)grid, 256, smem, st>>>(Z, P, Zout, g, acc_u64, acc_v64);
+    } else {
+        auto kfn = pair_grad_kernel<false>;
+        WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
+        kfn<<<(unsigned)grid, 256, smem, st>>>(Z, P, nullptr, g, acc_u64, acc_v64);
+    }
+    WISKI_CHECK_LAUNCH("kron_fused(pair_grad)");
+    count_launches(1);
+    return 0;
+}
+
+}  // namespace wiski
+
+extern "C" {
+/* Fused two-axes-per-pass Kronecker-Toeplitz MVM (fp32, every grid axis 32 points, d even, c % 16 == 0).
+ * Returns 3 when the shape is not supported (callers fall back to wiski_kron_toeplitz_mm_f32). */
+int wiski_kron_fused_supported(int d, const int64_t* h_g, int64_t c) { return wiski::fused_supported(d, h_g, c) ? 1 : 0; }
+
+int wiski_kron_fused_pair_apply_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X,
+                                    float* Y, int64_t c, void* stream) {
+    if (!wiski::fused_supported(d, h_g, c) || X == Y) { wiski::set_error("kron_fused_pair_apply: unsupported shape"); return 3; }
+    return wiski::fused_pair_apply(cols, d, h_g, gmax, pair, X, Y, c, wiski::as_stream(stream));
+}
+
+int wiski_kron_fused_pair_grad_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,
+                                   const float* P, float* Zout, int64_t c, double* acc_u64, double* acc_v64,
+                                   void* stream) {
+    if (!wiski::fused_supported(d, h_g, c)) { wiski::set_error("kron_fused_pair_grad: unsupported shape"); return 3; }
+    return wiski::fused_pair_grad(cols, d, h_g, gmax, pair, Z, P, Zout, c, acc_u64, acc_v64, wiski::as_stream(stream));
+}
+}

@@ -234,6 +234,33 @@ def _axis_geometry(sizes, c):
     return out
 
 
+def _fused_supported(sizes, X):
+    """Two-axes-per-pass fast path (kron_fused.cu): fp32, every grid axis 32 points, d even, c % 16 == 0."""
+    if X.dtype != torch.float32 or not X.is_cuda:
+        return False
+    h_g = (c_int64 * len(sizes))(*sizes)
+    return bool(_lib.load().wiski_kron_fused_supported(len(sizes), h_g, X.shape[1]))
+
+
+def _fused_pair_apply(cols, sizes, pair, X):
+    d, gmax = cols.shape
+    Y = torch.empty_like(X)
+    h_g = (c_int64 * d)(*sizes)
+    _lib.check(_lib.load().wiski_kron_fused_pair_apply_f32(_ptr(cols), d, h_g, gmax, pair, _ptr(X), _ptr(Y), X.shape[1],
+                                                           _stream()), "wiski_kron_fused_pair_apply")
+    return Y
+
+
+def _fused_pair_grad(cols, sizes, pair, Z, P, acc, store):
+    d, gmax = cols.shape
+    Zout = torch.empty_like(Z) if store else None
+    h_g = (c_int64 * d)(*sizes)
+    _lib.check(_lib.load().wiski_kron_fused_pair_grad_f32(_ptr(cols), d, h_g, gmax, pair, _ptr(Z), _ptr(P), _ptr(Zout),
+                                                          Z.shape[1], _ptr(acc[2 * pair]), _ptr(acc[2 * pair + 1]),
+                                                          _stream()), "wiski_kron_fused_pair_grad")
+    return Zout
+
+
 class _KronFn(torch.autograd.Function):
     """K X with the column gradient.  When cols needs grad the forward applies the axes in the order d-1, ..., 0 and
     keeps the suffix products S_i = T_{i+1} .. T_{d-1} X, so the backward only runs the prefix chain on the incoming
@@ -247,6 +274,17 @@ class _KronFn(torch.autograd.Function):
             ctx.save_for_backward(cols, X)
             ctx.suffix = None
             return _kron_mm(cols, sizes, X)
+        if _fused_supported(sizes, X):
+            # pairs applied last to first; M[p] = (pairs > p) applied to X is what the backward pair pass p needs
+            npairs = len(sizes) // 2
+            M = [None] * npairs
+            M[-1] = X.contiguous()
+            for p in range(npairs - 1, 0, -1):
+                M[p - 1] = _fused_pair_apply(cols, sizes, p, M[p])
+            Y = _fused_pair_apply(cols, sizes, 0, M[0])
+            ctx.save_for_backward(cols, *M)
+            ctx.suffix = "fused"
+            return Y
         geo = _axis_geometry(sizes, X.shape[1])
         S = [None] * len(sizes)
         S[-1] = X.contiguous()
@@ -268,8 +306,14 @@ class _KronFn(torch.autograd.Function):
         cols, *S = ctx.saved_tensors
         sizes = ctx.sizes
         d, gmax = cols.shape
-        geo = _axis_geometry(sizes, gY.shape[1])
         acc = torch.zeros(d, gmax, dtype=torch.float64, device=gY.device)
+        if ctx.suffix == "fused":
+            Zc = gY
+            npairs = d // 2
+            for p in range(npairs):
+                Zc = _fused_pair_grad(cols, sizes, p, Zc, S[p], acc, store=(p < npairs - 1 or ctx.needs_input_grad[1]))
+            return acc.to(cols.dtype), (Zc if ctx.needs_input_grad[1] else None), None
+        geo = _axis_geometry(sizes, gY.shape[1])
         Pz = gY
         for i in range(d):
             g, outer, inner = geo[i]

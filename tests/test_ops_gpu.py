@@ -97,7 +97,7 @@ def test_gather_scatter(dt, c):
     assert torch.allclose(out_t.cpu().double(), ref_t, **_tol(dt))
 
 
-KRON_CASES = [([128], 3), ([12, 9], 5), ([32, 32], 33), ([10, 10, 10], 7), ([8, 8, 8, 8], 16), ([5, 40, 6], 4),
+KRON_CASES = [([32, 32], 16), ([32, 32, 32, 32], 32), ([32, 32], 48), ([128], 3), ([12, 9], 5), ([32, 32], 33), ([10, 10, 10], 7), ([8, 8, 8, 8], 16), ([5, 40, 6], 4),
               ([300], 2), ([64, 16], 1), ([16, 16, 16, 16], 1)]
 
 
@@ -120,7 +120,7 @@ def test_kron_toeplitz_mm(dt, sizes, c):
 
 @pytest.mark.parametrize("dt", DT)
 @pytest.mark.parametrize("sizes,c", [([20], 3), ([12, 9], 5), ([6, 7, 5], 4), ([8, 8, 8, 8], 6), ([40, 6], 3),
-                                      ([32, 32], 17)])
+                                      ([32, 32], 17), ([32, 32], 32), ([32, 32, 32, 32], 16)])
 def test_kron_toeplitz_backward(dt, sizes, c):
     ops = _ops()
     d = len(sizes)
@@ -135,7 +135,7 @@ def test_kron_toeplitz_backward(dt, sizes, c):
     cg = _pad_cols(cols, dt).to(DEV).requires_grad_(True)
     Xg = X.to(dt).to(DEV).requires_grad_(True)
     (ops.kron_toeplitz_matmul(cg, sizes, Xg) * Z.to(dt).to(DEV)).sum().backward()
-    tol = dict(rtol=1e-9, atol=1e-9) if dt == torch.float64 else dict(rtol=1e-3, atol=1e-2)
+    tol = dict(rtol=1e-9, atol=1e-9) if dt == torch.float64 else dict(rtol=1e-3, atol=1e-2 * max(1.0, (m * c) ** 0.5 / 100))
     for i, g in enumerate(sizes):
         assert torch.allclose(cg.grad[i, :g].cpu().double(), cols_o[i].grad, **tol), f"grad col {i}"
         assert float(cg.grad[i, g:].abs().sum()) == 0.0
