@@ -167,7 +167,9 @@ def run_gpu(args):
         t += 1
     # ---- device-resident timing (value) with per-op events for the roofline
     prof_names = {"wiski_kron_toeplitz_mm", "wiski_kron_toeplitz_bwd_cols", "wiski_gram", "wiski_panel_rmul",
-                  "wiski_panel_lowrank_update", "wiski_gather", "wiski_scatter_add", "wiski_interp_fwd"}
+                  "wiski_panel_lowrank_update", "wiski_gather", "wiski_scatter_add", "wiski_interp_fwd",
+                  "wiski_kron_fused_pair_apply", "wiski_kron_fused_pair_grad", "wiski_kron_axis_apply",
+                  "wiski_kron_axis_contract"}
     ops.PROFILE = {"names": prof_names, "events": {}}
     clocks = ClockSampler(local_rank)
     launches0 = lib.wiski_launch_count()
@@ -207,6 +209,8 @@ def run_gpu(args):
     alg = {
         "wiski_kron_toeplitz_mm": ("hbm", 2.0 * m * r * b),                  # m x r panel, ideal single pass
         "wiski_kron_toeplitz_bwd_cols": ("hbm", 2.0 * m * r * b),            # read Z and X once
+        "wiski_kron_fused_pair_apply": ("hbm", 2.0 * m * r * b),             # read + write the panel (two axes per pass)
+        "wiski_kron_fused_pair_grad": ("hbm", 2.5 * m * r * b),              # read Z and P (+ write Z' on one of the two passes)
         "wiski_panel_lowrank_update": ("hbm", 2.0 * m * r * b),              # read + write the panel
         "wiski_gram": ("tensor", 2.0 * m * r * r),                           # flops
         "wiski_panel_rmul": ("tensor", 2.0 * m * r * r),

@@ -74,6 +74,35 @@ __device__ __forceinline__ void sym_apply32(float (&x)[G]) {
     }
 }
 
+// two lines at once: every coefficient fetched from the constant bank feeds two FFMAs
+template <int SLOT>
+__device__ __forceinline__ void sym_apply32x2(float (&x0)[G], float (&x1)[G]) {
+    float s0[H], a0[H], s1[H], a1[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        s0[j] = x0[j] + x0[G - 1 - j];
+        a0[j] = x0[j] - x0[G - 1 - j];
+        s1[j] = x1[j] + x1[G - 1 - j];
+        a1[j] = x1[j] - x1[G - 1 - j];
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        float ys0 = 0.f, ya0 = 0.f, ys1 = 0.f, ya1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const float cp = c_coef[SLOT][0][i][j], cm = c_coef[SLOT][1][i][j];
+            ys0 = fmaf(cp, s0[j], ys0);
+            ys1 = fmaf(cp, s1[j], ys1);
+            ya0 = fmaf(cm, a0[j], ya0);
+            ya1 = fmaf(cm, a1[j], ya1);
+        }
+        x0[i] = ys0 + ya0;
+        x0[G - 1 - i] = ys0 - ya0;
+        x1[i] = ys1 + ya1;
+        x1[G - 1 - i] = ys1 - ya1;
+    }
+}
+
 // acc[k] += sum_{|a-b|=k} z[a] p[b]
 __device__ __forceinline__ void contract32(const float (&z)[G], const float (&p)[G], float (&acc)[G]) {
 #pragma unroll
@@ -112,68 +141,87 @@ __device__ __forceinline__ void tile_coords(const PairGeom& g, int64_t tile, int
     col0 = cc * CB;
 }
 
-// stage one [32][32][16] tile: 4096 16-byte pieces
+// stage one [32][32][16] tile: 4096 16-byte pieces.  Thread t copies pieces t, t + NT, ...: piece q = (u, v, part)
+// with part = q & 3, v = (q >> 2) & 31, u = q >> 7, so consecutive pieces of a thread differ by NT/128 in u only and
+// both the global and the shared address advance by a constant stride (no per-piece index arithmetic).
 template <int NT>
 __device__ __forceinline__ void load_tile_async(float* buf, const float* __restrict__ X, const PairGeom& g,
                                                 int64_t rowbase, int64_t col0) {
+    static_assert(NT % 128 == 0, "NT must be a multiple of 128");
+    constexpr int USTEP = NT / 128;
+    const int q = threadIdx.x;
+    const int part = q & 3, v = (q >> 2) & 31, u0 = q >> 7;
+    const float* src = X + (rowbase + ((int64_t)u0 * G + v) * g.sv) * g.c + col0 + part * 4;
+    float* dst = buf + u0 * UP + v * CB + part * 4;
+    const int64_t sstride = (int64_t)USTEP * G * g.sv * g.c;
 #pragma unroll
-    for (int q = threadIdx.x; q < G * G * 4; q += NT) {
-        int part = q & 3, v = (q >> 2) & 31, u = q >> 7;
-        int64_t row = rowbase + ((int64_t)u * G + v) * g.sv;
-        cp_async16(buf + u * UP + v * CB + part * 4, X + row * g.c + col0 + part * 4);
+    for (int k = 0; k < G / USTEP; ++k) {
+        cp_async16(dst, src);
+        src += sstride;
+        dst += USTEP * UP;
     }
 }
 
 // ------------------------------------------------------------------ Y = (T_u x T_v) X   (forward pair apply)
 // slot 0 = factor of axis u, slot 1 = factor of axis v.
-template <int NT>
+template <int NT>   // NT must be 256 (two lines per thread and phase)
 __global__ void __launch_bounds__(NT, 1) pair_apply_kernel(const float* __restrict__ X, float* __restrict__ Y, PairGeom g) {
     extern __shared__ __align__(16) float smem[];
-    float* bufs[2] = {smem, smem + TILE_FLOATS};
     int64_t tile = blockIdx.x;
     int it = 0;
     if (tile < g.n_tiles) {
         int64_t rb, c0;
         tile_coords(g, tile, rb, c0);
-        load_tile_async<NT>(bufs[0], X, g, rb, c0);
+        load_tile_async<NT>(smem, X, g, rb, c0);
     }
     cp_async_commit();
+    const int64_t ustride = (int64_t)G * g.sv * g.c;      // elements between consecutive u rows in global memory
     for (; tile < g.n_tiles; tile += gridDim.x, ++it) {
-        float* buf = bufs[it & 1];
+        float* buf = smem + (it & 1) * TILE_FLOATS;       // derived from the __shared__ base so that LDS/STS are emitted
         int64_t next = tile + gridDim.x;
         if (next < g.n_tiles) {
             int64_t rb, c0;
             tile_coords(g, next, rb, c0);
-            load_tile_async<NT>(bufs[(it + 1) & 1], X, g, rb, c0);
+            load_tile_async<NT>(smem + ((it + 1) & 1) * TILE_FLOATS, X, g, rb, c0);
         }
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        // phase 1: along v; line (u, w)
-        for (int l = threadIdx.x; l < G * CB; l += NT) {
-            int w = l & (CB - 1), u = l / CB;
-            float* p = buf + u * UP + w;
-            float x[G];
+        // phase 1: along v; lines (u, w) and (u + 16, w) of this thread   [NT == 256: two lines per thread]
+        {
+            const int l = threadIdx.x;
+            const int w = l & (CB - 1), u = l / CB;
+            float* p0 = buf + u * UP + w;
+            float* p1 = p0 + (NT / CB) * UP;
+            float x0[G], x1[G];
 #pragma unroll
-            for (int v = 0; v < G; ++v) x[v] = p[v * CB];
-            sym_apply32<1>(x);
+            for (int v = 0; v < G; ++v) { x0[v] = p0[v * CB]; x1[v] = p1[v * CB]; }
+            sym_apply32x2<1>(x0, x1);
 #pragma unroll
-            for (int v = 0; v < G; ++v) p[v * CB] = x[v];
+            for (int v = 0; v < G; ++v) { p0[v * CB] = x0[v]; p1[v * CB] = x1[v]; }
         }
         __syncthreads();
-        // phase 2: along u; line (v, w); results go straight to global memory
-        int64_t rb, c0;
-        tile_coords(g, tile, rb, c0);
-        for (int l = threadIdx.x; l < G * CB; l += NT) {
-            int w = l & (CB - 1), v = l / CB;
-            const float* p = buf + v * CB + w;
-            float x[G];
+        // phase 2: along u; lines (v, w) and (v + 16, w); results go straight to global memory
+        {
+            int64_t rb, c0;
+            tile_coords(g, tile, rb, c0);
+            const int l = threadIdx.x;
+            const int w = l & (CB - 1), v = l / CB;
+            const float* p0 = buf + v * CB + w;
+            const float* p1 = p0 + (NT / CB) * CB;
+            float x0[G], x1[G];
 #pragma unroll
-            for (int u = 0; u < G; ++u) x[u] = p[u * UP];
-            sym_apply32<0>(x);
-            float* yp = Y + (rb + (int64_t)v * g.sv) * g.c + c0 + w;
+            for (int u = 0; u < G; ++u) { x0[u] = p0[u * UP]; x1[u] = p1[u * UP]; }
+            sym_apply32x2<0>(x0, x1);
+            float* yp0 = Y + (rb + (int64_t)v * g.sv) * g.c + c0 + w;
+            float* yp1 = yp0 + (int64_t)(NT / CB) * g.sv * g.c;
 #pragma unroll
-            for (int u = 0; u < G; ++u) yp[(int64_t)u * G * g.sv * g.c] = x[u];
+            for (int u = 0; u < G; ++u) {
+                *yp0 = x0[u];
+                *yp1 = x1[u];
+                yp0 += ustride;
+                yp1 += ustride;
+            }
         }
         __syncthreads();   // buffer may be refilled by the prefetch of the next iteration
     }
@@ -288,7 +336,7 @@ int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, co
     const int npairs = d / 2;
     const float* src = X;
     size_t smem = 2 * TILE_FLOATS * sizeof(float);
-    auto kfn = pair_apply_kernel<512>;
+    auto kfn = pair_apply_kernel<256>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
     for (int p = npairs - 1; p >= 0; --p) {
         PairGeom g;
@@ -297,7 +345,7 @@ int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, co
         float* dst = (p % 2 == 0) ? Y : work;
         if (int rc = set_coefficients(cols + (int64_t)(2 * p) * gmax, cols + (int64_t)(2 * p + 1) * gmax, st)) return rc;
         int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
-        kfn<<<(unsigned)grid, 512, smem, st>>>(src, dst, g);
+        kfn<<<(unsigned)grid, 256, smem, st>>>(src, dst, g);
         WISKI_CHECK_LAUNCH("kron_fused(pair_apply)");
         count_launches(1);
         src = dst;
@@ -312,10 +360,10 @@ int fused_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax,
     if (!make_geom(g, d, h_g, pair, c)) { set_error("kron_fused: unsupported shape"); return 3; }
     if (int rc = set_coefficients(cols + (int64_t)(2 * pair) * gmax, cols + (int64_t)(2 * pair + 1) * gmax, st)) return rc;
     size_t smem = 2 * TILE_FLOATS * sizeof(float);
-    auto kfn = pair_apply_kernel<512>;
+    auto kfn = pair_apply_kernel<256>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
     int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
-    kfn<<<(unsigned)grid, 512, smem, st>>>(X, Y, g);
+    kfn<<<(unsigned)grid, 256, smem, st>>>(X, Y, g);
     WISKI_CHECK_LAUNCH("kron_fused(pair_apply)");
     count_launches(1);
     return 0;

@@ -44,12 +44,16 @@ PROFILE = None
 
 def _call(name, dtype, *args):
     fn = getattr(_lib.load(), f"{name}_{_sfx(dtype)}")
+    _call_fn(name, fn, *args)
+
+
+def _call_fn(name, fn, *args):
     if PROFILE is not None and name in PROFILE["names"]:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _lib.check(fn(*args), name)
         e1.record()
-        PROFILE["events"].setdefault(name, []).append((e0, e1, args))
+        PROFILE["events"].setdefault(name, []).append((e0, e1, None))
         return
     _lib.check(fn(*args), name)
 
@@ -246,8 +250,8 @@ def _fused_pair_apply(cols, sizes, pair, X):
     d, gmax = cols.shape
     Y = torch.empty_like(X)
     h_g = (c_int64 * d)(*sizes)
-    _lib.check(_lib.load().wiski_kron_fused_pair_apply_f32(_ptr(cols), d, h_g, gmax, pair, _ptr(X), _ptr(Y), X.shape[1],
-                                                           _stream()), "wiski_kron_fused_pair_apply")
+    _call_fn("wiski_kron_fused_pair_apply", _lib.load().wiski_kron_fused_pair_apply_f32, _ptr(cols), d, h_g, gmax, pair,
+             _ptr(X), _ptr(Y), X.shape[1], _stream())
     return Y
 
 
@@ -255,9 +259,8 @@ def _fused_pair_grad(cols, sizes, pair, Z, P, acc, store):
     d, gmax = cols.shape
     Zout = torch.empty_like(Z) if store else None
     h_g = (c_int64 * d)(*sizes)
-    _lib.check(_lib.load().wiski_kron_fused_pair_grad_f32(_ptr(cols), d, h_g, gmax, pair, _ptr(Z), _ptr(P), _ptr(Zout),
-                                                          Z.shape[1], _ptr(acc[2 * pair]), _ptr(acc[2 * pair + 1]),
-                                                          _stream()), "wiski_kron_fused_pair_grad")
+    _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_fused_pair_grad_f32, _ptr(cols), d, h_g, gmax, pair,
+             _ptr(Z), _ptr(P), _ptr(Zout), Z.shape[1], _ptr(acc[2 * pair]), _ptr(acc[2 * pair + 1]), _stream())
     return Zout
 
 
