@@ -243,7 +243,9 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 s.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(b.y));
                 s.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(b.z));
                 s.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(b.w));
+#ifndef WISKI_TC_RAW_BIG
                 *big = b;
+#endif
                 *sml = s;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -400,14 +400,21 @@ int wiski_kron_fused_supported(int d, const int64_t* h_g, int64_t c) { return wi
 
 int wiski_kron_fused_pair_apply_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X,
                                     float* Y, int64_t c, void* stream) {
-    if (!wiski::fused_supported(d, h_g, c) || X == Y) { wiski::set_error("kron_fused_pair_apply: unsupported shape"); return 3; }
+    // only the two axes of the requested pair must have 32 points (a row-sharded slab has a shorter axis 0)
+    if (d < 2 || d > WISKI_MAX_DIMS || pair < 0 || 2 * pair + 1 >= d || X == Y) {
+        wiski::set_error("kron_fused_pair_apply: unsupported shape");
+        return 3;
+    }
     return wiski::fused_pair_apply(cols, d, h_g, gmax, pair, X, Y, c, wiski::as_stream(stream));
 }
 
 int wiski_kron_fused_pair_grad_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,
                                    const float* P, float* Zout, int64_t c, double* acc_u64, double* acc_v64,
                                    void* stream) {
-    if (!wiski::fused_supported(d, h_g, c)) { wiski::set_error("kron_fused_pair_grad: unsupported shape"); return 3; }
+    if (d < 2 || d > WISKI_MAX_DIMS || pair < 0 || 2 * pair + 1 >= d) {
+        wiski::set_error("kron_fused_pair_grad: unsupported shape");
+        return 3;
+    }
     return wiski::fused_pair_grad(cols, d, h_g, gmax, pair, Z, P, Zout, c, acc_u64, acc_v64, wiski::as_stream(stream));
 }
 }

@@ -128,14 +128,30 @@ def _apply_local_axes(X, cols, plan):
     return X
 
 
+def _fused_ok(plan, X):
+    """Fused two-axes-per-pass kernels usable: fp32 on CUDA, d = 4 with 32-point axes 1..3 and a 32-point axis 0,
+    and 16-column tiles both in the row-sharded (c) and the column-sharded (c / world) layout."""
+    return (X.is_cuda and X.dtype == torch.float32 and plan.d == 4 and all(s == 32 for s in plan.sizes)
+            and X.shape[1] % (16 * plan.world) == 0)
+
+
 class _ShardedKronFn(torch.autograd.Function):
     """Y_loc = (K X)_loc for a row-sharded panel X (c divisible by world); complete gradient w.r.t. cols."""
 
     @staticmethod
     def forward(ctx, cols, X, plan, comm):
         cols = cols.contiguous()
-        ctx.save_for_backward(cols, X)
         ctx.plan, ctx.comm = plan, comm
+        ctx.fused = _fused_ok(plan, X)
+        if ctx.fused:
+            # slab [g0/W, 32, 32, 32, c]: pair (2,3) is slab-local; pair (0,1) runs in the column-sharded layout
+            slab = [plan.g0_loc] + plan.sizes[1:]
+            X23 = ops._fused_pair_apply(cols, slab, 1, X.contiguous())
+            X23c = _to_cols(X23, plan, comm)
+            Yc = ops._fused_pair_apply(cols, plan.sizes, 0, X23c)
+            ctx.save_for_backward(cols, X, X23c)
+            return _to_rows(Yc, plan, comm)
+        ctx.save_for_backward(cols, X)
         Y = _apply_local_axes(X, cols, plan)
         Yc = _to_cols(Y, plan, comm)
         Yc = ops.kron_axis_apply(Yc, cols[0], plan.sizes[0], 1, Yc.numel() // plan.sizes[0])
@@ -143,8 +159,19 @@ class _ShardedKronFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gY):
-        cols, X = ctx.saved_tensors
         plan, comm = ctx.plan, ctx.comm
+        if ctx.fused:
+            cols, X, X23c = ctx.saved_tensors
+            d, gmax = cols.shape
+            acc = torch.zeros(d, gmax, dtype=torch.float64, device=X.device)
+            slab = [plan.g0_loc] + plan.sizes[1:]
+            Zc = _to_cols(gY.contiguous(), plan, comm)
+            Z01c = ops._fused_pair_grad(cols, plan.sizes, 0, Zc, X23c, acc, store=True)      # axes 0, 1 (+ Z01)
+            Z01 = _to_rows(Z01c, plan, comm)
+            ops._fused_pair_grad(cols, slab, 1, Z01, X, acc, store=False)                     # axes 2, 3
+            comm.allreduce_(acc)
+            return acc.to(cols.dtype), None, None, None
+        cols, X = ctx.saved_tensors
         d, gmax = cols.shape
         c = X.shape[1]
         acc = torch.zeros(d, gmax, dtype=torch.float64, device=X.device)
@@ -241,8 +268,9 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         keep = lam > tol * lam.max()
         lam, U = lam[keep].flip(0), U[:, keep].flip(1)
         r_eff = lam.numel()
-        mult = 16 * comm.world // math.gcd(16, comm.world)
-        r = ((r_eff + mult - 1) // mult) * mult          # multiple of 16 and of the number of ranks
+        # multiple of 16 x ranks: 16-column tiles must exist in the column-sharded layout of the fused kernels too
+        mult = 16 * comm.world
+        r = ((r_eff + mult - 1) // mult) * mult
         Upad = torch.zeros(n1, r, dtype=self.dtype, device=X.device)
         Upad[:, :r_eff] = U
         scale = torch.zeros(r, dtype=self.dtype, device=X.device)
