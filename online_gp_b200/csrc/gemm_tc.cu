@@ -119,7 +119,7 @@ __host__ __device__ inline uint32_t make_idesc(bool a_mn_major, bool b_mn_major,
 template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
 __global__ void __launch_bounds__(256, 1)
 tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ out,
-                 int64_t Mdim, int64_t Ndim, int64_t Kdim, int BN, int64_t k_per_slice, int64_t ld_out,
+                 int64_t Mdim, int64_t Ndim, int64_t Kdim, int BN, int n_tiles_n_arg, int64_t k_per_slice, int64_t ld_out,
                  int64_t slice_stride, float* __restrict__ dbg) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is at least 16-byte aligned -> realign.
@@ -135,8 +135,11 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t m0 = (int64_t)blockIdx.x * 128;
-    const int64_t n0 = (int64_t)blockIdx.y * BN;
+    // blockIdx.x enumerates (m-tile, n-tile) with the n-tile fastest: the CTAs that share an A tile are co-resident, so
+    // A is fetched from HBM once and served from L2 to the other n-tiles
+    const int n_tiles_n = n_tiles_n_arg;
+    const int64_t m0 = (int64_t)(blockIdx.x / n_tiles_n) * 128;
+    const int64_t n0 = (int64_t)(blockIdx.x % n_tiles_n) * BN;
     const int64_t k_begin = (int64_t)blockIdx.z * k_per_slice;
     int64_t k_end = k_begin + k_per_slice;
     if (k_end > Kdim) k_end = Kdim;
@@ -173,7 +176,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + B_BYTES));
                 const int k = (int)(k_begin + (int64_t)kb * BK);
                 if (A_KMAJOR) {
-                    tma_load_2d(sA, &tmA, &full_bar[stage], k, (int)m0);                 // box {32 k, 128 rows}
+                    tma_load_2d(sA, &tmA, &full_bar[stage], k, (int)m0);                 // box {BK k, 128 rows}
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)                                         // boxes {32 cols, BK rows}
@@ -205,14 +208,16 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int ks = 0; ks < BK / 8; ++ks) {
                     uint64_t dAb, dAs;
                     if (A_KMAJOR) {
-                        dAb = make_desc(aB + ks * 32, 0, 1024);
-                        dAs = make_desc(aS + ks * 32, 0, 1024);
+                        // K-major rows of BK floats: BK = 32 -> SWIZZLE_128B (8-row groups of 1024 B),
+                        //                            BK = 16 -> SWIZZLE_64B  (8-row groups of 512 B)
+                        dAb = make_desc(aB + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4);
+                        dAs = make_desc(aS + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4);
                     } else {
                         dAb = make_desc(aB + ks * 1024, BK * 128, 512, 1);
                         dAs = make_desc(aS + ks * 1024, BK * 128, 512, 1);
                     }
-                    const uint64_t dBb = B_KMAJOR ? make_desc(bB + ks * 32, 0, 1024) : make_desc(bB + ks * 1024, BK * 128, 512, 1);
-                    const uint64_t dBs = B_KMAJOR ? make_desc(bS + ks * 32, 0, 1024) : make_desc(bS + ks * 1024, BK * 128, 512, 1);
+                    const uint64_t dBb = B_KMAJOR ? make_desc(bB + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4) : make_desc(bB + ks * 1024, BK * 128, 512, 1);
+                    const uint64_t dBs = B_KMAJOR ? make_desc(bS + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4) : make_desc(bS + ks * 1024, BK * 128, 512, 1);
                     umma_tf32(tmem_base, dAs, dBb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
                     umma_tf32(tmem_base, dAb, dBs, idesc, 1u);
                     umma_tf32(tmem_base, dAb, dBb, idesc, 1u);
@@ -231,6 +236,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < num_kb; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+#pragma unroll 4
             for (int i = t; i < nvec; i += 128) {
                 // vectors [0, A_BYTES/16) belong to A (big at sA, small at sA + A_BYTES), the rest to B
                 const bool isA = i < A_BYTES / 16;
@@ -243,13 +249,13 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 s.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(b.y));
                 s.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(b.z));
                 s.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(b.w));
-#ifndef WISKI_TC_RAW_BIG
-                *big = b;
+#ifdef WISKI_TC_MASK_BIG
+                *big = b;      // not needed: kind::tf32 ignores the low 13 mantissa bits (measured: identical results)
 #endif
                 *sml = s;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (dbg != nullptr && kb == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+            if (dbg != nullptr && kb == 0 && blockIdx.x == 0 && blockIdx.z == 0) {
                 asm volatile("bar.sync 1, 128;" ::: "memory");
                 if (t < 64) {
                     dbg[t] = reinterpret_cast<float*>(sA)[t];
@@ -266,9 +272,13 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(tmem_full_bar, 0);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
+        // TMEM -> registers -> shared staging tile [128][BN + 4] -> coalesced 16-byte global stores.
+        // (Writing rows straight from registers would scatter every warp store over 32 rows.)  The operand ring is
+        // free at this point: every k-block has been loaded, split and consumed before tmem_full fires.
         const int wq = warp & 3;
-        const int64_t row = m0 + wq * 32 + lane;
-        float* orow = out + (int64_t)blockIdx.z * slice_stride + row * ld_out;
+        const int PITCH = BN + 4;                                  // words; 16-byte row stores hit distinct bank groups
+        float* stg = reinterpret_cast<float*>(smem);
+        const int lrow = wq * 32 + lane;
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t v[32];
             if (num_kb > 0) {
@@ -277,17 +287,23 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = 0u;
             }
-            if (dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && c0 == 0 && wq == 0 && lane < 2) {
+            if (dbg != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && c0 == 0 && wq == 0 && lane < 2) {
                 for (int j = 0; j < 32; ++j) dbg[256 + lane * 32 + j] = __uint_as_float(v[j]);
                 dbg[320] = (float)num_kb; dbg[321] = __uint_as_float(tmem_base);
             }
-            if (row < Mdim) {
+            uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)lrow * PITCH + c0);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int64_t col = n0 + c0 + j;
-                    if (col < Ndim) orow[col] = __uint_as_float(v[j]);
-                }
-            }
+            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
+        float* obase = out + (int64_t)blockIdx.z * slice_stride;
+        const int vec_per_row = BN / 4;
+        for (int i = t; i < 128 * vec_per_row; i += 128) {
+            const int rr = i / vec_per_row, c4 = i - rr * vec_per_row;
+            const int64_t row = m0 + rr, col = n0 + 4 * c4;
+            if (row < Mdim && col < Ndim)                       // Ndim % 4 == 0 (tc_shape_ok)
+                *reinterpret_cast<uint4*>(obase + row * ld_out + col) =
+                    *reinterpret_cast<const uint4*>(stg + (size_t)rr * PITCH + 4 * c4);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -313,7 +329,8 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // 2-D fp32 row-major tensor [rows][cols], box {32 cols, box_rows}, SWIZZLE_128B, OOB -> zeros.
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, bool mn_major) {
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int box_rows, bool mn_major,
+                    int box_cols = 32) {
     EncodeTiledFn enc = get_encode_fn();
     if (enc == nullptr) {
         set_error("tc gemm: cuTensorMapEncodeTiled unavailable");
@@ -321,11 +338,12 @@ static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t c
     }
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)cols * 4};
-    cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1u, 1u};
     CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                      mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                               : (box_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B),
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
@@ -345,7 +363,7 @@ static inline int pick_bn(int64_t n, int* ntiles) {
 }
 
 constexpr int kGramBK = 16, kGramStages = 4;
-constexpr int kRmulBK = 32, kRmulStages = 2;
+constexpr int kRmulBK = 16, kRmulStages = 4;
 constexpr int64_t kGramSliceRows = 2048;
 
 static inline bool tc_shape_ok(int64_t m, int64_t r, int64_t r2) {
@@ -359,8 +377,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, in
     size_t smem = (size_t)STAGES * 2 * ((size_t)128 * BK * 4 + (size_t)bn * BK * 4) + (3 * STAGES + 2) * 8 + 1024;
     auto kfn = tc_gemm3x_kernel<A_KMAJOR, B_KMAJOR, BK, STAGES>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
-    dim3 grid((unsigned)ceil_div(Mdim, 128), (unsigned)ntiles, (unsigned)nslices);
-    kfn<<<grid, 256, smem, st>>>(tmA, tmB, out, Mdim, Ndim, Kdim, bn, k_per_slice, ld_out, slice_stride, dbg);
+    // x = (m-tile, n-tile) flattened with the n-tile fastest
+    dim3 grid((unsigned)(ceil_div(Mdim, 128) * ntiles), 1, (unsigned)nslices);
+    kfn<<<grid, 256, smem, st>>>(tmA, tmB, out, Mdim, Ndim, Kdim, bn, ntiles, k_per_slice, ld_out, slice_stride, dbg);
     WISKI_CHECK_LAUNCH(name);
     count_launches(1);
     return 0;
@@ -404,7 +423,7 @@ int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r
 int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st) {
     if (!tc_shape_ok(m, r, r2)) return 3;
     CUtensorMap tmA, tmB;
-    if (int rc = make_map(&tmA, P, m, r, 128, false)) return rc;   // K-major A: box {32 k, 128 rows}
+    if (int rc = make_map(&tmA, P, m, r, 128, false, kRmulBK)) return rc;   // K-major A: box {BK k, 128 rows}
     if (int rc = make_map(&tmB, M, r, r2, kRmulBK, true)) return rc;   // MN-major B: box {32 cols, BK rows}
     int ntiles;
     int bn = pick_bn(r2, &ntiles);
@@ -416,8 +435,8 @@ int tc_panel_rmul_nt_f32(const float* P, int64_t m, int64_t r, const float* Mt, 
     CUtensorMap tmA, tmB;
     int ntiles;
     int bn = pick_bn(r2, &ntiles);
-    if (int rc = make_map(&tmA, P, m, r, 128, false)) return rc;
-    if (int rc = make_map(&tmB, Mt, r2, r, bn, false)) return rc;
+    if (int rc = make_map(&tmA, P, m, r, 128, false, kRmulBK)) return rc;
+    if (int rc = make_map(&tmB, Mt, r2, r, bn, false, kRmulBK)) return rc;
     return launch<true, true, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, r2, 0, st, "tc_panel_rmul_nt", g_tc_dbg);
 }
 
