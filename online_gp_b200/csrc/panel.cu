@@ -74,20 +74,32 @@ __global__ void rmul_skinny_kernel(const T* __restrict__ P, const T* __restrict_
     int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp; i < M; i += nwarps) {
-        T acc[NP];
+    for (int64_t i = warp; i < M; i += 2 * nwarps) {
+        const int64_t i2 = i + nwarps;
+        const bool has2 = i2 < M;
+        T acc[NP], acc2[NP];
 #pragma unroll
-        for (int t = 0; t < NP; ++t) acc[t] = T(0);
+        for (int t = 0; t < NP; ++t) { acc[t] = T(0); acc2[t] = T(0); }
+#pragma unroll 4
         for (int64_t j = lane; j < K; j += 32) {
             T x = P[i * K + j];
+            T x2 = has2 ? P[i2 * K + j] : T(0);
 #pragma unroll
             for (int t = 0; t < NP; ++t)
-                if (t < N) acc[t] += x * Mm[j * N + t];
+                if (t < N) {
+                    T mv = Mm[j * N + t];
+                    acc[t] += x * mv;
+                    acc2[t] += x2 * mv;
+                }
         }
 #pragma unroll
         for (int t = 0; t < NP; ++t) {
             T v = warp_sum(acc[t]);
-            if (lane == 0 && t < N) Out[i * N + t] = v;
+            T v2 = warp_sum(acc2[t]);
+            if (lane == 0 && t < N) {
+                Out[i * N + t] = v;
+                if (has2) Out[i2 * N + t] = v2;
+            }
         }
     }
 }
@@ -199,6 +211,58 @@ __global__ void gram_skinny_kernel(const T* __restrict__ A, const T* __restrict_
 #pragma unroll
         for (int t = 0; t < NP; ++t)
             if (t < r2) part[((int64_t)blockIdx.x * r + j) * r2 + t] = acc[t];
+    }
+}
+
+// r2 small, r <= 32*RJ: warp per row, lanes strided over the r columns, per-lane register accumulators; rows are
+// streamed fully coalesced (this is the L^T u half of the fused Q-MVM).  part: [gridDim.x][r][r2].
+template <typename T, int RJ, int NP>
+__global__ void __launch_bounds__(256) gram_skinny_warp_kernel(const T* __restrict__ A, const T* __restrict__ Bm,
+                                                               int64_t m, int64_t r, int r2, T* __restrict__ part) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* red = reinterpret_cast<T*>(smem_raw);   // [8][r*r2]
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T acc[RJ][NP];
+#pragma unroll
+    for (int jj = 0; jj < RJ; ++jj)
+#pragma unroll
+        for (int t = 0; t < NP; ++t) acc[jj][t] = T(0);
+    int64_t gw = (int64_t)blockIdx.x * 8 + warp, nw = (int64_t)gridDim.x * 8;
+    for (int64_t i = gw; i < m; i += 2 * nw) {
+        const int64_t i2 = i + nw;
+        const bool has2 = i2 < m;
+        T a0[RJ], a1[RJ];
+#pragma unroll
+        for (int jj = 0; jj < RJ; ++jj) {
+            int64_t j = lane + 32 * jj;
+            a0[jj] = (j < r) ? A[i * r + j] : T(0);
+            a1[jj] = (has2 && j < r) ? A[i2 * r + j] : T(0);
+        }
+        T b0[NP], b1[NP];
+#pragma unroll
+        for (int t = 0; t < NP; ++t) {
+            b0[t] = (t < r2) ? Bm[i * r2 + t] : T(0);
+            b1[t] = (has2 && t < r2) ? Bm[i2 * r2 + t] : T(0);
+        }
+#pragma unroll
+        for (int jj = 0; jj < RJ; ++jj)
+#pragma unroll
+            for (int t = 0; t < NP; ++t) acc[jj][t] += a0[jj] * b0[t] + a1[jj] * b1[t];
+    }
+    int64_t rc = r * r2;
+#pragma unroll
+    for (int jj = 0; jj < RJ; ++jj) {
+        int64_t j = lane + 32 * jj;
+#pragma unroll
+        for (int t = 0; t < NP; ++t)
+            if (j < r && t < r2) red[warp * rc + j * r2 + t] = acc[jj][t];
+    }
+    __syncthreads();
+    for (int64_t e = threadIdx.x; e < rc; e += blockDim.x) {
+        T sum = T(0);
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w * rc + e];
+        part[(int64_t)blockIdx.x * rc + e] = sum;
     }
 }
 
@@ -410,7 +474,31 @@ static int gram(const T* A, const T* Bm, int64_t m, int64_t r, int64_t r2, T* G,
     WISKI_CHECK_ARG(m >= 1 && r >= 1 && r2 >= 1 && work != nullptr, "gram: bad arguments");
     cudaStream_t st = as_stream(stream);
     int64_t n = r * r2;
-    if (r2 <= 4) {
+    if (r2 <= 2 && r <= 1024 && (size_t)8 * r * r2 * sizeof(T) <= 96 * 1024) {
+        int64_t nb = gram_skinny_blocks(m);
+        size_t smem = (size_t)8 * r * r2 * sizeof(T);
+        int rj = (int)ceil_div(r, 32);
+#define GSW(RJ, NP)                                                                                            \
+    do {                                                                                                       \
+        auto kfn = gram_skinny_warp_kernel<T, RJ, NP>;                                                         \
+        if (smem > 48 * 1024)                                                                                  \
+            WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
+                             "gram(attr)");                                                                    \
+        kfn<<<(unsigned)nb, 256, smem, st>>>(A, Bm, m, r, (int)r2, work);                                      \
+    } while (0)
+#define GSW_NP(RJ)                  \
+    do {                            \
+        if (r2 == 1) GSW(RJ, 1);    \
+        else GSW(RJ, 2);            \
+    } while (0)
+        if (rj <= 4) GSW_NP(4);
+        else if (rj <= 8) GSW_NP(8);
+        else if (rj <= 16) GSW_NP(16);
+        else GSW_NP(32);
+#undef GSW_NP
+#undef GSW
+        reduce_parts_kernel<T><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nb, n, (const T*)nullptr, G);
+    } else if (r2 <= 4) {
         int64_t nb = gram_skinny_blocks(m);
         int64_t rpb = ceil_div(m, nb);
         nb = ceil_div(m, rpb);
