@@ -145,6 +145,7 @@ def run_gpu(args):
 
     model, xs, ys = build_model(d, g, n_init, dtype, device)
     m = g ** d
+    model.gp._kernel_cache["WtW"].root_decomposition()      # Cholesky regime: the root is built lazily
     r = model.gp._kernel_cache["WtW"].root.shape[-1]
     ctx = (S.max_root_decomposition_size(MAX_ROOT), S.max_cholesky_size(MAX_CHOL), S.cg_tolerance(CG_TOL))
     for c in ctx:

@@ -112,38 +112,37 @@ __host__ __device__ inline uint32_t make_idesc(bool a_mn_major, bool b_mn_major,
 }
 
 // ------------------------------------------------------------------------------------------------ kernel
-// D[128 x BN] (+)= sum_k opA[k][m] * opB[k][n] over this CTA's K slice.
+// Persistent: each CTA walks work items  w = blockIdx.x, blockIdx.x + gridDim.x, ...  with
+//   w -> (K slice z, m-tile, n-tile), n-tile fastest (CTAs that share an A tile / a K slice run together and share
+//   operands through L2: ncu shows DRAM reads == one pass over each operand).
+// D[128 x BN] = sum_k opA[k][m] * opB[k][n] over the K slice.
 //   A_KMAJOR = false: A global [Kdim rows][Mdim cols] (MN-major; Gram).   true: A global [Mdim rows][Kdim cols] (rmul).
-//   B global [Kdim rows][Ndim cols] (MN-major) in both modes.
+//   B_KMAJOR likewise for B ([Kdim][Ndim] MN-major, or [Ndim][Kdim] K-major).
 // out: slice z writes out + z * slice_stride, row-major with leading dimension ld_out.
+// Warp roles (384 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 4-7 epilogue | 8-11 operand split.
+// Two TMEM accumulators (2 x BN <= 512 columns) let the MMAs of tile i+1 overlap the epilogue of tile i.
 template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ out,
-                 int64_t Mdim, int64_t Ndim, int64_t Kdim, int BN, int n_tiles_n_arg, int64_t k_per_slice, int64_t ld_out,
-                 int64_t slice_stride, float* __restrict__ dbg) {
+                 int64_t Mdim, int64_t Ndim, int64_t Kdim, int BN, int n_tiles_n, int n_tiles_m, int64_t n_work,
+                 int64_t k_per_slice, int64_t ld_out, int64_t slice_stride) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // 1024-byte alignment is required by SWIZZLE_128B; dynamic smem base is at least 16-byte aligned -> realign.
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int A_BYTES = 128 * BK * 4;
     const int B_BYTES = BN * BK * 4;
     const int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+    constexpr int STG_PITCH = 36;                               // words per staged row (32 + 4: conflict-free 16 B rows)
+    float* staging = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);        // [4 warps][32][36]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + 4 * 32 * STG_PITCH * 4);
     uint64_t* full_bar = bars;                  // [STAGES] TMA landed
     uint64_t* ready_bar = bars + STAGES;        // [STAGES] operands split
     uint64_t* empty_bar = bars + 2 * STAGES;    // [STAGES] MMAs retired
-    uint64_t* tmem_full_bar = bars + 3 * STAGES;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+    uint64_t* tmem_full_bar = bars + 3 * STAGES;       // [2]
+    uint64_t* tmem_empty_bar = bars + 3 * STAGES + 2;  // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // blockIdx.x enumerates (m-tile, n-tile) with the n-tile fastest: the CTAs that share an A tile are co-resident, so
-    // A is fetched from HBM once and served from L2 to the other n-tiles
-    const int n_tiles_n = n_tiles_n_arg;
-    const int64_t m0 = (int64_t)(blockIdx.x / n_tiles_n) * 128;
-    const int64_t n0 = (int64_t)(blockIdx.x % n_tiles_n) * BN;
-    const int64_t k_begin = (int64_t)blockIdx.z * k_per_slice;
-    int64_t k_end = k_begin + k_per_slice;
-    if (k_end > Kdim) k_end = Kdim;
-    const int num_kb = (int)((k_end - k_begin + BK - 1) / BK);
+    const int64_t tiles_per_slice = (int64_t)n_tiles_n * n_tiles_m;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -151,44 +150,64 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(&ready_bar[s], 128);
             mbar_init(&empty_bar[s], 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tmem_full_bar[a], 1);
+            mbar_init(&tmem_empty_bar[a], 4);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     }
-    if (warp == 2) tmem_alloc(tmem_ptr, 256);
+    if (warp == 2) tmem_alloc(tmem_ptr, 512);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_ptr;
+
+    // work item -> (m0, n0, k range)
+    auto decode = [&](int64_t w, int64_t& m0, int64_t& n0, int64_t& kb0, int& nkb, int64_t& z) {
+        z = w / tiles_per_slice;
+        const int64_t t = w - z * tiles_per_slice;
+        m0 = (t / n_tiles_n) * 128;
+        n0 = (t % n_tiles_n) * (int64_t)BN;
+        kb0 = z * k_per_slice;
+        int64_t k_end = kb0 + k_per_slice;
+        if (k_end > Kdim) k_end = Kdim;
+        nkb = (int)((k_end - kb0 + BK - 1) / BK);
+    };
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
-                uint8_t* sB = sA + 2 * A_BYTES;
-                mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + B_BYTES));
-                const int k = (int)(k_begin + (int64_t)kb * BK);
-                if (A_KMAJOR) {
-                    tma_load_2d(sA, &tmA, &full_bar[stage], k, (int)m0);                 // box {BK k, 128 rows}
-                } else {
+            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+                int64_t m0, n0, kb0, z;
+                int nkb;
+                decode(w, m0, n0, kb0, nkb, z);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+                    uint8_t* sB = sA + 2 * A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + B_BYTES));
+                    const int k = (int)(kb0 + (int64_t)kb * BK);
+                    if (A_KMAJOR) {
+                        tma_load_2d(sA, &tmA, &full_bar[stage], k, (int)m0);                 // box {BK k, 128 rows}
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)                                         // boxes {32 cols, BK rows}
-                        tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], (int)m0 + 32 * j, k);
+                        for (int j = 0; j < 4; ++j)                                         // boxes {32 cols, BK rows}
+                            tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], (int)m0 + 32 * j, k);
+                    }
+                    if (B_KMAJOR) {
+                        tma_load_2d(sB, &tmB, &full_bar[stage], k, (int)n0);                 // box {BK k, BN rows}
+                    } else {
+                        for (int j = 0; j < BN / 32; ++j)
+                            tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], (int)n0 + 32 * j, k);
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (B_KMAJOR) {
-                    tma_load_2d(sB, &tmB, &full_bar[stage], k, (int)n0);                 // box {32 k, BN rows}
-                } else {
-                    for (int j = 0; j < BN / 32; ++j)
-                        tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], (int)n0 + 32 * j, k);
-                }
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
@@ -197,118 +216,122 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t idesc = make_idesc(!A_KMAJOR, !B_KMAJOR, BN);
             int stage = 0;
             uint32_t phase = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(&ready_bar[stage], phase);
+            int64_t it = 0;
+            for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+                int64_t m0, n0, kb0, z;
+                int nkb;
+                decode(w, m0, n0, kb0, nkb, z);
+                const int acc = (int)(it & 1);
+                mbar_wait(&tmem_empty_bar[acc], (uint32_t)(((it >> 1) & 1) ^ 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t aB = smem_u32(smem + (size_t)stage * STAGE_BYTES);   // A big
-                const uint32_t aS = aB + A_BYTES;                                     // A small
-                const uint32_t bB = aB + 2 * A_BYTES;                                 // B big
-                const uint32_t bS = bB + B_BYTES;                                     // B small
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&ready_bar[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t aB = smem_u32(smem + (size_t)stage * STAGE_BYTES);   // A big
+                    const uint32_t aS = aB + A_BYTES;                                     // A small
+                    const uint32_t bB = aB + 2 * A_BYTES;                                 // B big
+                    const uint32_t bS = bB + B_BYTES;                                     // B small
 #pragma unroll
-                for (int ks = 0; ks < BK / 8; ++ks) {
-                    uint64_t dAb, dAs;
-                    if (A_KMAJOR) {
-                        // K-major rows of BK floats: BK = 32 -> SWIZZLE_128B (8-row groups of 1024 B),
-                        //                            BK = 16 -> SWIZZLE_64B  (8-row groups of 512 B)
-                        dAb = make_desc(aB + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4);
-                        dAs = make_desc(aS + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4);
-                    } else {
-                        dAb = make_desc(aB + ks * 1024, BK * 128, 512, 1);
-                        dAs = make_desc(aS + ks * 1024, BK * 128, 512, 1);
+                    for (int ks = 0; ks < BK / 8; ++ks) {
+                        uint64_t dAb, dAs;
+                        if (A_KMAJOR) {
+                            // K-major rows of BK floats: BK = 32 -> SWIZZLE_128B (8-row groups of 1024 B),
+                            //                            BK = 16 -> SWIZZLE_64B  (8-row groups of 512 B)
+                            dAb = make_desc(aB + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4);
+                            dAs = make_desc(aS + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4);
+                        } else {
+                            dAb = make_desc(aB + ks * 1024, BK * 128, 512, 1);
+                            dAs = make_desc(aS + ks * 1024, BK * 128, 512, 1);
+                        }
+                        const uint64_t dBb = B_KMAJOR ? make_desc(bB + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4)
+                                                      : make_desc(bB + ks * 1024, BK * 128, 512, 1);
+                        const uint64_t dBs = B_KMAJOR ? make_desc(bS + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4)
+                                                      : make_desc(bS + ks * 1024, BK * 128, 512, 1);
+                        umma_tf32(tmem_d, dAs, dBb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
+                        umma_tf32(tmem_d, dAb, dBs, idesc, 1u);
+                        umma_tf32(tmem_d, dAb, dBb, idesc, 1u);
                     }
-                    const uint64_t dBb = B_KMAJOR ? make_desc(bB + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4) : make_desc(bB + ks * 1024, BK * 128, 512, 1);
-                    const uint64_t dBs = B_KMAJOR ? make_desc(bS + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4) : make_desc(bS + ks * 1024, BK * 128, 512, 1);
-                    umma_tf32(tmem_base, dAs, dBb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
-                    umma_tf32(tmem_base, dAb, dBs, idesc, 1u);
-                    umma_tf32(tmem_base, dAb, dBb, idesc, 1u);
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == nkb - 1) umma_commit(&tmem_full_bar[acc]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty_bar[stage]);
-                if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+            }
+        }
+    } else if (warp >= 8) {
+        // ------------------------------------------------------------ operand split: small = x - trunc_tf32(x)
+        const int t = threadIdx.x - 256;
+        int stage = 0;
+        uint32_t phase = 0;
+        const int nvec = (A_BYTES + B_BYTES) / 16;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+            int64_t m0, n0, kb0, z;
+            int nkb;
+            decode(w, m0, n0, kb0, nkb, z);
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+#pragma unroll 4
+                for (int i = t; i < nvec; i += 128) {
+                    // vectors [0, A_BYTES/16) belong to A (big at sA, small at sA + A_BYTES), the rest to B
+                    const bool isA = i < A_BYTES / 16;
+                    uint4* big = reinterpret_cast<uint4*>(isA ? sA : sA + 2 * A_BYTES) + (isA ? i : i - A_BYTES / 16);
+                    uint4* sml = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(big) + (isA ? A_BYTES : B_BYTES));
+                    uint4 v = *big;
+                    uint4 s;
+                    // kind::tf32 ignores the low 13 mantissa bits of the raw tile (measured: results identical to an
+                    // explicitly masked "big" tile), so only the remainder tile has to be produced
+                    s.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xffffe000u));
+                    s.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xffffe000u));
+                    s.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xffffe000u));
+                    s.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xffffe000u));
+                    *sml = s;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&ready_bar[stage]);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ------------------------------------------------------------ operand split, then epilogue
-        const int t = threadIdx.x - 128;
-        int stage = 0;
-        uint32_t phase = 0;
-        const int nvec = (A_BYTES + B_BYTES) / 16;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(&full_bar[stage], phase);
-            uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
-#pragma unroll 4
-            for (int i = t; i < nvec; i += 128) {
-                // vectors [0, A_BYTES/16) belong to A (big at sA, small at sA + A_BYTES), the rest to B
-                const bool isA = i < A_BYTES / 16;
-                uint4* big = reinterpret_cast<uint4*>(isA ? sA : sA + 2 * A_BYTES) + (isA ? i : i - A_BYTES / 16);
-                uint4* sml = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(big) + (isA ? A_BYTES : B_BYTES));
-                uint4 v = *big;
-                uint4 b, s;
-                b.x = v.x & 0xffffe000u; b.y = v.y & 0xffffe000u; b.z = v.z & 0xffffe000u; b.w = v.w & 0xffffe000u;
-                s.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(b.x));
-                s.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(b.y));
-                s.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(b.z));
-                s.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(b.w));
-#ifdef WISKI_TC_MASK_BIG
-                *big = b;      // not needed: kind::tf32 ignores the low 13 mantissa bits (measured: identical results)
-#endif
-                *sml = s;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (dbg != nullptr && kb == 0 && blockIdx.x == 0 && blockIdx.z == 0) {
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                if (t < 64) {
-                    dbg[t] = reinterpret_cast<float*>(sA)[t];
-                    dbg[64 + t] = reinterpret_cast<float*>(sA + A_BYTES)[t];
-                    dbg[128 + t] = reinterpret_cast<float*>(sA + 2 * A_BYTES)[t];
-                    dbg[192 + t] = reinterpret_cast<float*>(sA + 2 * A_BYTES + B_BYTES)[t];
-                }
-            }
-            mbar_arrive(&ready_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 ; thread = output row
-        if (num_kb > 0) {
-            mbar_wait(tmem_full_bar, 0);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        // TMEM -> registers -> shared staging tile [128][BN + 4] -> coalesced 16-byte global stores.
-        // (Writing rows straight from registers would scatter every warp store over 32 rows.)  The operand ring is
-        // free at this point: every k-block has been loaded, split and consumed before tmem_full fires.
+        // ------------------------------------------------------------ epilogue: TMEM -> regs -> per-warp smem transpose
+        // -> 128-byte row segments in global memory.  Warp wq owns TMEM lanes (= output rows) 32 wq .. 32 wq + 31.
         const int wq = warp & 3;
-        const int PITCH = BN + 4;                                  // words; 16-byte row stores hit distinct bank groups
-        float* stg = reinterpret_cast<float*>(smem);
-        const int lrow = wq * 32 + lane;
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            if (num_kb > 0) {
-                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
-            } else {
+        float* stg = staging + wq * 32 * STG_PITCH;
+        int64_t it = 0;
+        for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+            int64_t m0, n0, kb0, z;
+            int nkb;
+            decode(w, m0, n0, kb0, nkb, z);
+            const int acc = (int)(it & 1);
+            mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float* obase = out + z * slice_stride;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + c0), v);
+                uint4* dst = reinterpret_cast<uint4*>(stg + lane * STG_PITCH);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = 0u;
-            }
-            if (dbg != nullptr && blockIdx.x == 0 && blockIdx.z == 0 && c0 == 0 && wq == 0 && lane < 2) {
-                for (int j = 0; j < 32; ++j) dbg[256 + lane * 32 + j] = __uint_as_float(v[j]);
-                dbg[320] = (float)num_kb; dbg[321] = __uint_as_float(tmem_base);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(stg + (size_t)lrow * PITCH + c0);
+                for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                __syncwarp();
+                // 8 lanes cover one 128-byte row segment; 4 rows per instruction
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");          // the four epilogue warps only
-        float* obase = out + (int64_t)blockIdx.z * slice_stride;
-        const int vec_per_row = BN / 4;
-        for (int i = t; i < 128 * vec_per_row; i += 128) {
-            const int rr = i / vec_per_row, c4 = i - rr * vec_per_row;
-            const int64_t row = m0 + rr, col = n0 + 4 * c4;
-            if (row < Mdim && col < Ndim)                       // Ndim % 4 == 0 (tc_shape_ok)
-                *reinterpret_cast<uint4*>(obase + row * ld_out + col) =
-                    *reinterpret_cast<const uint4*>(stg + (size_t)rr * PITCH + 4 * c4);
+                for (int rr = 0; rr < 32; rr += 4) {
+                    const int lr = rr + (lane >> 3), c4 = (lane & 7) * 4;
+                    const int64_t row = m0 + wq * 32 + lr, col = n0 + c0 + c4;
+                    if (row < Mdim && col < Ndim)                     // Ndim % 4 == 0 (tc_shape_ok)
+                        *reinterpret_cast<uint4*>(obase + row * ld_out + col) =
+                            *reinterpret_cast<const uint4*>(stg + lr * STG_PITCH + c4);
+                }
+                __syncwarp();
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 256);
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -373,13 +396,16 @@ static inline bool tc_shape_ok(int64_t m, int64_t r, int64_t r2) {
 template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, int64_t Mdim, int64_t Ndim, int64_t Kdim,
                   int bn, int ntiles, int64_t k_per_slice, int64_t nslices, int64_t ld_out, int64_t slice_stride,
-                  cudaStream_t st, const char* name, float* dbg = nullptr) {
-    size_t smem = (size_t)STAGES * 2 * ((size_t)128 * BK * 4 + (size_t)bn * BK * 4) + (3 * STAGES + 2) * 8 + 1024;
+                  cudaStream_t st, const char* name) {
+    size_t smem = (size_t)STAGES * 2 * ((size_t)128 * BK * 4 + (size_t)bn * BK * 4) + 4 * 32 * 36 * 4 +
+                  (3 * STAGES + 5) * 8 + 1024;
     auto kfn = tc_gemm3x_kernel<A_KMAJOR, B_KMAJOR, BK, STAGES>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
-    // x = (m-tile, n-tile) flattened with the n-tile fastest
-    dim3 grid((unsigned)(ceil_div(Mdim, 128) * ntiles), 1, (unsigned)nslices);
-    kfn<<<grid, 256, smem, st>>>(tmA, tmB, out, Mdim, Ndim, Kdim, bn, ntiles, k_per_slice, ld_out, slice_stride, dbg);
+    const int n_tiles_m = (int)ceil_div(Mdim, 128);
+    const int64_t n_work = (int64_t)n_tiles_m * ntiles * nslices;
+    const int64_t grid = n_work < kNumSMs ? n_work : kNumSMs;
+    kfn<<<(unsigned)grid, 384, smem, st>>>(tmA, tmB, out, Mdim, Ndim, Kdim, bn, ntiles, n_tiles_m, n_work, k_per_slice,
+                                           ld_out, slice_stride);
     WISKI_CHECK_LAUNCH(name);
     count_launches(1);
     return 0;
@@ -399,8 +425,6 @@ int64_t tc_gram_work_elems(int64_t m, int64_t r, int64_t r2) {
     return ceil_div(m, kGramSliceRows) * r * r2;
 }
 
-float* g_tc_dbg = nullptr;   // debug dump buffer (device), set by the standalone test only
-
 int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
                 cudaStream_t st) {
     if (!tc_shape_ok(m, r, r2)) return 3;
@@ -411,7 +435,7 @@ int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r
     int bn = pick_bn(r2, &ntiles);
     int64_t nslices = ceil_div(m, kGramSliceRows);
     if (int rc = launch<false, false, kGramBK, kGramStages>(tmA, tmB, work, r, r2, m, bn, ntiles, kGramSliceRows, nslices, r2,
-                                                     r * r2, st, "tc_gram", g_tc_dbg))
+                                                     r * r2, st, "tc_gram"))
         return rc;
     int64_t n = r * r2;
     reduce_slices_kernel<float><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nslices, n, G);
@@ -437,7 +461,7 @@ int tc_panel_rmul_nt_f32(const float* P, int64_t m, int64_t r, const float* Mt, 
     int bn = pick_bn(r2, &ntiles);
     if (int rc = make_map(&tmA, P, m, r, 128, false, kRmulBK)) return rc;
     if (int rc = make_map(&tmB, Mt, r2, r, bn, false, kRmulBK)) return rc;
-    return launch<true, true, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, r2, 0, st, "tc_panel_rmul_nt", g_tc_dbg);
+    return launch<true, true, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, r2, 0, st, "tc_panel_rmul_nt");
 }
 
 }  // namespace wiski

@@ -10,7 +10,6 @@ namespace wiski {
 int tc_gram_f32(const float*, const float*, int64_t, int64_t, int64_t, float*, float*, cudaStream_t);
 int tc_panel_rmul_f32(const float*, int64_t, int64_t, const float*, int64_t, float*, cudaStream_t);
 int64_t tc_gram_work_elems(int64_t, int64_t, int64_t);
-extern float* g_tc_dbg;
 int tc_panel_rmul_nt_f32(const float*, int64_t, int64_t, const float*, int64_t, float*, cudaStream_t);
 }
 
@@ -107,15 +106,8 @@ static void ones_probe(int64_t m, int64_t r) {
     cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dM, Mm.data(), Mm.size() * 4, cudaMemcpyHostToDevice);
     cudaMemset(dW, 0xff, wiski::tc_gram_work_elems(m, r, r) * 4);
-    float* dD; cudaMalloc(&dD, 512 * 4); cudaMemset(dD, 0xff, 512 * 4);
-    wiski::g_tc_dbg = dD;
     wiski::tc_gram_f32(dA, dA, m, r, r, dG, dW, 0);
     cudaDeviceSynchronize();
-    wiski::g_tc_dbg = nullptr;
-    { std::vector<float> D(512); cudaMemcpy(D.data(), dD, 512 * 4, cudaMemcpyDeviceToHost);
-      const char* names[5] = {"A_big", "A_small", "B_big", "B_small", "tmem"};
-      for (int b = 0; b < 5; ++b) { printf("  %s:", names[b]); for (int j = 0; j < 40; ++j) printf(" %g", D[64 * b + j]); printf("\n"); }
-      printf("  num_kb=%g tmem_base=0x%x\n", D[320], *reinterpret_cast<unsigned*>(&D[321])); }
     std::vector<float> G(r * r), O(m * r);
     cudaMemcpy(G.data(), dG, G.size() * 4, cudaMemcpyDeviceToHost);
     printf("ones gram m=%lld: expect G[i][j]=m*(1+i%%4)*(1+j%%4): ", (long long)m);

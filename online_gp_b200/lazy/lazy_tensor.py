@@ -539,6 +539,17 @@ class PanelGramLazyTensor(LazyTensor):
             self._eval = G + self.jitter * torch.eye(G.shape[-1], dtype=G.dtype, device=G.device)
         return self._eval
 
+    def cholesky(self, upper=False):
+        # Q = jitter I + L^T K L with K PSD: for jitter >= 1 it is positive definite by construction, so the
+        # factorisation is issued without the host-side `info` check (one device->host sync less per step);
+        # a breakdown (NaN inputs) still surfaces as NaNs downstream.
+        if not hasattr(self, "_chol_cache"):
+            if self.jitter >= 1.0:
+                self._chol_cache, _ = torch.linalg.cholesky_ex(self.evaluate(), check_errors=False)
+            else:
+                self._chol_cache = psd_safe_cholesky(self.evaluate())
+        return self._chol_cache.transpose(-1, -2) if upper else self._chol_cache
+
     def _solve(self, rhs, preconditioner=None, num_tridiag=0):
         if self.jitter != 1.0 or self.L.shape[1] > 1024:
             return torch.cholesky_solve(rhs, self.cholesky())
