@@ -389,3 +389,43 @@ def test_sharded_world1_fused_32x4_matches_single_device():
                 assert abs(float(reg.noise.mean()) - float(shd._noise())) <= 1e-4
     finally:
         torch.set_default_dtype(prev)
+
+
+FULL_SIZE = [
+    # BASELINE.json config shapes at full grid size (rank kept small so that the CPU oracle finishes in seconds)
+    (3, 128, 24, 8, "3droad-shaped: 128^3 grid, batch_size 8"),
+    (2, 256, 10, 6, "malaria-shaped: 256^2 grid, batch_size 6"),
+    (2, 1024, 20, 1, "target: 1024^2 grid, batch_size 1"),
+    (4, 32, 30, 1, "powerplant-shaped: 32^4 grid, batch_size 1"),
+]
+
+
+@pytest.mark.parametrize("d,g,n0,q,desc", FULL_SIZE)
+def test_full_size_grids_match_matfree_oracle(d, g, n0, q, desc):
+    """Posterior mean / variance and MLL at the full BASELINE grid sizes (fp32, 1e-2), before and after one update."""
+    if _dev() == "cpu":
+        pytest.skip("full-size grids: GPU only")
+    M = _mods()
+    dt = torch.float32
+    orc, model, X, y, hyp = _oracle_and_model(M, d, g, n0, dt, 0, "sym", "rbf", seed=2, max_root=64)
+    Xs = torch.rand(5, d, dtype=torch.float64, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    with M["S"].max_cholesky_size(800), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for step in range(2):
+            model.eval()
+            dist = model(Xs.to(dt).to(_dev()))
+            mo, co = orc.predict(Xs)
+            assert np.allclose(dist.mean.detach().cpu().double().numpy(), mo.detach().numpy(), rtol=1e-2,
+                               atol=1e-2 * float(mo.abs().max()))
+            vo = co.diagonal().detach().numpy()
+            assert np.allclose(dist.variance.detach().cpu().double().numpy(), vo, rtol=1e-2, atol=1e-2 * float(vo.max()))
+            model.train()
+            model.zero_grad()
+            mll = M["BatchedWoodburyMarginalLogLikelihood"](model.likelihood, model)
+            val = mll(model(None), None)
+            val.sum().backward()
+            assert np.allclose(val.item(), orc.mll().item(), rtol=1e-2)
+            xn, yn = X[n0:n0 + q], y[n0:n0 + q]
+            orc.condition_on_observations(xn, yn, torch.ones(q, dtype=torch.float64))
+            model.condition_on_observations(xn.to(dt).to(_dev()), yn.to(dt).to(_dev()).unsqueeze(-1),
+                                            torch.ones(q, 1, dtype=dt, device=_dev()), inplace=True)
