@@ -108,43 +108,28 @@ __global__ void rmul_skinny_kernel(const T* __restrict__ P, const T* __restrict_
 template <typename T, int QP>
 __global__ void lowrank_update_kernel(T* __restrict__ P, int64_t m, int64_t r, const T* __restrict__ U,
                                       const T* __restrict__ Vt, int q) {
-    // warp per row, two rows in flight (independent load streams); the second sweep re-reads the row from L1/L2
     int lane = threadIdx.x & 31;
     int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t i = warp; i < m; i += 2 * nwarps) {
-        const int64_t i2 = i + nwarps;
-        const bool has2 = i2 < m;
+    for (int64_t i = warp; i < m; i += nwarps) {
         T* row = P + i * r;
-        T* row2 = P + (has2 ? i2 : i) * r;
-        T dot[QP], dot2[QP];
+        T dot[QP];
 #pragma unroll
-        for (int t = 0; t < QP; ++t) { dot[t] = T(0); dot2[t] = T(0); }
-#pragma unroll 4
+        for (int t = 0; t < QP; ++t) dot[t] = T(0);
         for (int64_t j = lane; j < r; j += 32) {
-            T x = row[j], x2 = row2[j];
+            T x = row[j];
 #pragma unroll
             for (int t = 0; t < QP; ++t)
-                if (t < q) {
-                    T u = U[j * q + t];
-                    dot[t] += x * u;
-                    dot2[t] += x2 * u;
-                }
+                if (t < q) dot[t] += x * U[j * q + t];
         }
 #pragma unroll
-        for (int t = 0; t < QP; ++t) { dot[t] = warp_sum(dot[t]); dot2[t] = warp_sum(dot2[t]); }
-#pragma unroll 4
+        for (int t = 0; t < QP; ++t) dot[t] = warp_sum(dot[t]);
         for (int64_t j = lane; j < r; j += 32) {
-            T x = row[j], x2 = row2[j];
+            T x = row[j];
 #pragma unroll
             for (int t = 0; t < QP; ++t)
-                if (t < q) {
-                    T v = Vt[(int64_t)t * r + j];
-                    x += dot[t] * v;
-                    x2 += dot2[t] * v;
-                }
+                if (t < q) x += dot[t] * Vt[(int64_t)t * r + j];
             row[j] = x;
-            if (has2) row2[j] = x2;
         }
     }
 }
