@@ -111,6 +111,14 @@ int wiski_kron_fused_pair_grad_f32(const float* cols, int d, const int64_t* h_g,
                                    const float* P, float* Zout, int64_t c, double* acc_u64, double* acc_v64,
                                    void* stream);
 
+/* Directional form of pair_grad: with dirs [d,gmax] = d col_i / d lengthscale_i it returns, accumulated into out3
+ * (3 doubles):  <grad_{2p}, dirs_{2p}>, <grad_{2p+1}, dirs_{2p+1}> and <Z', K' P'> (= <grad_i, col_i> for every i),
+ * which is all a stationary product kernel with one lengthscale per dimension and scalar scales needs; it replaces
+ * the two 1024-FMA contractions per grid line by one 512-FMA application of the direction matrix and a dot. */
+int wiski_kron_fused_pair_grad_dir_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,
+                                       int pair, const float* Z, const float* P, float* Zout, int64_t c, double* out3,
+                                       void* stream);
+
 /* ---- k7: panel right-multiply  Out = P @ M,  P,Out [m,r], M [r,r2], Out [m,r2]  (Out must not alias P)
  * (replaces current_root.matmul(inner_root) / current_inv_root^T.matmul(inner_inv_root),
  * updated_root_lazy_tensor.py:97-100,115-117, and Kuu_Lmat @ qmat_solve, batched_fixed_noise_online_gp.py:376). */

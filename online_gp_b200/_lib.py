@@ -38,7 +38,7 @@ def _sigs(real, realp):
 
 #: every symbol include/wiski_b200.h declares (tests check the .so exports all of them)
 EXPORTED = ["wiski_last_error", "wiski_abi_version", "wiski_launch_count", "wiski_kron_fused_supported",
-            "wiski_kron_fused_pair_apply_f32", "wiski_kron_fused_pair_grad_f32", "wiski_gram_work_elems", "wiski_qmv_work_elems",
+            "wiski_kron_fused_pair_apply_f32", "wiski_kron_fused_pair_grad_f32", "wiski_kron_fused_pair_grad_dir_f32", "wiski_gram_work_elems", "wiski_qmv_work_elems",
             "wiski_cg_work_elems", "wiski_kron_toeplitz_bwd_work_elems"] + [
     f"{n}_{sfx}" for n in _sigs(c_float, POINTER(c_float)) for sfx in ("f32", "f64")]
 
@@ -70,6 +70,8 @@ def load():
     lib.wiski_kron_fused_pair_apply_f32.argtypes = [_P, c_int, _I64P, c_int64, c_int, _P, _P, c_int64, _S]
     lib.wiski_kron_fused_pair_grad_f32.restype = c_int
     lib.wiski_kron_fused_pair_grad_f32.argtypes = [_P, c_int, _I64P, c_int64, c_int, _P, _P, _P, c_int64, _P, _P, _S]
+    lib.wiski_kron_fused_pair_grad_dir_f32.restype = c_int
+    lib.wiski_kron_fused_pair_grad_dir_f32.argtypes = [_P, _P, c_int, _I64P, c_int64, c_int, _P, _P, _P, c_int64, _P, _S]
     for sfx, real in (("f32", c_float), ("f64", c_double)):
         for name, args in _sigs(real, POINTER(real)).items():
             fn = getattr(lib, f"{name}_{sfx}")

@@ -24,17 +24,18 @@ constexpr int CB = 16;         // panel columns per tile
 constexpr int UP = G * CB + 16;   // pitch (floats) of one u-group in shared memory: 32 rows of 16 + 16 pad
 constexpr int TILE_FLOATS = G * UP;   // 16896 floats = 67584 B
 
-__constant__ float c_coef[2][2][H][H];          // [slot][P|M][i][j]
-__device__ float g_coef_stage[2 * 2 * H * H];
+__constant__ float c_coef[4][2][H][H];          // [slot][P|M][i][j]; slots 0,1 = T_u, T_v; 2,3 = direction matrices T'_u, T'_v
+__device__ float g_coef_stage[4 * 2 * H * H];
 
-__global__ void prep_coef_kernel(const float* __restrict__ col0, const float* __restrict__ col1) {
+__global__ void prep_coef_kernel(const float* __restrict__ col0, const float* __restrict__ col1,
+                                 const float* __restrict__ col2, const float* __restrict__ col3) {
     int t = threadIdx.x;            // 256 threads: (i, j)
     int i = t / H, j = t % H;
     int d = i - j;
     d = d < 0 ? -d : d;
-    const float* cols[2] = {col0, col1};
+    const float* cols[4] = {col0, col1, col2, col3};
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < 4; ++s) {
         if (cols[s] == nullptr) continue;
         float a = cols[s][d], b = cols[s][G - 1 - i - j];
         g_coef_stage[((s * 2 + 0) * H + i) * H + j] = 0.5f * (a + b);
@@ -42,12 +43,14 @@ __global__ void prep_coef_kernel(const float* __restrict__ col0, const float* __
     }
 }
 
-static int set_coefficients(const float* col0, const float* col1, cudaStream_t st) {
-    prep_coef_kernel<<<1, 256, 0, st>>>(col0, col1);
+static int set_coefficients(const float* col0, const float* col1, cudaStream_t st, const float* dir0 = nullptr,
+                            const float* dir1 = nullptr) {
+    prep_coef_kernel<<<1, 256, 0, st>>>(col0, col1, dir0, dir1);
     void* stage = nullptr;
     WISKI_CHECK_CUDA(cudaGetSymbolAddress(&stage, g_coef_stage), "kron_fused(symbol)");
-    WISKI_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_coef, stage, sizeof(float) * 2 * 2 * H * H, 0, cudaMemcpyDeviceToDevice, st),
-                     "kron_fused(coef)");
+    const int nslots = (dir0 != nullptr) ? 4 : 2;
+    WISKI_CHECK_CUDA(cudaMemcpyToSymbolAsync(c_coef, stage, sizeof(float) * nslots * 2 * H * H, 0,
+                                             cudaMemcpyDeviceToDevice, st), "kron_fused(coef)");
     count_launches(1);
     return 0;
 }
@@ -100,6 +103,32 @@ __device__ __forceinline__ void sym_apply32x2(float (&x0)[G], float (&x1)[G]) {
         x0[G - 1 - i] = ys0 - ya0;
         x1[i] = ys1 + ya1;
         x1[G - 1 - i] = ys1 - ya1;
+    }
+}
+
+// ya = T_SA x and yb = T_SB x sharing the symmetric / antisymmetric parts of x
+template <int SA, int SB>
+__device__ __forceinline__ void sym_dual32(const float (&x)[G], float (&ya_)[G], float (&yb_)[G]) {
+    float s[H], a[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        s[j] = x[j] + x[G - 1 - j];
+        a[j] = x[j] - x[G - 1 - j];
+    }
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        float s0 = 0.f, a0 = 0.f, s1 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            s0 = fmaf(c_coef[SA][0][i][j], s[j], s0);
+            a0 = fmaf(c_coef[SA][1][i][j], a[j], a0);
+            s1 = fmaf(c_coef[SB][0][i][j], s[j], s1);
+            a1 = fmaf(c_coef[SB][1][i][j], a[j], a1);
+        }
+        ya_[i] = s0 + a0;
+        ya_[G - 1 - i] = s0 - a0;
+        yb_[i] = s1 + a1;
+        yb_[G - 1 - i] = s1 - a1;
     }
 }
 
@@ -308,6 +337,103 @@ pair_grad_kernel(const float* __restrict__ Z, const float* __restrict__ P, float
     }
 }
 
+// ------------------------------------------------------------------ backward pair kernel, directional form
+// The loss depends on column i only through <grad_i, dcol_i> (dcol_i = d col_i / d lengthscale_i) and <grad_i, col_i>
+// (every scale-type parameter), and  <grad_i, dcol_i> = sum_lines z^T T'_i p,  <grad_i, col_i> = <Z, K X>  for all i.
+// So instead of the full 32-entry column gradient (1024 FMA per grid line) the pass applies the *direction* matrix
+// T'_i (512 FMA) and takes a dot product.  Per tile:
+//   1: S = T_v P (lines along v)            2: zu = T_u z, zd = T'_u z;  s_u += zd . S;  z <- zu   (lines along u)
+//   3: s_v += (T'_v zu) . p;  s_scale += zu . S;  STORE: Zout = T_v zu                        (lines along v)
+// out3: [s_u, s_v, s_scale] doubles (accumulated).
+template <bool STORE>
+__global__ void __launch_bounds__(256, 1)
+pair_grad_jvp_kernel(const float* __restrict__ Z, const float* __restrict__ P, float* __restrict__ Zout, PairGeom g,
+                     double* __restrict__ out3) {
+    constexpr int NT = 256;
+    extern __shared__ __align__(16) float smem[];
+    float* zt = smem;
+    float* pt = smem + TILE_FLOATS;
+    float* st = smem + 2 * TILE_FLOATS;
+    float su = 0.f, sv = 0.f, ss = 0.f;
+    const int64_t vstride = g.sv * g.c;
+    for (int64_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        int64_t rb, c0;
+        tile_coords(g, tile, rb, c0);
+        load_tile_async<NT>(zt, Z, g, rb, c0);
+        load_tile_async<NT>(pt, P, g, rb, c0);
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+        // 1: S = T_v P
+#pragma unroll 1
+        for (int l = threadIdx.x; l < G * CB; l += NT) {
+            const int w = l & (CB - 1), u = l / CB;
+            float x[G];
+#pragma unroll
+            for (int v = 0; v < G; ++v) x[v] = pt[u * UP + v * CB + w];
+            sym_apply32<1>(x);
+#pragma unroll
+            for (int v = 0; v < G; ++v) st[u * UP + v * CB + w] = x[v];
+        }
+        __syncthreads();
+        // 2: lines along u
+#pragma unroll 1
+        for (int l = threadIdx.x; l < G * CB; l += NT) {
+            const int w = l & (CB - 1), v = l / CB;
+            float z[G], zu[G], zd[G];
+#pragma unroll
+            for (int u = 0; u < G; ++u) z[u] = zt[u * UP + v * CB + w];
+            sym_dual32<0, 2>(z, zu, zd);
+#pragma unroll
+            for (int u = 0; u < G; ++u) {
+                su = fmaf(zd[u], st[u * UP + v * CB + w], su);
+                zt[u * UP + v * CB + w] = zu[u];
+            }
+        }
+        __syncthreads();
+        // 3: lines along v
+#pragma unroll 1
+        for (int l = threadIdx.x; l < G * CB; l += NT) {
+            const int w = l & (CB - 1), u = l / CB;
+            float zu[G], zv[G], zd[G];
+#pragma unroll
+            for (int v = 0; v < G; ++v) {
+                zu[v] = zt[u * UP + v * CB + w];
+                ss = fmaf(zu[v], st[u * UP + v * CB + w], ss);
+            }
+            if (STORE) {
+                sym_dual32<1, 3>(zu, zv, zd);
+            } else {
+#pragma unroll
+                for (int v = 0; v < G; ++v) zd[v] = zu[v];
+                sym_apply32<3>(zd);
+            }
+#pragma unroll
+            for (int v = 0; v < G; ++v) sv = fmaf(zd[v], pt[u * UP + v * CB + w], sv);
+            if (STORE) {
+                float* yp = Zout + (rb + (int64_t)u * G * g.sv) * g.c + c0 + w;
+#pragma unroll
+                for (int v = 0; v < G; ++v) {
+                    *yp = zv[v];
+                    yp += vstride;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __shared__ float red[3][8];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    su = warp_sum(su); sv = warp_sum(sv); ss = warp_sum(ss);
+    if (lane == 0) { red[0][warp] = su; red[1][warp] = sv; red[2][warp] = ss; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += (double)red[threadIdx.x][w];
+        atomicAdd(&out3[threadIdx.x], s);
+    }
+}
+
 // ------------------------------------------------------------------ host side
 static bool make_geom(PairGeom& g, int d, const int64_t* h_g, int pair, int64_t c) {
     int u = 2 * pair, v = u + 1;
@@ -391,9 +517,43 @@ int fused_pair_grad(const float* cols, int d, const int64_t* h_g, int64_t gmax, 
     return 0;
 }
 
+// Directional backward pair pass (see pair_grad_jvp_kernel).  out3: 3 doubles, accumulated.
+int fused_pair_grad_jvp(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int pair,
+                        const float* Z, const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st) {
+    PairGeom g;
+    if (!make_geom(g, d, h_g, pair, c)) { set_error("kron_fused: unsupported shape"); return 3; }
+    if (int rc = set_coefficients(cols + (int64_t)(2 * pair) * gmax, cols + (int64_t)(2 * pair + 1) * gmax, st,
+                                  dirs + (int64_t)(2 * pair) * gmax, dirs + (int64_t)(2 * pair + 1) * gmax))
+        return rc;
+    size_t smem = 3 * TILE_FLOATS * sizeof(float);
+    int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
+    if (Zout != nullptr) {
+        auto kfn = pair_grad_jvp_kernel<true>;
+        WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
+        kfn<<<(unsigned)grid, 256, smem, st>>>(Z, P, Zout, g, out3);
+    } else {
+        auto kfn = pair_grad_jvp_kernel<false>;
+        WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
+        kfn<<<(unsigned)grid, 256, smem, st>>>(Z, P, nullptr, g, out3);
+    }
+    WISKI_CHECK_LAUNCH("kron_fused(pair_grad_jvp)");
+    count_launches(1);
+    return 0;
+}
+
 }  // namespace wiski
 
 extern "C" {
+int wiski_kron_fused_pair_grad_dir_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,
+                                       int pair, const float* Z, const float* P, float* Zout, int64_t c, double* out3,
+                                       void* stream) {
+    if (d < 2 || d > WISKI_MAX_DIMS || pair < 0 || 2 * pair + 1 >= d || dirs == nullptr) {
+        wiski::set_error("kron_fused_pair_grad_dir: unsupported shape");
+        return 3;
+    }
+    return wiski::fused_pair_grad_jvp(cols, dirs, d, h_g, gmax, pair, Z, P, Zout, c, out3, wiski::as_stream(stream));
+}
+
 /* Fused two-axes-per-pass Kronecker-Toeplitz MVM (fp32, every grid axis 32 points, d even, c % 16 == 0).
  * Returns 3 when the shape is not supported (callers fall back to wiski_kron_toeplitz_mm_f32). */
 int wiski_kron_fused_supported(int d, const int64_t* h_g, int64_t c) { return wiski::fused_supported(d, h_g, c) ? 1 : 0; }

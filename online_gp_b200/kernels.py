@@ -117,6 +117,26 @@ class Kernel(nn.Module, _PriorMixin):
         return torch.stack(rows, dim=-2)
 
 
+    def grid_column_dirs(self, grid):
+        """d grid_columns / d lengthscale_i per row (no grad), by forward-mode AD through ``base_1d``; ``None`` if the
+        grids differ in size.  Only the direction matters (any per-row scaling is absorbed downstream)."""
+        import torch.autograd.forward_ad as fwAD
+        gmax = max(g.numel() for g in grid)
+        if not all(g.numel() == gmax for g in grid):
+            return None
+        with torch.no_grad():
+            ell = self.lengthscale
+            d = len(grid)
+            G = torch.stack([g.to(ell.dtype) for g in grid])
+            dist = (G - G[:, :1]).abs()
+            li = (ell[..., 0, :] if ell.shape[-1] > 1 else ell[..., 0, :].expand(*ell.shape[:-2], d)).unsqueeze(-1)
+        with torch.enable_grad(), fwAD.dual_level():
+            dual = fwAD.make_dual(li.clone(), torch.ones_like(li))
+            out = self.base_1d(dist / dual)
+            tangent = fwAD.unpack_dual(out).tangent
+        return tangent.detach()
+
+
 class RBFKernel(Kernel):
     def base_1d(self, r):
         return torch.exp(-0.5 * r * r)
@@ -165,6 +185,9 @@ class ScaleKernel(Kernel):
         # last_dim_is_batch=True: every per-dimension factor is scaled (A.3 ii => amplitude outputscale**d)
         cols = self.base_kernel.grid_columns(grid)
         return cols * self.outputscale.reshape(*self.outputscale.shape, 1, 1)
+
+    def grid_column_dirs(self, grid):
+        return self.base_kernel.grid_column_dirs(grid)
 
 
 # ------------------------------------------------------------------ SKI
@@ -263,10 +286,15 @@ class GridInterpolationKernel(Kernel):
     def _inducing_forward(self, last_dim_is_batch=False, **params):
         """K_uu as a Kronecker product of Toeplitz factors (A.3); one operator per kernel batch element."""
         cols = self.base_kernel.grid_columns(self.grid)
+        dirs = None
+        if cols.requires_grad and torch.is_grad_enabled() and hasattr(self.base_kernel, "grid_column_dirs"):
+            dirs = self.base_kernel.grid_column_dirs(self.grid)
         if cols.dim() == 2:
-            return KroneckerToeplitzLazyTensor(cols, self.grid_sizes)
+            return KroneckerToeplitzLazyTensor(cols, self.grid_sizes, dirs)
         from .lazy.lazy_tensor import BatchLazyTensor
-        return BatchLazyTensor([KroneckerToeplitzLazyTensor(c, self.grid_sizes) for c in cols.reshape(-1, *cols.shape[-2:])])
+        cs = cols.reshape(-1, *cols.shape[-2:])
+        ds = [None] * cs.shape[0] if dirs is None else list(dirs.reshape(-1, *dirs.shape[-2:]))
+        return BatchLazyTensor([KroneckerToeplitzLazyTensor(c, self.grid_sizes, dd) for c, dd in zip(cs, ds)])
 
     def _interpolated(self, x1, x2=None):
         li, lv = self._compute_grid(x1)

@@ -573,8 +573,9 @@ class KroneckerToeplitzLazyTensor(LazyTensor):
     """K_uu = kron_i Toeplitz(cols[i]) — stands in for ``KroneckerProductLazyTensor(ToeplitzLazyTensor...)``
     (SURVEY App. A.3/A.4); ``_matmul`` is the Kronecker-Toeplitz CUDA kernel, differentiable w.r.t. ``cols``."""
 
-    def __init__(self, cols, sizes):
-        self.cols, self.sizes = cols, tuple(int(s) for s in sizes)
+    def __init__(self, cols, sizes, dirs=None):
+        # dirs (optional, [d,gmax], no grad): d cols[i] / d lengthscale_i — enables the directional backward pass
+        self.cols, self.sizes, self.dirs = cols, tuple(int(s) for s in sizes), dirs
         self.m = 1
         for s in self.sizes:
             self.m *= s
@@ -583,7 +584,7 @@ class KroneckerToeplitzLazyTensor(LazyTensor):
         return torch.Size((self.m, self.m))
 
     def _matmul(self, rhs):
-        return ops.kron_toeplitz_matmul(self.cols, self.sizes, rhs)
+        return ops.kron_toeplitz_matmul(self.cols, self.sizes, rhs, dirs=self.dirs)
 
     def _transpose_nonbatch(self):
         return self
@@ -593,7 +594,7 @@ class KroneckerToeplitzLazyTensor(LazyTensor):
         scale = torch.ones_like(self.cols[:, :1])
         scale = torch.cat([1.0 / other.reshape(1, 1).to(self.cols), scale[1:]], dim=0) if self.cols.shape[0] > 1 \
             else 1.0 / other.reshape(1, 1).to(self.cols)
-        return KroneckerToeplitzLazyTensor(self.cols * scale, self.sizes)
+        return KroneckerToeplitzLazyTensor(self.cols * scale, self.sizes, self.dirs)
 
     def __mul__(self, other):
         return self.__truediv__(1.0 / torch.as_tensor(other, dtype=self.cols.dtype, device=self.cols.device))
@@ -608,7 +609,7 @@ class KroneckerToeplitzLazyTensor(LazyTensor):
         return super().evaluate()
 
     def detach(self):
-        return KroneckerToeplitzLazyTensor(self.cols.detach(), self.sizes)
+        return KroneckerToeplitzLazyTensor(self.cols.detach(), self.sizes, self.dirs)
 
     dtype = property(lambda self: self.cols.dtype)
     device = property(lambda self: self.cols.device)

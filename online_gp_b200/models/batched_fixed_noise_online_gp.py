@@ -465,7 +465,8 @@ class FixedNoiseOnlineSKIGP(GP):
             raise RuntimeError(f"kernel batch ({len(items)}) does not match the number of outputs ({t})")
         out = []
         for o, K in enumerate(items):
-            K = KroneckerToeplitzLazyTensor(K.cols.to(self._dtype), K.sizes)
+            K = KroneckerToeplitzLazyTensor(K.cols.to(self._dtype), K.sizes,
+                                            None if K.dirs is None else K.dirs.to(self._dtype))
             if self.has_learnable_noise:
                 # append 1 / \sigma^2 into the Kuu term in the qmatrix
                 K = K / self._second_noise(o)

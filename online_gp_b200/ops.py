@@ -264,15 +264,36 @@ def _fused_pair_grad(cols, sizes, pair, Z, P, acc, store):
     return Zout
 
 
+def _fused_pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store):
+    d, gmax = cols.shape
+    Zout = torch.empty_like(Z) if store else None
+    h_g = (c_int64 * d)(*sizes)
+    _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_fused_pair_grad_dir_f32, _ptr(cols), _ptr(dirs), d, h_g,
+             gmax, pair, _ptr(Z), _ptr(P), _ptr(Zout), Z.shape[1], _ptr(out3), _stream())
+    return Zout
+
+
+def _surrogate_col_grad(cols, dirs, s_dir, s_scale):
+    """The vector g_i in span{dirs_i, cols_i} with <g_i, dirs_i> = s_dir_i and <g_i, cols_i> = s_scale: equivalent to
+    the true column gradient for every parameter that moves col_i only along those two directions."""
+    c64, d64 = cols.double(), dirs.double()
+    dd, dc, cc = (d64 * d64).sum(-1), (d64 * c64).sum(-1), (c64 * c64).sum(-1)
+    det = dd * cc - dc * dc
+    alpha = (s_dir * cc - s_scale * dc) / det
+    beta = (dd * s_scale - dc * s_dir) / det
+    return (alpha.unsqueeze(-1) * d64 + beta.unsqueeze(-1) * c64).to(cols.dtype)
+
+
 class _KronFn(torch.autograd.Function):
     """K X with the column gradient.  When cols needs grad the forward applies the axes in the order d-1, ..., 0 and
     keeps the suffix products S_i = T_{i+1} .. T_{d-1} X, so the backward only runs the prefix chain on the incoming
     gradient plus one contraction per axis (d-1 axis passes instead of 2(d-1))."""
 
     @staticmethod
-    def forward(ctx, cols, X, sizes):
+    def forward(ctx, cols, X, sizes, dirs=None):
         cols = cols.contiguous()
         ctx.sizes = sizes
+        ctx.dirs = None
         if not ctx.needs_input_grad[0]:
             ctx.save_for_backward(cols, X)
             ctx.suffix = None
@@ -287,6 +308,7 @@ class _KronFn(torch.autograd.Function):
             Y = _fused_pair_apply(cols, sizes, 0, M[0])
             ctx.save_for_backward(cols, *M)
             ctx.suffix = "fused"
+            ctx.dirs = None if dirs is None else dirs.detach().to(cols.dtype).contiguous()
             return Y
         geo = _axis_geometry(sizes, X.shape[1])
         S = [None] * len(sizes)
@@ -305,7 +327,7 @@ class _KronFn(torch.autograd.Function):
         gY = gY.contiguous()
         if ctx.suffix is None:
             cols, X = ctx.saved_tensors
-            return None, (_kron_mm(cols, ctx.sizes, gY) if ctx.needs_input_grad[1] else None), None
+            return None, (_kron_mm(cols, ctx.sizes, gY) if ctx.needs_input_grad[1] else None), None, None
         cols, *S = ctx.saved_tensors
         sizes = ctx.sizes
         d, gmax = cols.shape
@@ -313,9 +335,19 @@ class _KronFn(torch.autograd.Function):
         if ctx.suffix == "fused":
             Zc = gY
             npairs = d // 2
+            if ctx.dirs is not None:
+                # directional form: one 512-FMA direction apply + dot per grid line instead of a 1024-FMA contraction
+                out = torch.zeros(npairs, 3, dtype=torch.float64, device=gY.device)
+                for p in range(npairs):
+                    Zc = _fused_pair_grad_dir(cols, ctx.dirs, sizes, p, Zc, S[p], out[p],
+                                              store=(p < npairs - 1 or ctx.needs_input_grad[1]))
+                gcols = _surrogate_col_grad(cols[:, :sizes[0]], ctx.dirs[:, :sizes[0]], out[:, :2].reshape(-1), out[-1, 2])
+                if gcols.shape[1] < gmax:
+                    gcols = torch.nn.functional.pad(gcols, (0, gmax - gcols.shape[1]))
+                return gcols, (Zc if ctx.needs_input_grad[1] else None), None, None
             for p in range(npairs):
                 Zc = _fused_pair_grad(cols, sizes, p, Zc, S[p], acc, store=(p < npairs - 1 or ctx.needs_input_grad[1]))
-            return acc.to(cols.dtype), (Zc if ctx.needs_input_grad[1] else None), None
+            return acc.to(cols.dtype), (Zc if ctx.needs_input_grad[1] else None), None, None
         geo = _axis_geometry(sizes, gY.shape[1])
         Pz = gY
         for i in range(d):
@@ -324,18 +356,20 @@ class _KronFn(torch.autograd.Function):
             if i < d - 1 or ctx.needs_input_grad[1]:
                 Pz = kron_axis_apply(Pz, cols[i], g, outer, inner)
         gX = Pz if ctx.needs_input_grad[1] else None      # K symmetric: after all d axes Pz = K gY
-        return acc.to(cols.dtype), gX, None
+        return acc.to(cols.dtype), gX, None, None
 
 
-def kron_toeplitz_matmul(cols, sizes, X):
+def kron_toeplitz_matmul(cols, sizes, X, dirs=None):
     """(T(cols[0]) x ... x T(cols[d-1])) @ X for X [m,c]; cols [d,gmax] (row i valid in its first sizes[i] entries).
-    Differentiable w.r.t. cols and X."""
+    Differentiable w.r.t. cols and X.  ``dirs`` [d,gmax] (optional): d cols[i] / d lengthscale_i; when given (and the
+    fused fp32 path applies) the backward returns a *surrogate* column gradient that is exact for parameters moving
+    cols[i] along dirs[i] or along cols[i] itself (lengthscales and scalar scales) — see ``_surrogate_col_grad``."""
     if X.dim() != 2:
         raise ValueError("kron_toeplitz_matmul: X must be [m,c]")
     if cols.dtype != X.dtype:
         raise TypeError("kron_toeplitz_matmul: cols and X must share a dtype")
     if torch.is_grad_enabled() and (cols.requires_grad or X.requires_grad):
-        return _KronFn.apply(cols, X, tuple(sizes))
+        return _KronFn.apply(cols, X, tuple(sizes), dirs)
     return _kron_mm(cols.detach().contiguous(), tuple(sizes), X.detach())
 
 

@@ -139,10 +139,11 @@ class _ShardedKronFn(torch.autograd.Function):
     """Y_loc = (K X)_loc for a row-sharded panel X (c divisible by world); complete gradient w.r.t. cols."""
 
     @staticmethod
-    def forward(ctx, cols, X, plan, comm):
+    def forward(ctx, cols, X, plan, comm, dirs=None):
         cols = cols.contiguous()
         ctx.plan, ctx.comm = plan, comm
         ctx.fused = _fused_ok(plan, X)
+        ctx.dirs = None if (dirs is None or not ctx.fused) else dirs.detach().to(cols.dtype).contiguous()
         if ctx.fused:
             # slab [g0/W, 32, 32, 32, c]: pair (2,3) is slab-local; pair (0,1) runs in the column-sharded layout
             slab = [plan.g0_loc] + plan.sizes[1:]
@@ -166,11 +167,19 @@ class _ShardedKronFn(torch.autograd.Function):
             acc = torch.zeros(d, gmax, dtype=torch.float64, device=X.device)
             slab = [plan.g0_loc] + plan.sizes[1:]
             Zc = _to_cols(gY.contiguous(), plan, comm)
+            if ctx.dirs is not None:
+                out = torch.zeros(2, 3, dtype=torch.float64, device=X.device)
+                Z01c = ops._fused_pair_grad_dir(cols, ctx.dirs, plan.sizes, 0, Zc, X23c, out[0], store=True)
+                Z01 = _to_rows(Z01c, plan, comm)
+                ops._fused_pair_grad_dir(cols, ctx.dirs, slab, 1, Z01, X, out[1], store=False)
+                comm.allreduce_(out)
+                gcols = ops._surrogate_col_grad(cols, ctx.dirs, out[:, :2].reshape(-1), out[-1, 2])
+                return gcols, None, None, None, None
             Z01c = ops._fused_pair_grad(cols, plan.sizes, 0, Zc, X23c, acc, store=True)      # axes 0, 1 (+ Z01)
             Z01 = _to_rows(Z01c, plan, comm)
             ops._fused_pair_grad(cols, slab, 1, Z01, X, acc, store=False)                     # axes 2, 3
             comm.allreduce_(acc)
-            return acc.to(cols.dtype), None, None, None
+            return acc.to(cols.dtype), None, None, None, None
         cols, X = ctx.saved_tensors
         d, gmax = cols.shape
         c = X.shape[1]
@@ -192,7 +201,7 @@ class _ShardedKronFn(torch.autograd.Function):
             if i < d - 1:
                 Pz = ops.kron_axis_apply(Pz, cols[i], g, outer, inner)
         comm.allreduce_(acc)
-        return acc.to(cols.dtype), None, None, None
+        return acc.to(cols.dtype), None, None, None, None
 
 
 class _ShardedGramFn(torch.autograd.Function):
@@ -299,7 +308,8 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         noise = self._noise()
         scale = torch.cat([(1.0 / noise).reshape(1, 1), torch.ones(plan.d - 1, 1, dtype=self.dtype, device=cols.device)])
         cols = cols * scale                                                       # Kuu / sigma^2 (:340)
-        KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm)                   # :348
+        dirs = self.covar_module.base_kernel.grid_column_dirs(self.covar_module.grid)
+        KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm, dirs)             # :348
         r = self.L_loc.shape[1]
         Q = _ShardedGramFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355
         b_full = comm.allgather(self.b_loc).reshape(plan.m, 1)

@@ -213,3 +213,30 @@ def test_q_matvec_and_cg(dt, m, r, c):
     ref = torch.linalg.solve(Q2, v.double())
     assert iters <= 200
     assert torch.allclose(x.cpu().double(), ref, **(dict(rtol=1e-6, atol=1e-7) if dt == torch.float64 else dict(rtol=1e-3, atol=1e-4)))
+
+
+def test_kron_directional_backward_matches_full_gradient():
+    """32^4 fused path: the surrogate column gradient of the directional backward has the same inner products with
+    dirs[i] and cols[i] as the full column gradient (which is all lengthscale / scale parameters see)."""
+    ops = _ops()
+    sizes, c = [32, 32, 32, 32], 16
+    m = 32 ** 4
+    gen = torch.Generator().manual_seed(7)
+    ell = torch.tensor([0.4, 0.7, 0.5, 0.9])
+    grid = torch.linspace(-1.17, 1.17, 32)
+    r = (grid - grid[0]).abs().unsqueeze(0) / ell.unsqueeze(-1)
+    cols = torch.exp(-0.5 * r * r) * 0.7
+    dirs = torch.exp(-0.5 * r * r) * r * r / ell.unsqueeze(-1)
+    X = torch.randn(m, c, generator=gen) / 30
+    Z = torch.randn(m, c, generator=gen) / 30
+    outs = []
+    for use_dirs in (False, True):
+        cg = cols.clone().to(DEV).requires_grad_(True)
+        Y = ops.kron_toeplitz_matmul(cg, sizes, X.to(DEV), dirs=dirs.to(DEV) if use_dirs else None)
+        (Y * Z.to(DEV)).sum().backward()
+        outs.append(cg.grad.cpu().double())
+    full, sur = outs
+    for i in range(4):
+        for v in (dirs[i].double(), cols[i].double()):
+            a, b = float(full[i] @ v), float(sur[i] @ v)
+            assert abs(a - b) <= 2e-3 * max(abs(a), float(full[i].abs().max() * v.abs().max())), (i, a, b)
