@@ -287,7 +287,8 @@ class GridInterpolationKernel(Kernel):
         """K_uu as a Kronecker product of Toeplitz factors (A.3); one operator per kernel batch element."""
         cols = self.base_kernel.grid_columns(self.grid)
         dirs = None
-        if cols.requires_grad and torch.is_grad_enabled() and hasattr(self.base_kernel, "grid_column_dirs"):
+        if (settings.kron_directional_grad.on() and cols.requires_grad and torch.is_grad_enabled()
+                and hasattr(self.base_kernel, "grid_column_dirs")):
             dirs = self.base_kernel.grid_column_dirs(self.grid)
         if cols.dim() == 2:
             return KroneckerToeplitzLazyTensor(cols, self.grid_sizes, dirs)

@@ -308,7 +308,8 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         noise = self._noise()
         scale = torch.cat([(1.0 / noise).reshape(1, 1), torch.ones(plan.d - 1, 1, dtype=self.dtype, device=cols.device)])
         cols = cols * scale                                                       # Kuu / sigma^2 (:340)
-        dirs = self.covar_module.base_kernel.grid_column_dirs(self.covar_module.grid)
+        dirs = self.covar_module.base_kernel.grid_column_dirs(self.covar_module.grid) \
+            if settings.kron_directional_grad.on() else None
         KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm, dirs)             # :348
         r = self.L_loc.shape[1]
         Q = _ShardedGramFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355

@@ -138,3 +138,11 @@ class root_update_mode(_value_context):
 class check_interp_bounds(_feature_flag):
     """Raise GPyTorch's out-of-bounds RuntimeError eagerly (costs one device->host flag read per call)."""
     _state = True
+
+
+class kron_directional_grad(_feature_flag):
+    """Use the directional (JVP) form of the fused Kronecker column-gradient pass (one 512-FMA direction apply + dot
+    per grid line instead of a 1024-FMA contraction; ``ops._surrogate_col_grad``).  Numerically equivalent for
+    lengthscale / scale parameters and parity-tested, but measured on B200 it is *not* faster than the full
+    contraction pass (the pass is limited by its strided 64-byte tile traffic, not by FMA count), so it is off."""
+    _state = False

@@ -370,21 +370,25 @@ def test_sharded_world1_fused_32x4_matches_single_device():
         gen = torch.Generator().manual_seed(3)
         X = torch.rand(n0 + steps, d, generator=gen) * 2 - 1
         y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen)).unsqueeze(-1)
-        with warnings.catch_warnings(), M["S"].max_cholesky_size(2048), M["S"].max_root_decomposition_size(64):
+        # the single-device model runs the directional (JVP) gradient pass, the sharded one the full contraction pass
+        with warnings.catch_warnings(), M["S"].max_cholesky_size(2048), M["S"].max_root_decomposition_size(64), \
+                M["S"].kron_directional_grad(True):
             warnings.simplefilter("ignore")
             reg = M["OnlineSKIRegression"](M["Identity"](d), X[:n0].to(_dev()), y[:n0].to(_dev()), lr=1e-2, grid_size=g,
                                            grid_bound=1.0)
-            shd = ShardedOnlineSKIRegression(X[:n0].to(_dev()), y[:n0].to(_dev()), lr=1e-2, grid_size=g, grid_bound=1.0,
-                                             comm=Comm())
+            with M["S"].kron_directional_grad(False):
+                shd = ShardedOnlineSKIRegression(X[:n0].to(_dev()), y[:n0].to(_dev()), lr=1e-2, grid_size=g,
+                                                 grid_bound=1.0, comm=Comm())
             assert shd.L_loc.shape[1] % 16 == 0
             for t in range(steps):
                 xt, yt = X[n0 + t:n0 + t + 1].to(_dev()), y[n0 + t:n0 + t + 1].to(_dev())
-                with M["S"].detach_interp_coeff(True):
+                with M["S"].detach_interp_coeff(True), M["S"].kron_directional_grad(True):
                     r1 = reg.evaluate(xt, yt)
-                r2 = shd.evaluate(xt, yt)
+                    l1 = reg.update(xt, yt)[1]
+                with M["S"].kron_directional_grad(False):
+                    r2 = shd.evaluate(xt, yt)
+                    l2 = shd.update(xt, yt)[1]
                 assert abs(r1[0] - r2[0]) <= 1e-3 * max(1, abs(r1[0])) and abs(r1[1] - r2[1]) <= 1e-3 * max(1, abs(r1[1]))
-                l1 = reg.update(xt, yt)[1]
-                l2 = shd.update(xt, yt)[1]
                 assert abs(l1 - l2) <= 1e-3 * max(1, abs(l1))
                 assert abs(float(reg.noise.mean()) - float(shd._noise())) <= 1e-4
     finally:
