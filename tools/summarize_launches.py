@@ -11,14 +11,14 @@ def short(name):
     return name[:90]
 
 
-def main(path, skip=0):
+def main(path, skip=0, count=None):
     rows = []
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     for row in csv.DictReader(lines):
         if row.get("Metric Name") == "gpu__time_duration.sum":
             rows.append((short(row["Kernel Name"]), float(row["Metric Value"]), row["Grid Size"], row["Block Size"]))
-    rows = rows[skip:]
+    rows = rows[skip:] if count is None else rows[skip:skip + count]
     tot = defaultdict(float)
     cnt = defaultdict(int)
     for n, t, _, _ in rows:
@@ -33,4 +33,4 @@ def main(path, skip=0):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0, int(sys.argv[3]) if len(sys.argv) > 3 else None)
