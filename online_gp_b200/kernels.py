@@ -256,6 +256,7 @@ class GridInterpolationKernel(Kernel):
         for i, g in enumerate(grid):
             self.register_buffer(f"grid_{i}", g)
         self._specs = {}
+        self._stencil_memo = None
 
     @property
     def grid(self):
@@ -279,8 +280,17 @@ class GridInterpolationKernel(Kernel):
         batch_shape, n, d = inputs.shape[:-2], inputs.shape[-2], inputs.shape[-1]
         if d != self.num_dims:
             raise RuntimeError(f"expected inputs with {self.num_dims} dimensions, got {d}")
-        idx, val = ops.interpolate(inputs.reshape(-1, d), self.grid_spec(),
-                                   check_bounds=settings.check_interp_bounds.on())
+        flat = inputs.reshape(-1, d)
+        # one-entry memo: the streaming loop interpolates the same batch twice (evaluate, then condition in update).
+        # The memo keeps the tensor alive, so an equal data_ptr + version means unchanged contents.
+        memo = self._stencil_memo
+        tracked = flat.requires_grad and torch.is_grad_enabled()
+        if (memo is not None and not tracked and memo[0].data_ptr() == flat.data_ptr() and memo[0].shape == flat.shape
+                and memo[0].dtype == flat.dtype and memo[0].stride() == flat.stride() and memo[1] == flat._version):
+            idx, val = memo[2], memo[3]
+        else:
+            idx, val = ops.interpolate(flat, self.grid_spec(), check_bounds=settings.check_interp_bounds.on())
+            self._stencil_memo = None if tracked else (flat.detach(), flat._version, idx, val)
         return idx.view(*batch_shape, n, -1), val.view(*batch_shape, n, -1)
 
     def _inducing_forward(self, last_dim_is_batch=False, **params):
@@ -303,7 +313,8 @@ class GridInterpolationKernel(Kernel):
             ri, rv = li, lv
         else:
             ri, rv = self._compute_grid(x2)
-        return InterpolatedLazyTensor(self._inducing_forward(), li, lv, ri, rv)
+        # K_uu is built on first use: conditioning and the eval forward only read the stencils
+        return InterpolatedLazyTensor(self._inducing_forward, li, lv, ri, rv)
 
     def forward(self, x1, x2=None, **params):
         if x1.dim() == 1:

@@ -621,10 +621,17 @@ class InterpolatedLazyTensor(LazyTensor):
 
     def __init__(self, base_lazy_tensor, left_interp_indices, left_interp_values, right_interp_indices=None,
                  right_interp_values=None):
-        self.base_lazy_tensor = base_lazy_tensor
+        # ``base_lazy_tensor`` may be given as a zero-argument callable; it is then built on first access
+        self._base = base_lazy_tensor
         self.left_interp_indices, self.left_interp_values = left_interp_indices, left_interp_values
         self.right_interp_indices = left_interp_indices if right_interp_indices is None else right_interp_indices
         self.right_interp_values = left_interp_values if right_interp_values is None else right_interp_values
+
+    @property
+    def base_lazy_tensor(self):
+        if callable(self._base) and not isinstance(self._base, LazyTensor):
+            self._base = self._base()
+        return self._base
 
     def _size(self):
         return torch.Size((*self.left_interp_indices.shape[:-1], self.right_interp_indices.shape[-2]))
@@ -640,7 +647,7 @@ class InterpolatedLazyTensor(LazyTensor):
         return ops.left_interp(li, lv, self.base_lazy_tensor._matmul(up))
 
     def _transpose_nonbatch(self):
-        return InterpolatedLazyTensor(self.base_lazy_tensor, self.right_interp_indices, self.right_interp_values,
+        return InterpolatedLazyTensor(self._base, self.right_interp_indices, self.right_interp_values,
                                       self.left_interp_indices, self.left_interp_values)
 
     def _sparse_left_interp_t(self, indices, values):

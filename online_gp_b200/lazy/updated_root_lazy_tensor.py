@@ -31,6 +31,8 @@ def _sym_factors(p):
         lam = (p * p).sum().reshape(1, 1)
         s = torch.sqrt(1.0 + lam)
         return 1.0 / (s + 1.0), -1.0 / (s * (s + 1.0))
+    if p.is_cuda and torch.cuda.is_current_stream_capturing():
+        return _sym_factors_iterative(p)        # eigh reads its status flag back on the host: not capturable
     G = p.t() @ p
     lam, V = torch.linalg.eigh(G)
     lam = lam.clamp_min(0.0)
@@ -38,6 +40,24 @@ def _sym_factors(p):
     C = (V / (s + 1.0)) @ V.t()
     Cp = (V * (-1.0 / (s * (s + 1.0)))) @ V.t()
     return C, Cp
+
+
+def _sym_factors_iterative(p, iters=10):
+    """Same factors without an eigendecomposition (no host read, so it can be captured in a CUDA graph): the
+    Denman-Beavers iteration  Y <- (Y + Z^-1) / 2,  Z <- (Z + Y^-1) / 2  on A / ||A||_F, A = I + p^T p, gives
+    Y -> A^(1/2), Z -> A^(-1/2) quadratically (Higham, Functions of Matrices, §6.3)."""
+    q = p.shape[1]
+    eye = torch.eye(q, dtype=p.dtype, device=p.device)
+    A = eye + p.t() @ p
+    c = torch.linalg.matrix_norm(A)
+    Y, Z = A / c, eye
+    for _ in range(iters):
+        Yi, _ = torch.linalg.inv_ex(Y)
+        Zi, _ = torch.linalg.inv_ex(Z)
+        Y, Z = 0.5 * (Y + Zi), 0.5 * (Z + Yi)
+    rc = c.sqrt()
+    C, _ = torch.linalg.inv_ex(eye + Y * rc)
+    return C, -((Z / rc) @ C)
 
 
 class UpdatedRootLazyTensor(LazyTensor):

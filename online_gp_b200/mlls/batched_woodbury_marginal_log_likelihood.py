@@ -39,6 +39,8 @@ class BatchedWoodburyMarginalLogLikelihood(nn.Module):
         logdet_term = inner_logdet + current_cache["D_logdet"]
 
         num_data = self.model.num_data
+        if getattr(self.model, "_num_data_t", None) is not None:
+            num_data = self.model._num_data_t       # device-side counter (CUDA-graph mode): same value, no host constant
 
         # add in add'l noise
         final_term = num_data * math.log(2 * math.pi)

@@ -262,6 +262,7 @@ class FixedNoiseOnlineSKIGP(GP):
             )
 
         self._batch_shape = _batch_shape
+        self._num_data_t = None          # optional device-side copy of ``num_data`` (OnlineSKIRegression graph mode)
         self.train_inputs = [None]
         self.train_targets = None
 
@@ -426,6 +427,8 @@ class FixedNoiseOnlineSKIGP(GP):
 
         if inplace:
             self.num_data = self.num_data + X.shape[-2]
+            if self._num_data_t is not None:
+                self._num_data_t.add_(X.shape[-2])
             self._kernel_cache = new_kernel_cache
             self._dump_caches()
         else:
@@ -541,6 +544,8 @@ class FixedNoiseOnlineSKIGP(GP):
             create_w_cache=True,
         )
         self.num_data = train_inputs.shape[-2]
+        if self._num_data_t is not None:
+            self._num_data_t.fill_(float(self.num_data))
 
     def to(self, *args, **kwargs):
         device = args[0] if args else kwargs.get("device")

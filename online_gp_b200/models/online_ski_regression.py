@@ -8,7 +8,7 @@ Same class, constructor and methods as ``online_gp/models/online_ski_regression.
 import torch
 from torch.optim.lr_scheduler import CosineAnnealingLR
 
-from .. import settings
+from .. import ops, settings
 from ..mlls.batched_woodbury_marginal_log_likelihood import BatchedWoodburyMarginalLogLikelihood
 from ..mlls.streaming_partial_mll import sm_partial_mll
 from ..settings import detach_interp_coeff
@@ -42,6 +42,7 @@ class OnlineSKIRegression(torch.nn.Module):
         self._target_batch_shape = target_batch_shape
         self.target_dim = init_y.size(-1)
         self._raw_inputs = [init_x]
+        self._graphs = None          # opt-in CUDA-graph replay of evaluate() / update(): enable_cuda_graphs()
 
     def forward(self, inputs):
         inputs = inputs.view(-1, self.stem.input_dim)
@@ -66,22 +67,33 @@ class OnlineSKIRegression(torch.nn.Module):
         pred_var = pred_var + self.gp.likelihood.second_noise.to(pred_var.dtype).reshape(1, -1)
         return pred_mean, pred_var
 
+    def _evaluate_stats(self, input_batch, target_batch):
+        """[rmse, nll] of one chunk as a device tensor (no host read)."""
+        pred_mean, pred_var = self.predict(input_batch)
+        rmse = (pred_mean - target_batch).pow(2).mean().sqrt()
+        diag_dist = torch.distributions.Normal(pred_mean, pred_var.sqrt(), validate_args=False)
+        nll = -diag_dist.log_prob(target_batch).mean()
+        return torch.stack([rmse, nll])
+
     def evaluate(self, inputs, targets):
         inputs = inputs.view(-1, self.stem.input_dim)
         targets = targets.view(-1, self.target_dim)
+        if self._graph_usable(inputs):
+            return self._evaluate_graphed(inputs, targets)
+        self._graph_phase(None)
         # Don't use `torch.no_grad` here, caches will be used for training
         self.eval()
-        rmse, nll = 0, 0
         chunks = list(zip(inputs.split(1024), targets.split(1024)))
-        num_batches = len(chunks)
-        for input_batch, target_batch in chunks:
-            pred_mean, pred_var = self.predict(input_batch)
-            rmse += (pred_mean - target_batch).pow(2).mean().sqrt().item() / num_batches
-            diag_dist = torch.distributions.Normal(pred_mean, pred_var.sqrt(), validate_args=False)
-            nll += -diag_dist.log_prob(target_batch).mean().item() / num_batches
+        # one device->host read for the whole call: the per-chunk statistics stay on the device and the interpolation
+        # bounds flags are read back after them (the reference reads rmse and nll with one .item() each, :72-77)
+        with settings.defer_interp_bounds_check(inputs.is_cuda):
+            stats = [self._evaluate_stats(input_batch, target_batch) for input_batch, target_batch in chunks]
+            rmse, nll = torch.stack(stats).mean(0).tolist()
+        ops.flush_bounds_checks()
         return rmse, nll
 
     def fit(self, inputs, targets, num_epochs, test_dataset=None):
+        self._graph_phase(None)
         records = []
         gp_lr_sched = CosineAnnealingLR(self.gp_optimizer, num_epochs, 1e-4)
         stem_lr_sched = CosineAnnealingLR(self.stem_optimizer, num_epochs, 1e-4)
@@ -117,9 +129,12 @@ class OnlineSKIRegression(torch.nn.Module):
     def update(self, inputs, targets, update_stem=True, update_gp=True):
         inputs = inputs.view(-1, self.stem.input_dim)
         targets = targets.view(-1, self.target_dim)
+        if update_gp and self._graph_usable(inputs) and self._graphs["phase"] == "evaluated":
+            return self._update_graphed(inputs, targets)
+        self._graph_phase(None)
 
         stem_loss = self._update_stem(inputs, targets) if update_stem else 0.
-        gp_loss = self._update_gp(inputs, targets) if update_gp else 0.
+        gp_loss = self._update_gp_tensor(inputs, targets) if update_gp else 0.
 
         with torch.no_grad():
             features = self.stem(inputs)
@@ -127,13 +142,18 @@ class OnlineSKIRegression(torch.nn.Module):
             self.gp.condition_on_observations(features, targets, noise_term, inplace=True)
             self._raw_inputs = [torch.cat([*self._raw_inputs, inputs])]
             self.stem.train()
-            if update_stem:
+            if update_stem and self._stem_has_batchnorm():
                 self._get_features(inputs)
 
         self.eval()
-        return stem_loss, gp_loss
+        # the loss is read back only now, with the conditioning kernels already queued behind the hyper-parameter step
+        return stem_loss, (gp_loss.item() if torch.is_tensor(gp_loss) else gp_loss)
 
-    def _update_gp(self, inputs, targets):
+    def _stem_has_batchnorm(self):
+        # `_get_features` only exists to refresh BatchNorm statistics (:133-134); without such layers it is a no-op
+        return any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in self.stem.modules())
+
+    def _update_gp_tensor(self, inputs, targets):
         self.gp_optimizer.zero_grad()
 
         self.gp.train()
@@ -147,7 +167,10 @@ class OnlineSKIRegression(torch.nn.Module):
 
         self.gp.zero_grad()
         self.gp.eval()
-        return loss.item()
+        return loss.detach()
+
+    def _update_gp(self, inputs, targets):
+        return self._update_gp_tensor(inputs, targets).item()
 
     def _update_stem(self, inputs, targets):
         self.stem_optimizer.zero_grad()
@@ -184,11 +207,14 @@ class OnlineSKIRegression(torch.nn.Module):
         return features
 
     def set_train_data(self, inputs, targets):
+        self._graph_phase(None)
         noise = torch.ones_like(targets)
         self.gp.set_train_data(inputs, targets, noise)
 
     def set_lr(self, gp_lr, stem_lr=None, bn_mom=None):
         stem_lr = gp_lr if stem_lr is None else stem_lr
+        if self._graphs is not None:
+            self.enable_cuda_graphs(True, warmup_calls=self._graphs["warm0"])     # captured graphs hold the old optimiser
         self.gp_optimizer = torch.optim.Adam(self.gp.parameters(), lr=gp_lr)
         self.stem_optimizer = torch.optim.Adam(self.stem.parameters(), lr=stem_lr)
         if bn_mom is not None:
@@ -199,3 +225,145 @@ class OnlineSKIRegression(torch.nn.Module):
     @property
     def noise(self):
         return self.gp.likelihood.noise
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the streaming step
+    # One streaming step issues ~300 kernels, most of them tiny r x r / scalar ops whose launch cost (and the stalls
+    # after every host read) the host cannot hide once the panel kernels are sharded over several GPUs.  In graph mode
+    # ``evaluate`` and ``update`` each replay one captured CUDA graph over static input buffers and read their scalar
+    # results back with a single device->host copy.  The captured sequence is exactly the eager code path above
+    # (capture runs the same Python once); everything that changes from step to step lives in device memory
+    # (panels, caches, Adam state, the observation counter ``gp._num_data_t``).
+    def enable_cuda_graphs(self, enabled=True, warmup_calls=2):
+        """Opt in / out.  The first ``warmup_calls`` evaluate/update pairs still run eagerly (library handles, lazy
+        module loading), the next pair is captured, later pairs replay.  Calls that do not fit the captured form
+        (different batch size, trainable stem, update() without a preceding evaluate()) run eagerly."""
+        if self._graphs is not None:
+            self._graphs.clear()          # drops the captured graphs and their private memory pool
+        self._graphs = None
+        if enabled:
+            self._graphs = {"eval": None, "upd": None, "q": None, "phase": None, "warm": int(warmup_calls),
+                            "warm0": int(warmup_calls), "failed": False, "replays": 0, "launches": 0}
+        return self
+
+    def _graph_phase(self, phase):
+        if self._graphs is not None:
+            self._graphs["phase"] = phase
+
+    def _graph_usable(self, inputs):
+        G = self._graphs
+        if G is None or G["failed"] or not inputs.is_cuda or inputs.shape[0] > 1024:
+            return False
+        if G["q"] is not None and inputs.shape[0] != G["q"]:
+            return False
+        if self._stem_has_batchnorm() or any(p.requires_grad for p in self.stem.parameters()):
+            return False
+        return True
+
+    def _graph_setup(self, inputs, targets):
+        G = self._graphs
+        G["q"] = inputs.shape[0]
+        G["x"] = torch.empty_like(inputs).contiguous()
+        G["y"] = torch.empty_like(targets).contiguous()
+        G["stream"] = torch.cuda.Stream(device=inputs.device)
+        G["pool"] = torch.cuda.graph_pool_handle()
+        # the observation counter moves to the device so that the MLL's n-dependent terms follow the stream
+        self.gp._num_data_t = torch.full((), float(self.gp.num_data), dtype=targets.dtype, device=inputs.device)
+        # Adam with device-side step counters (capturable); keeps the moments accumulated so far
+        opt = self.gp_optimizer
+        for group in opt.param_groups:
+            group["capturable"] = True
+        for p, st in opt.state.items():
+            if "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
+                st["step"] = st["step"].to(device=p.device, dtype=torch.float32)
+
+    def _capture(self, fn):
+        from .. import _lib
+        G = self._graphs
+        graph = torch.cuda.CUDAGraph()
+        sink = []
+        ops._BOUNDS_SINK = sink
+        l0 = _lib.load().wiski_launch_count()
+        try:
+            with torch.cuda.graph(graph, pool=G["pool"], stream=G["stream"]):
+                res = fn()
+                flags = [f.to(res.dtype) for f, _, _ in sink]
+                out = torch.cat([res.reshape(-1)] + [f.reshape(-1) for f in flags])
+        finally:
+            ops._BOUNDS_SINK = None
+        return {"graph": graph, "out": out, "n_res": res.numel(), "checks": [(x, spec) for _, x, spec in sink],
+                "launches": int(_lib.load().wiski_launch_count() - l0)}
+
+    def _replay(self, cap):
+        cap["graph"].replay()
+        G = self._graphs
+        G["replays"] += 1
+        G["launches"] += cap["launches"]
+        vals = cap["out"].tolist()                      # the one device->host read of the call
+        for k, (x, spec) in enumerate(cap["checks"]):
+            if vals[cap["n_res"] + k] != 0:
+                ops._raise_out_of_bounds(x, spec)
+        return vals[:cap["n_res"]]
+
+    def _graph_fail(self, err):
+        import warnings
+        warnings.warn(f"CUDA-graph capture failed ({type(err).__name__}: {err}); continuing eagerly", RuntimeWarning)
+        G = self._graphs
+        G["failed"] = True
+        G["eval"] = G["upd"] = None
+        self.gp._dump_caches()
+
+    def _evaluate_graphed(self, inputs, targets):
+        G = self._graphs
+        if G["eval"] is None and G["warm"] > 0:
+            G["warm"] -= 1
+            saved, self._graphs = self._graphs, None
+            try:
+                return self.evaluate(inputs, targets)
+            finally:
+                self._graphs = saved
+        if G["q"] is None:
+            self._graph_setup(inputs, targets)
+        G["x"].copy_(inputs)
+        G["y"].copy_(targets)
+        if G["eval"] is None:
+            self.eval()
+            self.gp._dump_caches()
+            try:
+                G["eval"] = self._capture(lambda: self._evaluate_stats(G["x"], G["y"]))
+            except Exception as err:            # noqa: BLE001 - any capture problem means: run eagerly
+                self._graph_fail(err)
+                return self.evaluate(inputs, targets)
+        rmse, nll = self._replay(G["eval"])
+        G["phase"] = "evaluated"
+        return rmse, nll
+
+    def _update_graphed(self, inputs, targets):
+        G = self._graphs
+        n_before = self.gp.num_data
+        G["x"].copy_(inputs)
+        G["y"].copy_(targets)
+        if G["upd"] is None:
+            def body():
+                loss = self._update_gp_tensor(G["x"], G["y"])
+                with torch.no_grad():
+                    self.gp.condition_on_observations(self.stem(G["x"]), G["y"], torch.ones_like(G["y"]), inplace=True)
+                return loss
+            try:
+                G["upd"] = self._capture(body)
+            except Exception as err:            # noqa: BLE001
+                self.gp.num_data = n_before
+                self._graph_fail(err)
+                G["phase"] = None
+                return self.update(inputs, targets)
+        (gp_loss,) = self._replay(G["upd"])
+        G["phase"] = None
+        self.gp.num_data = n_before + inputs.shape[0]
+        self.gp._dump_caches()
+        self._raw_inputs = [torch.cat([*self._raw_inputs, inputs])]
+        self.eval()
+        return 0., gp_loss
+
+    @property
+    def graph_launches(self):
+        """Kernels of this library executed through graph replays so far (bench.py adds them to gpu_launches)."""
+        return 0 if self._graphs is None else self._graphs["launches"]

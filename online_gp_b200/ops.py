@@ -8,7 +8,7 @@ from ctypes import c_double, c_float, c_int, c_int64
 
 import torch
 
-from . import _lib
+from . import _lib, settings
 
 
 def _require_cuda(*tensors):
@@ -106,12 +106,47 @@ def _interp_fwd(x, spec, check_bounds):
     h = spec.host(x.dtype)
     _call("wiski_interp_fwd", x.dtype, _ptr(x), q, spec.d, spec.h_sizes, h["lo"], h["delta"], h["first4"], h["last4"],
           h["gmin"], h["gmax"], _ptr(idx), _ptr(val), _ptr(flag), _stream())
-    if check_bounds and q > 0 and int(flag.item()) != 0:
-        xmin, xmax = x.min().item(), x.max().item()
-        raise RuntimeError(
-            "Received data that was out of bounds for the specified grid. Grid bounds were (%.3f, %.3f), but min = "
-            "%.3f, max = %.3f" % (min(spec.gmin), max(spec.gmax_v), xmin, xmax))
+    if check_bounds and q > 0:
+        if _BOUNDS_SINK is not None:
+            _BOUNDS_SINK.append((flag, x, spec))          # CUDA-graph capture: the caller reads the flag after replay
+        elif settings.defer_interp_bounds_check.on():
+            _queue_bounds_check(flag, x, spec)
+        elif int(flag.item()) != 0:
+            _raise_out_of_bounds(x, spec)
     return idx, val
+
+
+def _raise_out_of_bounds(x, spec):
+    xmin, xmax = x.min().item(), x.max().item()
+    raise RuntimeError(
+        "Received data that was out of bounds for the specified grid. Grid bounds were (%.3f, %.3f), but min = "
+        "%.3f, max = %.3f" % (min(spec.gmin), max(spec.gmax_v), xmin, xmax))
+
+
+#: set to a list while a CUDA graph is being captured (``OnlineSKIRegression._capture``): flags are collected, not read
+_BOUNDS_SINK = None
+
+#: bounds flags whose device->host read was deferred (``settings.defer_interp_bounds_check``): (event, pinned, x, spec)
+_PENDING_BOUNDS = []
+
+
+def _queue_bounds_check(flag, x, spec):
+    host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+    host.copy_(flag, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    _PENDING_BOUNDS.append((ev, host, x, spec))
+
+
+def flush_bounds_checks():
+    """Raise GPyTorch's out-of-bounds RuntimeError for any interpolation whose flag read was deferred.  Waits only
+    for the (long finished) flag copies, not for the work queued after them."""
+    while _PENDING_BOUNDS:
+        ev, host, x, spec = _PENDING_BOUNDS.pop(0)
+        ev.synchronize()
+        if int(host[0]) != 0:
+            _PENDING_BOUNDS.clear()
+            _raise_out_of_bounds(x, spec)
 
 
 class _InterpFn(torch.autograd.Function):

@@ -140,6 +140,13 @@ class check_interp_bounds(_feature_flag):
     _state = True
 
 
+class defer_interp_bounds_check(_feature_flag):
+    """Queue the out-of-bounds flag of ``ops.interpolate`` (async copy to pinned memory + event) instead of reading
+    it back at once; ``ops.flush_bounds_checks()`` raises later without stalling the stream.  Used by
+    ``OnlineSKIRegression.evaluate``, which flushes before it returns (no model state is modified in between)."""
+    _state = False
+
+
 class kron_directional_grad(_feature_flag):
     """Use the directional (JVP) form of the fused Kronecker column-gradient pass (one 512-FMA direction apply + dot
     per grid line instead of a 1024-FMA contraction; ``ops._surrogate_col_grad``).  Numerically equivalent for

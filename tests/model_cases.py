@@ -433,3 +433,128 @@ def test_full_size_grids_match_matfree_oracle(d, g, n0, q, desc):
             orc.condition_on_observations(xn, yn, torch.ones(q, dtype=torch.float64))
             model.condition_on_observations(xn.to(dt).to(_dev()), yn.to(dt).to(_dev()).unsqueeze(-1),
                                             torch.ones(q, 1, dtype=dt, device=_dev()), inplace=True)
+
+
+def test_sym_factors_iterative_matches_eigh():
+    """The capture-safe (no host read) form of the rank-q square-root factors equals the eigendecomposition form."""
+    from online_gp_b200.lazy.updated_root_lazy_tensor import _sym_factors, _sym_factors_iterative
+    gen = torch.Generator().manual_seed(3)
+    for q, scale in [(2, 0.3), (6, 1.0), (8, 5.0)]:
+        p = (torch.randn(40, q, generator=gen) * scale).to(_dev())
+        p[:, 1] = p[:, 0]                                   # rank-deficient batch (duplicate point)
+        C, Cp = _sym_factors(p)
+        C2, Cp2 = _sym_factors_iterative(p)
+        eye = torch.eye(40, dtype=p.dtype, device=p.device)
+        F, F2 = eye + p @ C @ p.t(), eye + p @ C2 @ p.t()
+        Fi, Fi2 = eye + p @ Cp @ p.t(), eye + p @ Cp2 @ p.t()
+        assert torch.allclose(F, F2, rtol=1e-9, atol=1e-9 * float(F.abs().max()))
+        assert torch.allclose(Fi, Fi2, rtol=1e-9, atol=1e-9)
+        assert torch.allclose(F2 @ F2, eye + p @ p.t(), rtol=1e-9, atol=1e-9 * float((p @ p.t()).abs().max() + 1))
+
+
+def test_stencil_memo_and_lazy_kuu():
+    """evaluate(x) followed by update(x) interpolates x once; a changed tensor (new version / new storage) misses."""
+    M = _mods()
+    from online_gp_b200 import ops
+    d, g, n0 = 2, 8, 12
+    gen = torch.Generator().manual_seed(1)
+    X = (torch.rand(n0 + 4, d, generator=gen) * 2 - 1).to(_dev())
+    y = torch.sin(3 * X.sum(-1, keepdim=True))
+    calls = []
+    orig = ops._interp_fwd
+
+    def counting(x, spec, check_bounds):
+        calls.append(x.shape[0])
+        return orig(x, spec, check_bounds)
+
+    with warnings.catch_warnings(), M["S"].max_cholesky_size(2048):
+        warnings.simplefilter("ignore")
+        reg = M["OnlineSKIRegression"](M["Identity"](d), X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0)
+        ops._interp_fwd = counting
+        try:
+            xt, yt = X[n0:n0 + 1], y[n0:n0 + 1]
+            with M["S"].detach_interp_coeff(True):
+                reg.evaluate(xt, yt)
+            reg.update(xt, yt)
+            assert calls == [1]                              # condition_on_observations reused evaluate's stencils
+            xt2 = X[n0 + 1:n0 + 2].clone()
+            reg.update(xt2, y[n0 + 1:n0 + 2])
+            assert calls == [1, 1]
+            xt2.add_(0.01)                                   # same storage, new version -> recomputed
+            reg.update(xt2, y[n0 + 1:n0 + 2])
+            assert calls == [1, 1, 1]
+        finally:
+            ops._interp_fwd = orig
+
+
+def test_cuda_graph_stream_matches_eager():
+    """Graph mode (OnlineSKIRegression.enable_cuda_graphs) replays the captured evaluate / update sequence; the stream
+    of (rmse, nll, loss), the hyper-parameters and the root panels must follow the eager model step by step.
+    fp32 at the fused 32^4 shape and fp64 on a small grid; also q = 3 (iterative square-root factors under capture)."""
+    if _dev() == "cpu":
+        pytest.skip("CUDA graphs: GPU only")
+    M = _mods()
+    for d, g, n0, q, dt, tol in [(4, 32, 24, 1, torch.float32, 2e-3), (2, 12, 30, 1, torch.float64, 1e-9),
+                                 (3, 8, 30, 3, torch.float64, 1e-8)]:
+        prev = torch.get_default_dtype()
+        torch.set_default_dtype(dt)
+        try:
+            steps = 7
+            gen = torch.Generator().manual_seed(9)
+            X = (torch.rand(n0 + steps * q, d, generator=gen) * 2 - 1).to(dt).to(_dev())
+            y = (torch.sin(3 * X.sum(-1, keepdim=True)) + 0.1 * torch.randn(n0 + steps * q, 1, generator=gen).to(dt).to(_dev()))
+            with warnings.catch_warnings(), M["S"].max_cholesky_size(2048), M["S"].max_root_decomposition_size(64):
+                warnings.simplefilter("ignore")
+                warnings.filterwarnings("error", message="CUDA-graph capture failed")   # a failed capture fails the test
+                regs = []
+                for graphs in (False, True):
+                    reg = M["OnlineSKIRegression"](M["Identity"](d), X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0)
+                    reg.set_lr(1e-2)
+                    if graphs:
+                        reg.enable_cuda_graphs(True, warmup_calls=2)
+                    regs.append(reg)
+                for t in range(steps):
+                    s = slice(n0 + t * q, n0 + (t + 1) * q)
+                    outs = []
+                    for reg in regs:
+                        with M["S"].detach_interp_coeff(True):
+                            rmse, nll = reg.evaluate(X[s], y[s])
+                        _, loss = reg.update(X[s], y[s])
+                        outs.append((rmse, nll, loss, float(reg.noise.mean())))
+                    for a, b in zip(*outs):
+                        assert abs(a - b) <= tol * max(1.0, abs(a)), (d, g, q, t, outs)
+                eager, graphed = regs
+                assert graphed._graphs["eval"] is not None and graphed._graphs["upd"] is not None
+                assert graphed._graphs["replays"] == 2 * (steps - 2) and graphed.graph_launches > 0
+                assert graphed.gp.num_data == eager.gp.num_data == n0 + steps * q
+                assert float(graphed.gp._num_data_t) == n0 + steps * q
+                Le, Lg = eager.gp._kernel_cache["WtW"].root, graphed.gp._kernel_cache["WtW"].root
+                assert torch.allclose(Le @ Le.transpose(-1, -2) if Le.shape[-2] <= 4096 else Le, Lg @ Lg.transpose(-1, -2)
+                                      if Lg.shape[-2] <= 4096 else Lg, rtol=tol * 10, atol=tol * 10 * float(Le.abs().max()))
+                # an update() without a preceding evaluate() falls back to the eager path and keeps the state in step
+                s = slice(n0, n0 + q)
+                l1 = eager.update(X[s], y[s])[1]
+                l2 = graphed.update(X[s], y[s])[1]
+                assert abs(l1 - l2) <= tol * max(1.0, abs(l1))
+                # out-of-bounds input raises from the replayed evaluate() too
+                with pytest.raises(RuntimeError, match="out of bounds"):
+                    graphed.evaluate(X[s] + 5.0, y[s])
+        finally:
+            torch.set_default_dtype(prev)
+
+
+def test_deferred_bounds_check_raises_from_evaluate():
+    M = _mods()
+    if _dev() == "cpu":
+        pytest.skip("bounds flag lives on the device")
+    d, g, n0 = 2, 8, 12
+    X = (torch.rand(n0, d) * 2 - 1).to(_dev())
+    y = torch.sin(3 * X.sum(-1, keepdim=True))
+    with warnings.catch_warnings(), M["S"].max_cholesky_size(2048):
+        warnings.simplefilter("ignore")
+        reg = M["OnlineSKIRegression"](M["Identity"](d), X, y, lr=1e-2, grid_size=g, grid_bound=1.0)
+        with pytest.raises(RuntimeError, match="out of bounds"):
+            reg.evaluate(X[:1] + 3.0, y[:1])
+        from online_gp_b200 import ops
+        assert not ops._PENDING_BOUNDS
+        reg.evaluate(X[:1], y[:1])                            # and the model keeps working afterwards
