@@ -151,7 +151,7 @@ def run_gpu(args):
     for c in ctx:
         c.__enter__()
     K, W = args.steps, args.warmup
-    need = (K + W) * 2 * q
+    need = (2 * K + W + 8) * q
     assert xs.shape[0] >= need, "stream too short"
     xd, yd = xs.to(device), ys.to(device)
     xh, yh = xs.pin_memory(), ys.pin_memory()
@@ -166,14 +166,33 @@ def run_gpu(args):
     for _ in range(W):
         one_step(model, *batch_dev(t))
         t += 1
-    # ---- device-resident timing (value) with per-op events for the roofline
     prof_names = {"wiski_kron_toeplitz_mm", "wiski_kron_toeplitz_bwd_cols", "wiski_gram", "wiski_panel_rmul",
                   "wiski_panel_lowrank_update", "wiski_gather", "wiski_scatter_add", "wiski_interp_fwd",
                   "wiski_kron_fused_pair_apply", "wiski_kron_fused_pair_grad", "wiski_kron_axis_apply",
                   "wiski_kron_axis_contract"}
-    ops.PROFILE = {"names": prof_names, "events": {}}
+    use_graphs = not args.no_graphs
+    KP = K
+    if use_graphs:
+        # graph replays run no Python, so the per-kernel CUDA-event timings behind `roofline` / `per_op_ms_per_step`
+        # come from an eager pass of the same steps on the same state, right before the timed region
+        KP = min(K, 5)
+        ops.PROFILE = {"names": prof_names, "events": {}}
+        torch.cuda.synchronize()
+        for _ in range(KP):
+            one_step(model, *batch_dev(t))
+            t += 1
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        model.enable_cuda_graphs(True, warmup_calls=1)
+        for _ in range(3):                       # 1 eager, 1 capture + first replay, 1 replay: all untimed
+            one_step(model, *batch_dev(t))
+            t += 1
+        use_graphs = model._graphs is not None and not model._graphs.failed and model._graphs.upd is not None
+    else:
+        ops.PROFILE = {"names": prof_names, "events": {}}
+    # ---- device-resident timing (value)
     clocks = ClockSampler(local_rank)
-    launches0 = lib.wiski_launch_count()
+    launches0 = lib.wiski_launch_count() + model.graph_launches
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -183,8 +202,9 @@ def run_gpu(args):
     e1.record()
     torch.cuda.synchronize()
     ms_dev = e0.elapsed_time(e1)
-    launches = lib.wiski_launch_count() - launches0
-    prof, ops.PROFILE = ops.PROFILE, None
+    launches = lib.wiski_launch_count() + model.graph_launches - launches0
+    if ops.PROFILE is not None:
+        prof, ops.PROFILE = ops.PROFILE, None
     # ---- end-to-end timing from pinned host memory
     torch.cuda.synchronize()
     e0.record()
@@ -201,7 +221,7 @@ def run_gpu(args):
     per_op = {}
     for name, evs in prof["events"].items():
         tot = sum(a.elapsed_time(bb) for a, bb, _ in evs)
-        per_op[name] = {"calls_per_step": len(evs) / K, "ms_per_step": tot / K, "ms_per_call": tot / len(evs)}
+        per_op[name] = {"calls_per_step": len(evs) / KP, "ms_per_step": tot / KP, "ms_per_call": tot / len(evs)}
     step_ms = ms_dev / K
     dom = max(per_op, key=lambda n: per_op[n]["ms_per_step"])
     hbm_peak, tf_peak, peak_src = peaks()
@@ -247,7 +267,10 @@ def run_gpu(args):
         "config": {"workload": args.workload, "description": desc, "d": d, "grid": g, "m": m, "q": q, "n_init": n_init,
                    "root_rank": r, "stencil": 4 ** d, "l2": "panels (m*r*%d B = %.2f GB each) are far larger than L2" % (b, m * r * b / 1e9),
                    "step": "evaluate + update (Adam step on Woodbury MLL + condition_on_observations)",
-                   "root_update_mode": S.root_update_mode.value()},
+                   "root_update_mode": S.root_update_mode.value(),
+                   "cuda_graphs": bool(use_graphs),
+                   "per_op_timing": ("eager pass of %d steps before the timed region (graph replays run no host code)" % KP)
+                   if not args.no_graphs else "CUDA events inside the timed region"},
         "clocks": clk,
         "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": q * (d + 1) * b,
                 "d2h_bytes_per_step": 3 * b + 4},
@@ -297,6 +320,18 @@ def run_gpu_sharded(args, rank, world, device, dtype):
     for _ in range(W):
         step(xd[t * q:(t + 1) * q], yd[t * q:(t + 1) * q])
         t += 1
+    use_graphs = not args.no_graphs
+    if use_graphs:
+        model.enable_cuda_graphs(True, warmup_calls=1)
+        for _ in range(3):                       # 1 eager, 1 capture + first replay, 1 replay: all untimed
+            step(xd[t * q:(t + 1) * q], yd[t * q:(t + 1) * q])
+            t += 1
+        ok = torch.tensor([int(model._graphs is not None and not model._graphs.failed and model._graphs.upd is not None)],
+                          device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        use_graphs = bool(ok.item())
+        if not use_graphs:
+            model.enable_cuda_graphs(False)
     clocks = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
 
     def timed(from_host):
@@ -320,9 +355,9 @@ def run_gpu_sharded(args, rank, world, device, dtype):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    l0 = lib.wiski_launch_count()
+    l0 = lib.wiski_launch_count() + model.graph_launches
     ms_dev = timed(False)
-    launches = lib.wiski_launch_count() - l0
+    launches = lib.wiski_launch_count() + model.graph_launches - l0
     ms_e2e = timed(True)
     clk = clocks.stop()
     for c in ctx:
@@ -337,7 +372,8 @@ def run_gpu_sharded(args, rank, world, device, dtype):
                        "parallelism": f"inducing-grid rows sharded over {world} GPUs (grid axis 0), r x r algebra replicated",
                        "rows_per_gpu": m // world,
                        "l2": "per-GPU panel slab (%.2f GB) larger than L2" % (m // world * r * b / 1e9),
-                       "step": "evaluate + update (Adam step on Woodbury MLL + condition_on_observations)"},
+                       "step": "evaluate + update (Adam step on Woodbury MLL + condition_on_observations)",
+                       "cuda_graphs": bool(use_graphs)},
             "clocks": clk,
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": q * (d + 1) * b,
                     "d2h_bytes_per_step": 3 * b},
@@ -437,6 +473,7 @@ def main():
     ap.add_argument("--workload", default="powerplant_4d_g32", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="run the timed steps eagerly instead of replaying CUDA graphs")
     ap.add_argument("--cpu-budget", type=float, default=30.0, help="seconds of CPU work for the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

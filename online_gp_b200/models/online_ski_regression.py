@@ -9,6 +9,7 @@ import torch
 from torch.optim.lr_scheduler import CosineAnnealingLR
 
 from .. import ops, settings
+from ..graphs import StepGraphs, make_adam_capturable
 from ..mlls.batched_woodbury_marginal_log_likelihood import BatchedWoodburyMarginalLogLikelihood
 from ..mlls.streaming_partial_mll import sm_partial_mll
 from ..settings import detach_interp_coeff
@@ -129,7 +130,7 @@ class OnlineSKIRegression(torch.nn.Module):
     def update(self, inputs, targets, update_stem=True, update_gp=True):
         inputs = inputs.view(-1, self.stem.input_dim)
         targets = targets.view(-1, self.target_dim)
-        if update_gp and self._graph_usable(inputs) and self._graphs["phase"] == "evaluated":
+        if update_gp and self._graph_usable(inputs) and self._graphs.phase == "evaluated":
             return self._update_graphed(inputs, targets)
         self._graph_phase(None)
 
@@ -214,7 +215,7 @@ class OnlineSKIRegression(torch.nn.Module):
     def set_lr(self, gp_lr, stem_lr=None, bn_mom=None):
         stem_lr = gp_lr if stem_lr is None else stem_lr
         if self._graphs is not None:
-            self.enable_cuda_graphs(True, warmup_calls=self._graphs["warm0"])     # captured graphs hold the old optimiser
+            self.enable_cuda_graphs(True, warmup_calls=self._graphs.warm0)     # captured graphs hold the old optimiser
         self.gp_optimizer = torch.optim.Adam(self.gp.parameters(), lr=gp_lr)
         self.stem_optimizer = torch.optim.Adam(self.stem.parameters(), lr=stem_lr)
         if bn_mom is not None:
@@ -226,137 +227,79 @@ class OnlineSKIRegression(torch.nn.Module):
     def noise(self):
         return self.gp.likelihood.noise
 
-    # ------------------------------------------------------------------ CUDA-graph replay of the streaming step
-    # One streaming step issues ~300 kernels, most of them tiny r x r / scalar ops whose launch cost (and the stalls
-    # after every host read) the host cannot hide once the panel kernels are sharded over several GPUs.  In graph mode
-    # ``evaluate`` and ``update`` each replay one captured CUDA graph over static input buffers and read their scalar
-    # results back with a single device->host copy.  The captured sequence is exactly the eager code path above
-    # (capture runs the same Python once); everything that changes from step to step lives in device memory
-    # (panels, caches, Adam state, the observation counter ``gp._num_data_t``).
+    # ------------------------------------------------------------------ CUDA-graph replay (online_gp_b200/graphs.py)
     def enable_cuda_graphs(self, enabled=True, warmup_calls=2):
-        """Opt in / out.  The first ``warmup_calls`` evaluate/update pairs still run eagerly (library handles, lazy
-        module loading), the next pair is captured, later pairs replay.  Calls that do not fit the captured form
-        (different batch size, trainable stem, update() without a preceding evaluate()) run eagerly."""
-        if self._graphs is not None:
-            self._graphs.clear()          # drops the captured graphs and their private memory pool
-        self._graphs = None
-        if enabled:
-            self._graphs = {"eval": None, "upd": None, "q": None, "phase": None, "warm": int(warmup_calls),
-                            "warm0": int(warmup_calls), "failed": False, "replays": 0, "launches": 0}
+        """Opt in / out of replaying ``evaluate`` / ``update`` as captured CUDA graphs.  The first ``warmup_calls``
+        evaluate/update pairs still run eagerly (library handles, lazy module loading), the next pair is captured,
+        later pairs replay.  Calls that do not fit the captured form (different batch size, trainable stem,
+        ``update()`` without a preceding ``evaluate()``) run eagerly on the same state."""
+        self._graphs = StepGraphs(warmup_calls) if enabled else None
         return self
 
     def _graph_phase(self, phase):
         if self._graphs is not None:
-            self._graphs["phase"] = phase
+            self._graphs.phase = phase
 
     def _graph_usable(self, inputs):
         G = self._graphs
-        if G is None or G["failed"] or not inputs.is_cuda or inputs.shape[0] > 1024:
+        if G is None or G.failed or not inputs.is_cuda or inputs.shape[0] > 1024:
             return False
-        if G["q"] is not None and inputs.shape[0] != G["q"]:
+        if G.q is not None and inputs.shape[0] != G.q:
             return False
         if self._stem_has_batchnorm() or any(p.requires_grad for p in self.stem.parameters()):
             return False
         return True
 
-    def _graph_setup(self, inputs, targets):
-        G = self._graphs
-        G["q"] = inputs.shape[0]
-        G["x"] = torch.empty_like(inputs).contiguous()
-        G["y"] = torch.empty_like(targets).contiguous()
-        G["stream"] = torch.cuda.Stream(device=inputs.device)
-        G["pool"] = torch.cuda.graph_pool_handle()
-        # the observation counter moves to the device so that the MLL's n-dependent terms follow the stream
-        self.gp._num_data_t = torch.full((), float(self.gp.num_data), dtype=targets.dtype, device=inputs.device)
-        # Adam with device-side step counters (capturable); keeps the moments accumulated so far
-        opt = self.gp_optimizer
-        for group in opt.param_groups:
-            group["capturable"] = True
-        for p, st in opt.state.items():
-            if "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
-                st["step"] = st["step"].to(device=p.device, dtype=torch.float32)
-
-    def _capture(self, fn):
-        from .. import _lib
-        G = self._graphs
-        graph = torch.cuda.CUDAGraph()
-        sink = []
-        ops._BOUNDS_SINK = sink
-        l0 = _lib.load().wiski_launch_count()
-        try:
-            with torch.cuda.graph(graph, pool=G["pool"], stream=G["stream"]):
-                res = fn()
-                flags = [f.to(res.dtype) for f, _, _ in sink]
-                out = torch.cat([res.reshape(-1)] + [f.reshape(-1) for f in flags])
-        finally:
-            ops._BOUNDS_SINK = None
-        return {"graph": graph, "out": out, "n_res": res.numel(), "checks": [(x, spec) for _, x, spec in sink],
-                "launches": int(_lib.load().wiski_launch_count() - l0)}
-
-    def _replay(self, cap):
-        cap["graph"].replay()
-        G = self._graphs
-        G["replays"] += 1
-        G["launches"] += cap["launches"]
-        vals = cap["out"].tolist()                      # the one device->host read of the call
-        for k, (x, spec) in enumerate(cap["checks"]):
-            if vals[cap["n_res"] + k] != 0:
-                ops._raise_out_of_bounds(x, spec)
-        return vals[:cap["n_res"]]
-
     def _graph_fail(self, err):
-        import warnings
-        warnings.warn(f"CUDA-graph capture failed ({type(err).__name__}: {err}); continuing eagerly", RuntimeWarning)
-        G = self._graphs
-        G["failed"] = True
-        G["eval"] = G["upd"] = None
+        self._graphs.fail(err)
         self.gp._dump_caches()
 
     def _evaluate_graphed(self, inputs, targets):
         G = self._graphs
-        if G["eval"] is None and G["warm"] > 0:
-            G["warm"] -= 1
-            saved, self._graphs = self._graphs, None
+        if G.eval is None and G.warm > 0:
+            G.warm -= 1
+            self._graphs = None
             try:
                 return self.evaluate(inputs, targets)
             finally:
-                self._graphs = saved
-        if G["q"] is None:
-            self._graph_setup(inputs, targets)
-        G["x"].copy_(inputs)
-        G["y"].copy_(targets)
-        if G["eval"] is None:
+                self._graphs = G
+        if G.q is None:
+            G.setup(inputs, targets)
+            # the observation counter moves to the device so that the MLL's n-dependent terms follow the stream
+            self.gp._num_data_t = torch.full((), float(self.gp.num_data), dtype=targets.dtype, device=inputs.device)
+            make_adam_capturable(self.gp_optimizer)
+        G.load(inputs, targets)
+        if G.eval is None:
             self.eval()
             self.gp._dump_caches()
             try:
-                G["eval"] = self._capture(lambda: self._evaluate_stats(G["x"], G["y"]))
+                G.eval = G.capture(lambda: self._evaluate_stats(G.x, G.y))
             except Exception as err:            # noqa: BLE001 - any capture problem means: run eagerly
                 self._graph_fail(err)
                 return self.evaluate(inputs, targets)
-        rmse, nll = self._replay(G["eval"])
-        G["phase"] = "evaluated"
+        rmse, nll = G.replay(G.eval)
+        G.phase = "evaluated"
         return rmse, nll
 
     def _update_graphed(self, inputs, targets):
         G = self._graphs
         n_before = self.gp.num_data
-        G["x"].copy_(inputs)
-        G["y"].copy_(targets)
-        if G["upd"] is None:
+        G.load(inputs, targets)
+        if G.upd is None:
             def body():
-                loss = self._update_gp_tensor(G["x"], G["y"])
+                loss = self._update_gp_tensor(G.x, G.y)
                 with torch.no_grad():
-                    self.gp.condition_on_observations(self.stem(G["x"]), G["y"], torch.ones_like(G["y"]), inplace=True)
+                    self.gp.condition_on_observations(self.stem(G.x), G.y, torch.ones_like(G.y), inplace=True)
                 return loss
             try:
-                G["upd"] = self._capture(body)
+                G.upd = G.capture(body)
             except Exception as err:            # noqa: BLE001
                 self.gp.num_data = n_before
                 self._graph_fail(err)
-                G["phase"] = None
+                G.phase = None
                 return self.update(inputs, targets)
-        (gp_loss,) = self._replay(G["upd"])
-        G["phase"] = None
+        (gp_loss,) = G.replay(G.upd)
+        G.phase = None
         self.gp.num_data = n_before + inputs.shape[0]
         self.gp._dump_caches()
         self._raw_inputs = [torch.cat([*self._raw_inputs, inputs])]
@@ -366,4 +309,4 @@ class OnlineSKIRegression(torch.nn.Module):
     @property
     def graph_launches(self):
         """Kernels of this library executed through graph replays so far (bench.py adds them to gpu_launches)."""
-        return 0 if self._graphs is None else self._graphs["launches"]
+        return 0 if self._graphs is None else self._graphs.launches

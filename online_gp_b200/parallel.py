@@ -26,6 +26,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops, settings
+from .graphs import StepGraphs, make_adam_capturable
 from .kernels import GridInterpolationKernel, RBFKernel, ScaleKernel
 from .lazy.updated_root_lazy_tensor import _sym_factors
 from .likelihoods import FNMGLikelihood
@@ -253,6 +254,8 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         self.gp_optimizer = torch.optim.Adam(self.parameters(), lr=lr)
         self._init_caches(init_x, init_y[:, 0], torch.ones_like(init_y[:, 0]))
         self._pieces = None
+        self._graphs = None          # opt-in CUDA-graph replay: enable_cuda_graphs()
+        self._n_t = None             # device-side copy of num_data (graph mode)
 
     # ---- state
     def _stencils(self, x):
@@ -343,10 +346,19 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             var = cov.diagonal().unsqueeze(-1) + P["noise"]                        # predict(): + second_noise
         return mean, var
 
-    def evaluate(self, x, y):
+    def _evaluate_stats(self, x, y):
         mean, var = self.predict(x)
-        rmse = (mean - y).pow(2).mean().sqrt().item()
-        nll = -torch.distributions.Normal(mean, var.sqrt(), validate_args=False).log_prob(y).mean().item()
+        rmse = (mean - y).pow(2).mean().sqrt()
+        nll = -torch.distributions.Normal(mean, var.sqrt(), validate_args=False).log_prob(y).mean()
+        return torch.stack([rmse, nll])
+
+    def evaluate(self, x, y):
+        if self._graph_usable(x):
+            return self._evaluate_graphed(x, y)
+        self._graph_phase(None)
+        with settings.defer_interp_bounds_check(x.is_cuda):
+            rmse, nll = self._evaluate_stats(x, y).tolist()          # one device->host read
+        ops.flush_bounds_checks()
         return rmse, nll
 
     # ---- Woodbury MLL (batched_woodbury_marginal_log_likelihood.py:19-52)
@@ -360,28 +372,103 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             logdet = logdet - logdet.detach()
         inducing_qform = (P["b_full"] * P["Kb_full"]).sum()
         inv_quad = (self.response_cache - inducing_qform + inner_qform) / P["noise"]
-        n = self.num_data
+        n = self.num_data if self._n_t is None else self._n_t
         final = n * math.log(2 * math.pi) + n * P["noise"].log()
         return -0.5 * (inv_quad + logdet + self.D_logdet + final) / n
 
     # ---- update (online_ski_regression.py:113-146)
-    def update(self, x, y):
+    def _hyper_step(self):
         self.gp_optimizer.zero_grad()
         with settings.skip_logdet_forward(True):
             loss = -self.mll()
         loss.backward()
         self.gp_optimizer.step()
         self._pieces = None
-        gp_loss = loss.item()
+        return loss.detach()
+
+    def update(self, x, y):
+        if self._graph_usable(x) and self._graphs.phase == "evaluated":
+            return self._update_graphed(x, y)
+        self._graph_phase(None)
+        loss = self._hyper_step()
         with torch.no_grad():
             self.condition_on_observations(x, y[:, 0], torch.ones_like(y[:, 0]))
-        return 0.0, gp_loss
+        return 0.0, loss.item()          # read back with the conditioning kernels already queued
 
     def condition_on_observations(self, x, y, D):
         idx_l, val_l = self._stencils(x)
-        self.response_cache = self.response_cache + (y * y / D).sum()
-        self.D_logdet = self.D_logdet + D.log().sum()
+        self.response_cache.add_((y * y / D).sum())           # in place: graph replays must see the running values
+        self.D_logdet.add_(D.log().sum())
         ops.scatter_add_(self.b_loc, idx_l, val_l, (y / D).unsqueeze(-1))
         self._root_update(idx_l, val_l / D.clamp_min(1e-7).sqrt().unsqueeze(-1))
         self.num_data += x.shape[0]
+        if self._n_t is not None:
+            self._n_t.add_(x.shape[0])
         self._pieces = None
+
+    # ---- CUDA-graph replay (online_gp_b200/graphs.py); every rank takes the same path by construction
+    def enable_cuda_graphs(self, enabled=True, warmup_calls=2):
+        self._graphs = StepGraphs(warmup_calls) if enabled else None
+        return self
+
+    def _graph_phase(self, phase):
+        if self._graphs is not None:
+            self._graphs.phase = phase
+
+    def _graph_usable(self, x):
+        G = self._graphs
+        return not (G is None or G.failed or not x.is_cuda or (G.q is not None and x.shape[0] != G.q))
+
+    def _evaluate_graphed(self, x, y):
+        G = self._graphs
+        if G.eval is None and G.warm > 0:
+            G.warm -= 1
+            self._graphs = None
+            try:
+                return self.evaluate(x, y)
+            finally:
+                self._graphs = G
+        if G.q is None:
+            G.setup(x, y)
+            self._n_t = torch.full((), float(self.num_data), dtype=self.dtype, device=x.device)
+            make_adam_capturable(self.gp_optimizer)
+        G.load(x, y)
+        if G.eval is None:
+            self._pieces = None
+            try:
+                G.eval = G.capture(lambda: self._evaluate_stats(G.x, G.y))
+            except Exception as err:            # noqa: BLE001
+                G.fail(err)
+                self._pieces = None
+                return self.evaluate(x, y)
+        rmse, nll = G.replay(G.eval)
+        G.phase = "evaluated"
+        return rmse, nll
+
+    def _update_graphed(self, x, y):
+        G = self._graphs
+        n_before = self.num_data
+        G.load(x, y)
+        if G.upd is None:
+            def body():
+                loss = self._hyper_step()
+                with torch.no_grad():
+                    self.condition_on_observations(G.x, G.y[:, 0], torch.ones_like(G.y[:, 0]))
+                return loss
+            try:
+                G.upd = G.capture(body)
+            except Exception as err:            # noqa: BLE001
+                self.num_data = n_before
+                G.fail(err)
+                G.phase = None
+                self._pieces = None
+                return self.update(x, y)
+        (loss,) = G.replay(G.upd)
+        G.phase = None
+        self.num_data = n_before + x.shape[0]
+        self._pieces = None
+        return 0.0, loss
+
+    @property
+    def graph_launches(self):
+        return 0 if self._graphs is None else self._graphs.launches

@@ -524,8 +524,8 @@ def test_cuda_graph_stream_matches_eager():
                     for a, b in zip(*outs):
                         assert abs(a - b) <= tol * max(1.0, abs(a)), (d, g, q, t, outs)
                 eager, graphed = regs
-                assert graphed._graphs["eval"] is not None and graphed._graphs["upd"] is not None
-                assert graphed._graphs["replays"] == 2 * (steps - 2) and graphed.graph_launches > 0
+                assert graphed._graphs.eval is not None and graphed._graphs.upd is not None
+                assert graphed._graphs.replays == 2 * (steps - 2) and graphed.graph_launches > 0
                 assert graphed.gp.num_data == eager.gp.num_data == n0 + steps * q
                 assert float(graphed.gp._num_data_t) == n0 + steps * q
                 Le, Lg = eager.gp._kernel_cache["WtW"].root, graphed.gp._kernel_cache["WtW"].root

@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--q", type=int, default=1)
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--graphs", action="store_true", help="replay the sharded step as CUDA graphs (eager single-GPU reference)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -47,6 +48,8 @@ def main():
     rows = []
     with S.max_root_decomposition_size(512), S.max_cholesky_size(2048):
         sh = ShardedOnlineSKIRegression(X[:args.n0], y[:args.n0], lr=1e-2, grid_size=args.g, grid_bound=1.0, comm=Comm())
+        if args.graphs:
+            sh.enable_cuda_graphs(True, warmup_calls=1)
         for t in range(args.steps):
             s = slice(args.n0 + t * args.q, args.n0 + (t + 1) * args.q)
             rmse, nll = sh.evaluate(X[s], y[s])
@@ -74,7 +77,9 @@ def main():
                 worst = max(worst, abs(u - v))
                 ok = ok and abs(u - v) <= tol
             print(json.dumps({"world": world, "d": args.d, "g": args.g, "n0": args.n0, "q": args.q, "steps": args.steps,
-                              "dtype": args.dtype, "rank_root": int(sh.L_loc.shape[1]), "rows_per_rank": int(sh.L_loc.shape[0]),
+                              "dtype": args.dtype, "cuda_graphs": bool(args.graphs and sh._graphs is not None and not sh._graphs.failed
+                                                                          and sh._graphs.upd is not None),
+                              "graph_replays": 0 if sh._graphs is None else sh._graphs.replays, "rank_root": int(sh.L_loc.shape[1]), "rows_per_rank": int(sh.L_loc.shape[0]),
                               "worst_rel_err": worst, "parity": bool(ok), "sharded": rows, "single_gpu": ref_rows}))
     if world > 1:
         flag = torch.tensor([0 if ok else 1], device=dev)
