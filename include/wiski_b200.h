@@ -98,6 +98,18 @@ int wiski_kron_axis_contract_f32(const float* Z, const float* P, int64_t g, int6
 int wiski_kron_axis_contract_f64(const double* Z, const double* P, int64_t g, int64_t outer, int64_t inner,
                                  double* acc64, void* stream);
 
+/* Tensor-core form of the same two building blocks for axes with g >= 64 points (fp32; g % 4 == 0, inner % 4 == 0,
+ * inner >= 64): an axis of that size is a real contraction (2 g flop per element), so it runs as a batched tcgen05
+ * GEMM with 3xTF32 split operands — apply: Y[o] = T X[o] with the dense symmetric Toeplitz factor built in `work`;
+ * contract: S = sum_o Z[o] P[o]^T (g x g, K-sliced partials in `work`), then acc64[k] += sum_{|a-b|=k} S[a][b].
+ * work = scratch of wiski_kron_axis_tc_work_elems(g, outer, inner, contract) floats (0 = shape not supported; use the
+ * SIMT entry points above).  This is what replaces ToeplitzLazyTensor's FFT MVM (App. A.4) on 128^3 / 256^2 / 1024^2 grids. */
+int64_t wiski_kron_axis_tc_work_elems(int64_t g, int64_t outer, int64_t inner, int contract);
+int wiski_kron_axis_apply_tc_f32(const float* X, float* Y, const float* col, int64_t g, int64_t outer, int64_t inner,
+                                 float* work, void* stream);
+int wiski_kron_axis_contract_tc_f32(const float* Z, const float* P, int64_t g, int64_t outer, int64_t inner,
+                                    double* acc64, float* work, void* stream);
+
 /* Fused fast path of k9 / k15 for grids whose axes all have 32 points (fp32, d even, c % 16 == 0; BASELINE config 2):
  * two axes per pass, grid tiles staged in shared memory.  wiski_kron_toeplitz_mm_f32 dispatches to it by itself;
  * the pair-level entry points let the autograd layer keep the intermediate panel of the forward pass.

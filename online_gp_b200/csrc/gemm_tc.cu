@@ -111,6 +111,19 @@ __host__ __device__ inline uint32_t make_idesc(bool a_mn_major, bool b_mn_major,
     return d;
 }
 
+// How a work item's slice index z maps to operand coordinates (all zero / false = plain K-sliced GEMM):
+//   K coordinate of A (B) starts at z * a_kstride (z * b_kstride);  the slice covers min(k_per_slice, Kdim - z * a_kstride);
+//   with nb > 0 a work item instead walks nb "batches" of kbpb k-blocks each: batch o = z * nb + j adds
+//   o * a_mstride (o * b_nstride) to the MN coordinate of A (B) and restarts K at 0 (sum over batches of A_o^T B_o);
+//   m_fastest orders the tiles of one slice m-tile-fastest (CTAs running together share the B tile through L2).
+struct Batching {
+    int64_t a_kstride, b_kstride;
+    int64_t a_mstride, b_nstride;
+    int64_t n_batches;      // total number of batches (nb > 0)
+    int nb, kbpb;
+    int m_fastest;
+};
+
 // ------------------------------------------------------------------------------------------------ kernel
 // Persistent: each CTA walks work items  w = blockIdx.x, blockIdx.x + gridDim.x, ...  with
 //   w -> (K slice z, m-tile, n-tile), n-tile fastest (CTAs that share an A tile / a K slice run together and share
@@ -125,7 +138,7 @@ template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
 __global__ void __launch_bounds__(384, 1)
 tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ out,
                  int64_t Mdim, int64_t Ndim, int64_t Kdim, int BN, int n_tiles_n, int n_tiles_m, int64_t n_work,
-                 int64_t k_per_slice, int64_t ld_out, int64_t slice_stride) {
+                 int64_t k_per_slice, int64_t ld_out, int64_t slice_stride, const Batching bt) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int A_BYTES = 128 * BK * 4;
@@ -170,12 +183,23 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto decode = [&](int64_t w, int64_t& m0, int64_t& n0, int64_t& kb0, int& nkb, int64_t& z) {
         z = w / tiles_per_slice;
         const int64_t t = w - z * tiles_per_slice;
-        m0 = (t / n_tiles_n) * 128;
-        n0 = (t % n_tiles_n) * (int64_t)BN;
-        kb0 = z * k_per_slice;
-        int64_t k_end = kb0 + k_per_slice;
-        if (k_end > Kdim) k_end = Kdim;
-        nkb = (int)((k_end - kb0 + BK - 1) / BK);
+        if (bt.m_fastest) {
+            m0 = (t % n_tiles_m) * 128;
+            n0 = (t / n_tiles_m) * (int64_t)BN;
+        } else {
+            m0 = (t / n_tiles_n) * 128;
+            n0 = (t % n_tiles_n) * (int64_t)BN;
+        }
+        kb0 = z * bt.a_kstride;
+        if (bt.nb > 0) {
+            int64_t nbh = bt.n_batches - z * bt.nb;
+            if (nbh > bt.nb) nbh = bt.nb;
+            nkb = (int)nbh * bt.kbpb;
+        } else {
+            int64_t k_end = kb0 + k_per_slice;
+            if (k_end > Kdim) k_end = Kdim;
+            nkb = (int)((k_end - kb0 + BK - 1) / BK);
+        }
     };
 
     if (warp == 0) {
@@ -192,19 +216,29 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
                     uint8_t* sB = sA + 2 * A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + B_BYTES));
-                    const int k = (int)(kb0 + (int64_t)kb * BK);
+                    int kA, kB, mA = (int)m0, nB = (int)n0;
+                    if (bt.nb > 0) {
+                        const int j = kb / bt.kbpb;
+                        const int64_t o = z * bt.nb + j;
+                        kA = kB = (kb - j * bt.kbpb) * BK;
+                        mA += (int)(o * bt.a_mstride);
+                        nB += (int)(o * bt.b_nstride);
+                    } else {
+                        kA = (int)(kb0 + (int64_t)kb * BK);
+                        kB = (int)(z * bt.b_kstride + (int64_t)kb * BK);
+                    }
                     if (A_KMAJOR) {
-                        tma_load_2d(sA, &tmA, &full_bar[stage], k, (int)m0);                 // box {BK k, 128 rows}
+                        tma_load_2d(sA, &tmA, &full_bar[stage], kA, mA);                     // box {BK k, 128 rows}
                     } else {
 #pragma unroll
                         for (int j = 0; j < 4; ++j)                                         // boxes {32 cols, BK rows}
-                            tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], (int)m0 + 32 * j, k);
+                            tma_load_2d(sA + j * (BK * 128), &tmA, &full_bar[stage], mA + 32 * j, kA);
                     }
                     if (B_KMAJOR) {
-                        tma_load_2d(sB, &tmB, &full_bar[stage], k, (int)n0);                 // box {BK k, BN rows}
+                        tma_load_2d(sB, &tmB, &full_bar[stage], kB, nB);                     // box {BK k, BN rows}
                     } else {
                         for (int j = 0; j < BN / 32; ++j)
-                            tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], (int)n0 + 32 * j, k);
+                            tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], nB + 32 * j, kB);
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -396,7 +430,9 @@ static inline bool tc_shape_ok(int64_t m, int64_t r, int64_t r2) {
 template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, int64_t Mdim, int64_t Ndim, int64_t Kdim,
                   int bn, int ntiles, int64_t k_per_slice, int64_t nslices, int64_t ld_out, int64_t slice_stride,
-                  cudaStream_t st, const char* name) {
+                  cudaStream_t st, const char* name, const Batching* btp = nullptr) {
+    Batching bt = {k_per_slice, k_per_slice, 0, 0, 0, 0, 0, 0};
+    if (btp != nullptr) bt = *btp;
     size_t smem = (size_t)STAGES * 2 * ((size_t)128 * BK * 4 + (size_t)bn * BK * 4) + 4 * 32 * 36 * 4 +
                   (3 * STAGES + 5) * 8 + 1024;
     auto kfn = tc_gemm3x_kernel<A_KMAJOR, B_KMAJOR, BK, STAGES>;
@@ -405,7 +441,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, in
     const int64_t n_work = (int64_t)n_tiles_m * ntiles * nslices;
     const int64_t grid = n_work < kNumSMs ? n_work : kNumSMs;
     kfn<<<(unsigned)grid, 384, smem, st>>>(tmA, tmB, out, Mdim, Ndim, Kdim, bn, ntiles, n_tiles_m, n_work, k_per_slice,
-                                           ld_out, slice_stride);
+                                           ld_out, slice_stride, bt);
     WISKI_CHECK_LAUNCH(name);
     count_launches(1);
     return 0;
@@ -462,6 +498,111 @@ int tc_panel_rmul_nt_f32(const float* P, int64_t m, int64_t r, const float* Mt, 
     if (int rc = make_map(&tmA, P, m, r, 128, false, kRmulBK)) return rc;
     if (int rc = make_map(&tmB, Mt, r2, r, bn, false, kRmulBK)) return rc;
     return launch<true, true, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, r2, 0, st, "tc_panel_rmul_nt");
+}
+
+// ------------------------------------------------------------------------------------------------ Kronecker axes
+// One Kronecker axis with g >= 64 points is a real contraction (2 g flop per element), so it runs on the tensor
+// cores as a batched GEMM over the panel viewed as [outer, g, inner]:
+//   apply     Y[o] = T X[o]                 A = T (dense symmetric Toeplitz, g x g, MN-major), B = X[o] (g x inner, MN-major)
+//   contract  S = sum_o Z[o] P[o]^T (g x g)  A = Z[o], B = P[o] (both K-major, K = inner), then acc[k] += sum_{|a-b|=k} S[a][b]
+__global__ void toeplitz_dense_kernel(const float* __restrict__ col, int g, float* __restrict__ T) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)g * g) return;
+    int a = (int)(e / g), b = (int)(e % g);
+    T[e] = col[a > b ? a - b : b - a];
+}
+
+// acc64[k] += sum_{a} S[a][a+k] (+ S[a+k][a] for k > 0); one block per diagonal
+__global__ void fold_diagonals_kernel(const float* __restrict__ S, int g, double* __restrict__ acc64) {
+    const int k = blockIdx.x;
+    double s = 0.0;
+    for (int a = threadIdx.x; a + k < g; a += blockDim.x) {
+        s += (double)S[(int64_t)a * g + a + k];
+        if (k > 0) s += (double)S[(int64_t)(a + k) * g + a];
+    }
+    __shared__ double red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+        acc64[k] += t;
+    }
+}
+
+bool tc_axis_ok(int64_t g, int64_t outer, int64_t inner) {
+    return g >= 64 && g <= 65536 && (g % 4) == 0 && (inner % 4) == 0 && inner >= 64 && outer >= 1 &&
+           outer * g < (int64_t)1 << 31 && inner < (int64_t)1 << 31;
+}
+
+static void contract_plan(int64_t g, int64_t outer, int64_t inner, int64_t* nslices, int64_t* kps, int* nb) {
+    int nt;
+    pick_bn(g, &nt);
+    const int64_t tiles = ceil_div(g, 128) * nt;
+    const int64_t want = ceil_div((int64_t)4 * kNumSMs, tiles);          // ~4 waves of work items
+    if (outer == 1) {
+        int64_t k = ceil_div(ceil_div(inner, want), 16) * 16;
+        if (k < 2048) k = 2048;
+        *kps = k;
+        *nslices = ceil_div(inner, k);
+        *nb = 0;
+    } else {
+        int64_t ns = outer < want ? outer : want;
+        *nb = (int)ceil_div(outer, ns);
+        *nslices = ceil_div(outer, (int64_t)*nb);
+        *kps = inner;
+    }
+}
+
+int64_t tc_axis_work_elems(int64_t g, int64_t outer, int64_t inner, int contract) {
+    if (!tc_axis_ok(g, outer, inner)) return 0;
+    if (!contract) return g * g;
+    int64_t nslices, kps;
+    int nb;
+    contract_plan(g, outer, inner, &nslices, &kps, &nb);
+    return (nslices + 1) * g * g;
+}
+
+int tc_axis_apply_f32(const float* X, float* Y, const float* col, int64_t g, int64_t outer, int64_t inner, float* work,
+                      cudaStream_t st) {
+    if (!tc_axis_ok(g, outer, inner)) return 3;
+    toeplitz_dense_kernel<<<(unsigned)ceil_div(g * g, 256), 256, 0, st>>>(col, (int)g, work);
+    WISKI_CHECK_LAUNCH("tc_axis_apply(toeplitz)");
+    count_launches(1);
+    CUtensorMap tmA, tmB;
+    if (int rc = make_map(&tmA, work, g, g, kGramBK, true)) return rc;
+    if (int rc = make_map(&tmB, X, outer * g, inner, kGramBK, true)) return rc;
+    int ntiles;
+    int bn = pick_bn(inner, &ntiles);
+    Batching bt = {0, g, 0, 0, 0, 0, 0, 1};
+    return launch<false, false, kGramBK, kGramStages>(tmA, tmB, Y, g, inner, g, bn, ntiles, g, outer, inner, g * inner, st,
+                                                      "tc_axis_apply", &bt);
+}
+
+int tc_axis_contract_f32(const float* Z, const float* P, int64_t g, int64_t outer, int64_t inner, double* acc64,
+                         float* work, cudaStream_t st) {
+    if (!tc_axis_ok(g, outer, inner)) return 3;
+    int64_t nslices, kps;
+    int nb;
+    contract_plan(g, outer, inner, &nslices, &kps, &nb);
+    int ntiles;
+    int bn = pick_bn(g, &ntiles);
+    CUtensorMap tmA, tmB;
+    if (int rc = make_map(&tmA, Z, outer * g, inner, 128, false, kRmulBK)) return rc;
+    if (int rc = make_map(&tmB, P, outer * g, inner, bn, false, kRmulBK)) return rc;
+    Batching bt = {kps, kps, 0, 0, 0, 0, 0, 0};
+    if (nb > 0) bt = Batching{0, 0, g, g, outer, nb, (int)ceil_div(inner, kRmulBK), 0};
+    float* parts = work + g * g;
+    if (int rc = launch<true, true, kRmulBK, kRmulStages>(tmA, tmB, parts, g, g, inner, bn, ntiles, kps, nslices, g, g * g,
+                                                          st, "tc_axis_contract", &bt))
+        return rc;
+    const int64_t n = g * g;
+    reduce_slices_kernel<float><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(parts, nslices, n, work);
+    fold_diagonals_kernel<<<(unsigned)g, 256, 0, st>>>(work, (int)g, acc64);
+    WISKI_CHECK_LAUNCH("tc_axis_contract(fold)");
+    count_launches(2);
+    return 0;
 }
 
 }  // namespace wiski

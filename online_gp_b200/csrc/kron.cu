@@ -16,6 +16,14 @@
 
 namespace wiski {
 
+// gemm_tc.cu: batched tensor-core GEMM forms of one Kronecker axis (fp32, g >= 64)
+int64_t tc_axis_work_elems(int64_t g, int64_t outer, int64_t inner, int contract);
+int tc_axis_apply_f32(const float* X, float* Y, const float* col, int64_t g, int64_t outer, int64_t inner, float* work,
+                      cudaStream_t st);
+int tc_axis_contract_f32(const float* Z, const float* P, int64_t g, int64_t outer, int64_t inner, double* acc64,
+                         float* work, cudaStream_t st);
+
+
 // kron_fused.cu: two axes per pass for 32-point axes (fp32)
 bool fused_supported(int d, const int64_t* h_g, int64_t c);
 int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, const float* X, int64_t c, float* Y,
@@ -394,6 +402,26 @@ int wiski_kron_axis_contract_f64(const double* Z, const double* P, int64_t g, in
                                  double* acc64, void* stream) {
     WISKI_CHECK_ARG(g >= 1 && outer >= 0 && inner >= 1 && acc64 != nullptr, "kron_axis_contract: bad arguments");
     return wiski::launch_axis_contract<double>(Z, P, g, outer, inner, acc64, wiski::as_stream(stream));
+}
+// tensor-core (tcgen05) form of the two building blocks for axes with g >= 64 points (gemm_tc.cu)
+int64_t wiski_kron_axis_tc_work_elems(int64_t g, int64_t outer, int64_t inner, int contract) {
+    return wiski::tc_axis_work_elems(g, outer, inner, contract);
+}
+int wiski_kron_axis_apply_tc_f32(const float* X, float* Y, const float* col, int64_t g, int64_t outer, int64_t inner,
+                                 float* work, void* stream) {
+    WISKI_CHECK_ARG(X != Y && work != nullptr, "kron_axis_apply_tc: bad arguments");
+    int rc = wiski::tc_axis_apply_f32(X, Y, col, g, outer, inner, work, wiski::as_stream(stream));
+    if (rc == 3) wiski::set_error("kron_axis_apply_tc: shape g=%lld outer=%lld inner=%lld not supported", (long long)g,
+                                  (long long)outer, (long long)inner);
+    return rc;
+}
+int wiski_kron_axis_contract_tc_f32(const float* Z, const float* P, int64_t g, int64_t outer, int64_t inner,
+                                    double* acc64, float* work, void* stream) {
+    WISKI_CHECK_ARG(acc64 != nullptr && work != nullptr, "kron_axis_contract_tc: bad arguments");
+    int rc = wiski::tc_axis_contract_f32(Z, P, g, outer, inner, acc64, work, wiski::as_stream(stream));
+    if (rc == 3) wiski::set_error("kron_axis_contract_tc: shape g=%lld outer=%lld inner=%lld not supported", (long long)g,
+                                  (long long)outer, (long long)inner);
+    return rc;
 }
 int wiski_kron_toeplitz_mm_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, const float* X, int64_t c,
                                float* Y, float* work, void* stream) {

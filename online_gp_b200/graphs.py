@@ -78,4 +78,7 @@ def make_adam_capturable(opt):
         group["capturable"] = True
     for p, st in opt.state.items():
         if "step" in st and torch.is_tensor(st["step"]) and not st["step"].is_cuda:
-            st["step"] = st["step"].to(device=p.device, dtype=torch.float32)
+            # same scalar dtype torch.optim uses for capturable state (the bias corrections are then evaluated on the
+            # device in this precision: hyper-parameters follow the eager trajectory to ~1e-7 relative, not bit-exactly)
+            sdt = torch.float64 if torch.get_default_dtype() == torch.float64 else torch.float32
+            st["step"] = st["step"].to(device=p.device, dtype=sdt)

@@ -236,11 +236,24 @@ def scatter_add_(dst, idx, val, src):
 
 
 # ---------------------------------------------------------------------------------------------- Kronecker-Toeplitz
+def _tc_axis_work(X, g, outer, inner, contract):
+    """Scratch for the tensor-core form of one Kronecker axis (fp32, g >= 64), or None if the shape is not eligible."""
+    if X.dtype != torch.float32 or not X.is_cuda or g < 64 or not settings.kron_tensor_core_axes.on():
+        return None
+    n = int(_lib.load().wiski_kron_axis_tc_work_elems(int(g), int(outer), int(inner), int(contract)))
+    return torch.empty(n, dtype=torch.float32, device=X.device) if n > 0 else None
+
+
 def _kron_mm(cols, sizes, X):
     _require_cuda(cols, X)
     d, gmax = cols.shape
     m, c = X.shape
     X = X.contiguous()
+    if X.dtype == torch.float32 and X.is_cuda and max(sizes) >= 64 and settings.kron_tensor_core_axes.on():
+        # large axes: per-axis passes, each on the tensor cores when its shape is eligible (kron_axis_apply)
+        for (g, outer, inner), col in zip(_axis_geometry(sizes, c), cols):
+            X = kron_axis_apply(X, col, g, outer, inner)
+        return X
     Y = torch.empty_like(X)
     work = torch.empty_like(X) if d > 1 else None
     h_g = (c_int64 * d)(*sizes)
@@ -413,6 +426,11 @@ def kron_axis_apply(X, col, g, outer, inner):
     _require_cuda(X, col)
     X = X.contiguous()
     Y = torch.empty_like(X)
+    work = _tc_axis_work(X, g, outer, inner, 0)
+    if work is not None:
+        _call_fn("wiski_kron_axis_apply", _lib.load().wiski_kron_axis_apply_tc_f32, _ptr(X), _ptr(Y),
+                 _ptr(col.contiguous()), int(g), int(outer), int(inner), _ptr(work), _stream())
+        return Y
     _call("wiski_kron_axis_apply", X.dtype, _ptr(X), _ptr(Y), _ptr(col.contiguous()), int(g), int(outer), int(inner),
           _stream())
     return Y
@@ -421,6 +439,11 @@ def kron_axis_apply(X, col, g, outer, inner):
 def kron_axis_contract(Z, P, g, outer, inner, acc64):
     """acc64[k] += sum over lines of sum_{|a-b|=k} Z[o,a,w] P[o,b,w]  (acc64: float64 [g], accumulated in place)."""
     _require_cuda(Z, P, acc64)
+    work = _tc_axis_work(Z, g, outer, inner, 1)
+    if work is not None:
+        _call_fn("wiski_kron_axis_contract", _lib.load().wiski_kron_axis_contract_tc_f32, _ptr(Z.contiguous()),
+                 _ptr(P.contiguous()), int(g), int(outer), int(inner), _ptr(acc64), _ptr(work), _stream())
+        return acc64
     _call("wiski_kron_axis_contract", Z.dtype, _ptr(Z.contiguous()), _ptr(P.contiguous()), int(g), int(outer), int(inner),
           _ptr(acc64), _stream())
     return acc64

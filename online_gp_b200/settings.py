@@ -140,6 +140,12 @@ class check_interp_bounds(_feature_flag):
     _state = True
 
 
+class kron_tensor_core_axes(_feature_flag):
+    """Run Kronecker axes with g >= 64 grid points (fp32) as batched tcgen05 GEMMs with 3xTF32 split operands instead
+    of the direct SIMT kernels (the 128^3, 256^2 and 1024^2 grids of BASELINE.json); off = SIMT everywhere."""
+    _state = True
+
+
 class defer_interp_bounds_check(_feature_flag):
     """Queue the out-of-bounds flag of ``ops.interpolate`` (async copy to pinned memory + event) instead of reading
     it back at once; ``ops.flush_bounds_checks()`` raises later without stalling the stream.  Used by

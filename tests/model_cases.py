@@ -494,8 +494,8 @@ def test_cuda_graph_stream_matches_eager():
     if _dev() == "cpu":
         pytest.skip("CUDA graphs: GPU only")
     M = _mods()
-    for d, g, n0, q, dt, tol in [(4, 32, 24, 1, torch.float32, 2e-3), (2, 12, 30, 1, torch.float64, 1e-9),
-                                 (3, 8, 30, 3, torch.float64, 1e-8)]:
+    for d, g, n0, q, dt, tol in [(4, 32, 24, 1, torch.float32, 2e-3), (2, 12, 30, 1, torch.float64, 1e-6),
+                                 (3, 8, 30, 3, torch.float64, 1e-6)]:
         prev = torch.get_default_dtype()
         torch.set_default_dtype(dt)
         try:

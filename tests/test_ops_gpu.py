@@ -240,3 +240,71 @@ def test_kron_directional_backward_matches_full_gradient():
         for v in (dirs[i].double(), cols[i].double()):
             a, b = float(full[i] @ v), float(sur[i] @ v)
             assert abs(a - b) <= 2e-3 * max(abs(a), float(full[i].abs().max() * v.abs().max())), (i, a, b)
+
+
+# ---- tensor-core (tcgen05, 3xTF32) form of one Kronecker axis: g >= 64, fp32
+TC_AXIS_CASES = [(64, 3, 80), (128, 1, 4096), (128, 5, 64), (256, 2, 528), (1024, 1, 2048), (1024, 3, 432),
+                 (100, 2, 68), (72, 7, 4 * 37)]
+
+
+@pytest.mark.parametrize("g,outer,inner", TC_AXIS_CASES)
+def test_kron_axis_tensor_core_apply_and_contract(g, outer, inner):
+    ops = _ops()
+    from online_gp_b200 import _lib, settings as S
+    assert _lib.load().wiski_kron_axis_tc_work_elems(g, outer, inner, 0) == g * g        # the fast path is taken
+    assert _lib.load().wiski_kron_axis_tc_work_elems(g, outer, inner, 1) >= 2 * g * g
+    gen = torch.Generator().manual_seed(g + outer + inner)
+    col = (torch.exp(-0.002 * torch.arange(g, dtype=torch.float64) ** 2) + 0.05 * torch.rand(g, generator=gen, dtype=torch.float64))
+    X = torch.randn(outer * g * inner, 1, generator=gen, dtype=torch.float32)
+    Z = torch.randn(outer * g * inner, 1, generator=gen, dtype=torch.float32)
+    ar = torch.arange(g)
+    T = col[(ar.unsqueeze(0) - ar.unsqueeze(1)).abs()]
+    X3, Z3 = X.double().reshape(outer, g, inner), Z.double().reshape(outer, g, inner)
+    ref_apply = torch.einsum("ab,obw->oaw", T, X3).reshape(-1, 1)
+    Sfull = torch.einsum("oaw,obw->ab", Z3, X3)
+    ref_acc = torch.zeros(g, dtype=torch.float64).index_add_(0, (ar.unsqueeze(0) - ar.unsqueeze(1)).abs().reshape(-1),
+                                                             Sfull.reshape(-1))
+    Xd, Zd, cd = X.to(DEV), Z.to(DEV), col.float().to(DEV)
+    out = ops.kron_axis_apply(Xd, cd, g, outer, inner)
+    scale = float(ref_apply.abs().max())
+    assert torch.allclose(out.cpu().double(), ref_apply, rtol=2e-4, atol=2e-5 * scale)
+    acc = torch.zeros(g, dtype=torch.float64, device=DEV)
+    acc += 1.0                                                # accumulates onto the caller's values
+    ops.kron_axis_contract(Zd, Xd, g, outer, inner, acc)
+    assert torch.allclose(acc.cpu() - 1.0, ref_acc, rtol=1e-3, atol=1e-4 * float(Sfull.abs().max()) * g ** 0.5)
+    # and it agrees with the SIMT kernels of the same entry points
+    with S.kron_tensor_core_axes(False):
+        out_simt = ops.kron_axis_apply(Xd, cd, g, outer, inner)
+        acc_simt = torch.zeros(g, dtype=torch.float64, device=DEV)
+        ops.kron_axis_contract(Zd, Xd, g, outer, inner, acc_simt)
+    assert torch.allclose(out, out_simt, rtol=2e-4, atol=2e-5 * scale)
+    assert torch.allclose(acc - 1.0, acc_simt, rtol=1e-3, atol=1e-4 * float(Sfull.abs().max()) * g ** 0.5)
+
+
+@pytest.mark.parametrize("sizes,c", [([128, 128], 64), ([64, 64, 64], 16), ([256, 256], 48), ([1024, 1024], 16)])
+def test_kron_large_axes_forward_backward_tensor_core(sizes, c):
+    """Full K X and its column gradient on grids with >= 64 points per axis (fp32): tensor-core path vs the fp64 oracle
+    (forward) and vs the SIMT path (gradient)."""
+    ops = _ops()
+    from online_gp_b200 import settings as S
+    d = len(sizes)
+    m = int(np.prod(sizes))
+    grid = create_grid(sizes, [(-1.1, 1.1)] * d)
+    hyp = Hypers(d, kind="rbf")
+    cols = [cc.detach() for cc in kuu_columns(grid, hyp)]
+    gen = torch.Generator().manual_seed(m + c)
+    X = torch.randn(m, c, generator=gen, dtype=torch.float32)
+    Z = torch.randn(m, c, generator=gen, dtype=torch.float32)
+    ref = o_kron([cc.double() for cc in cols], X.double())
+    grads = []
+    for tc in (True, False):
+        with S.kron_tensor_core_axes(tc):
+            cg = _pad_cols(cols, torch.float32).to(DEV).requires_grad_(True)
+            out = ops.kron_toeplitz_matmul(cg, sizes, X.to(DEV))
+            (out * Z.to(DEV)).sum().backward()
+            grads.append(cg.grad.clone())
+            assert torch.allclose(out.detach().cpu().double(), ref, rtol=2e-4, atol=2e-5 * float(ref.abs().max()))
+            with torch.no_grad():
+                out2 = ops.kron_toeplitz_matmul(cg.detach(), sizes, X.to(DEV))
+            assert torch.allclose(out2, out.detach(), rtol=1e-5, atol=1e-5 * float(ref.abs().max()))
+    assert torch.allclose(grads[0], grads[1], rtol=1e-3, atol=1e-4 * float(grads[1].abs().max()))
