@@ -135,6 +135,10 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # the row <-> column exchanges are large point-to-point transfers: let NCCL spread them over enough channels
+        # to fill NVLink 5 (its default of a few p2p channels per peer reaches ~200 GB/s of the 900 GB/s per direction)
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "64")
         dist.init_process_group("nccl", device_id=device)
     d, g, q, n_init, desc = WORKLOADS[args.workload]
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
@@ -278,11 +282,42 @@ def run_gpu(args):
         "roofline": roof,
         "per_op_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_op.items())},
     }
+    out["cg_mvm"] = cg_mvm_roofline(model, m, r, b, hbm_peak, peak_src)
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_budget)
     for c in ctx:
         c.__exit__(None, None, None)
     print(json.dumps(out))
+
+
+def cg_mvm_roofline(model, m, r, b, hbm_peak, peak_src, reps=20):
+    """BASELINE.json's second metric: achieved GB/s of the CG matrix-vector product  w = (I + L^T K L) v  — the closure
+    GPyTorch's linear_cg calls — as one fused pass over the two m x r panels (wiski_q_matvec), and
+    of the panel Kronecker-Toeplitz MVM  K L  that feeds it.  CUDA events around `reps` back-to-back launches on the
+    model's own panels (3.6 GB per launch: far larger than L2)."""
+    from online_gp_b200 import ops
+    with torch.no_grad():
+        L = model.gp._root_panels()[0]
+        K = model.gp.Kuu.items[0].detach()
+        KL = K._matmul(L)
+        v = torch.randn(r, 1, dtype=L.dtype, device=L.device)
+        res = {}
+        for name, fn, nbytes in (("q_matvec", lambda: ops.q_matvec(L, KL, v), 2.0 * m * r * b),
+                                 ("kron_toeplitz_mm_panel", lambda: K._matmul(L), 2.0 * m * r * b)):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            res[name] = {"ms_per_call": ms, "algorithmic_bytes_per_call": nbytes, "achieved": gbs, "unit": "GB/s",
+                         "peak": hbm_peak, "frac": gbs / hbm_peak, "peak_source": peak_src}
+        model.gp._dump_caches()
+    return res
 
 
 def run_gpu_sharded(args, rank, world, device, dtype):
@@ -380,8 +415,14 @@ def run_gpu_sharded(args, rank, world, device, dtype):
             "gpu_launches": int(launches),
             "roofline": None,
         }
-        print(json.dumps(out))
-    dist.destroy_process_group()
+        print(json.dumps(out), flush=True)
+    # captured graphs hold NCCL work: release them (and everything queued) before the communicator is torn down
+    model.enable_cuda_graphs(False)
+    del model
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0)          # skip interpreter teardown: destroying the process group under live CUDA-graph state can hang
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)

@@ -123,6 +123,17 @@ int wiski_kron_fused_pair_grad_f32(const float* cols, int d, const int64_t* h_g,
                                    const float* P, float* Zout, int64_t c, double* acc_u64, double* acc_v64,
                                    void* stream);
 
+/* The same two passes with explicit operand layouts, for the row <-> column exchange of the row-sharded multi-GPU
+ * path: h_lay holds (ld, cw, cstride) per operand — X, Y for pair_apply; Z, P, Zout for pair_grad — where element
+ * (row, col) of the operand lives at ptr + (col / cw) * cstride + row * ld + col % cw.  Plain row-major is
+ * (c, c, 0); "column-chunked" (cw = c / world, ld = cw, cstride = rows * cw) is the send / receive buffer of an
+ * all-to-all, so no transposing copy is needed on either side of the collective.  cw % 16 == 0, ld, cstride % 4 == 0. */
+int wiski_kron_fused_pair_apply_lay_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair,
+                                        const float* X, float* Y, int64_t c, const int64_t* h_lay, void* stream);
+int wiski_kron_fused_pair_grad_lay_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair,
+                                       const float* Z, const float* P, float* Zout, int64_t c, double* acc_u64,
+                                       double* acc_v64, const int64_t* h_lay, void* stream);
+
 /* Directional form of pair_grad: with dirs [d,gmax] = d col_i / d lengthscale_i it returns, accumulated into out3
  * (3 doubles):  <grad_{2p}, dirs_{2p}>, <grad_{2p+1}, dirs_{2p+1}> and <Z', K' P'> (= <grad_i, col_i> for every i),
  * which is all a stationary product kernel with one lengthscale per dimension and scalar scales needs; it replaces

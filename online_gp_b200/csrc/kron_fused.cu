@@ -162,6 +162,18 @@ struct PairGeom {
     int64_t n_tiles;     // n_before * sv * n_chunks
 };
 
+// Where element (row, col) of an operand panel lives: plain row-major (ld = cw = c, cstride = 0) or column-chunked —
+// columns cut into blocks of cw, block j a row-major [rows, cw] matrix at ptr + j * cstride (the send / receive
+// layout of the row <-> column all-to-all of the sharded path, online_gp_b200/parallel.py).  cw % 16 == 0, so a
+// 16-column tile never straddles two blocks.
+struct PanelLay {
+    int64_t ld, cw, cstride;
+};
+__device__ __forceinline__ int64_t tile_offset(const PanelLay& l, int64_t col0) {
+    const int64_t j = col0 / l.cw;
+    return j * l.cstride + (col0 - j * l.cw);
+}
+
 __device__ __forceinline__ void tile_coords(const PairGeom& g, int64_t tile, int64_t& rowbase, int64_t& col0) {
     int64_t cc = tile % g.n_chunks;
     int64_t o = tile / g.n_chunks;
@@ -175,14 +187,14 @@ __device__ __forceinline__ void tile_coords(const PairGeom& g, int64_t tile, int
 // both the global and the shared address advance by a constant stride (no per-piece index arithmetic).
 template <int NT>
 __device__ __forceinline__ void load_tile_async(float* buf, const float* __restrict__ X, const PairGeom& g,
-                                                int64_t rowbase, int64_t col0) {
+                                                int64_t rowbase, int64_t col0, const PanelLay& lay) {
     static_assert(NT % 128 == 0, "NT must be a multiple of 128");
     constexpr int USTEP = NT / 128;
     const int q = threadIdx.x;
     const int part = q & 3, v = (q >> 2) & 31, u0 = q >> 7;
-    const float* src = X + (rowbase + ((int64_t)u0 * G + v) * g.sv) * g.c + col0 + part * 4;
+    const float* src = X + tile_offset(lay, col0) + (rowbase + ((int64_t)u0 * G + v) * g.sv) * lay.ld + part * 4;
     float* dst = buf + u0 * UP + v * CB + part * 4;
-    const int64_t sstride = (int64_t)USTEP * G * g.sv * g.c;
+    const int64_t sstride = (int64_t)USTEP * G * g.sv * lay.ld;
 #pragma unroll
     for (int k = 0; k < G / USTEP; ++k) {
         cp_async16(dst, src);
@@ -194,24 +206,25 @@ __device__ __forceinline__ void load_tile_async(float* buf, const float* __restr
 // ------------------------------------------------------------------ Y = (T_u x T_v) X   (forward pair apply)
 // slot 0 = factor of axis u, slot 1 = factor of axis v.
 template <int NT>   // NT must be 256 (two lines per thread and phase)
-__global__ void __launch_bounds__(NT, 1) pair_apply_kernel(const float* __restrict__ X, float* __restrict__ Y, PairGeom g) {
+__global__ void __launch_bounds__(NT, 1) pair_apply_kernel(const float* __restrict__ X, float* __restrict__ Y, PairGeom g,
+                                                           PanelLay lx, PanelLay ly) {
     extern __shared__ __align__(16) float smem[];
     int64_t tile = blockIdx.x;
     int it = 0;
     if (tile < g.n_tiles) {
         int64_t rb, c0;
         tile_coords(g, tile, rb, c0);
-        load_tile_async<NT>(smem, X, g, rb, c0);
+        load_tile_async<NT>(smem, X, g, rb, c0, lx);
     }
     cp_async_commit();
-    const int64_t ustride = (int64_t)G * g.sv * g.c;      // elements between consecutive u rows in global memory
+    const int64_t ustride = (int64_t)G * g.sv * ly.ld;    // elements between consecutive u rows of the output
     for (; tile < g.n_tiles; tile += gridDim.x, ++it) {
         float* buf = smem + (it & 1) * TILE_FLOATS;       // derived from the __shared__ base so that LDS/STS are emitted
         int64_t next = tile + gridDim.x;
         if (next < g.n_tiles) {
             int64_t rb, c0;
             tile_coords(g, next, rb, c0);
-            load_tile_async<NT>(smem + ((it + 1) & 1) * TILE_FLOATS, X, g, rb, c0);
+            load_tile_async<NT>(smem + ((it + 1) & 1) * TILE_FLOATS, X, g, rb, c0, lx);
         }
         cp_async_commit();
         cp_async_wait<1>();
@@ -242,8 +255,8 @@ __global__ void __launch_bounds__(NT, 1) pair_apply_kernel(const float* __restri
 #pragma unroll
             for (int u = 0; u < G; ++u) { x0[u] = p0[u * UP]; x1[u] = p1[u * UP]; }
             sym_apply32x2<0>(x0, x1);
-            float* yp0 = Y + (rb + (int64_t)v * g.sv) * g.c + c0 + w;
-            float* yp1 = yp0 + (int64_t)(NT / CB) * g.sv * g.c;
+            float* yp0 = Y + tile_offset(ly, c0) + (rb + (int64_t)v * g.sv) * ly.ld + w;
+            float* yp1 = yp0 + (int64_t)(NT / CB) * g.sv * ly.ld;
 #pragma unroll
             for (int u = 0; u < G; ++u) {
                 *yp0 = x0[u];
@@ -263,7 +276,7 @@ __global__ void __launch_bounds__(NT, 1) pair_apply_kernel(const float* __restri
 template <bool STORE>
 __global__ void __launch_bounds__(256, 1)
 pair_grad_kernel(const float* __restrict__ Z, const float* __restrict__ P, float* __restrict__ Zout, PairGeom g,
-                 double* __restrict__ acc_u64, double* __restrict__ acc_v64) {
+                 double* __restrict__ acc_u64, double* __restrict__ acc_v64, PanelLay lz, PanelLay lp, PanelLay lo) {
     constexpr int NT = 256;
     extern __shared__ __align__(16) float smem[];
     float* zt = smem;
@@ -275,8 +288,8 @@ pair_grad_kernel(const float* __restrict__ Z, const float* __restrict__ P, float
     for (int64_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
         int64_t rb, c0;
         tile_coords(g, tile, rb, c0);
-        load_tile_async<NT>(zt, Z, g, rb, c0);
-        load_tile_async<NT>(pt, P, g, rb, c0);
+        load_tile_async<NT>(zt, Z, g, rb, c0, lz);
+        load_tile_async<NT>(pt, P, g, rb, c0, lp);
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
@@ -312,9 +325,9 @@ pair_grad_kernel(const float* __restrict__ Z, const float* __restrict__ P, float
             contract32(z, p, acc_v);
             if (STORE) {
                 sym_apply32<1>(z);
-                float* yp = Zout + (rb + (int64_t)u * G * g.sv) * g.c + c0 + w;
+                float* yp = Zout + tile_offset(lo, c0) + (rb + (int64_t)u * G * g.sv) * lo.ld + w;
 #pragma unroll
-                for (int v = 0; v < G; ++v) yp[(int64_t)v * g.sv * g.c] = z[v];
+                for (int v = 0; v < G; ++v) yp[(int64_t)v * g.sv * lo.ld] = z[v];
             }
         }
         __syncthreads();
@@ -356,11 +369,12 @@ pair_grad_jvp_kernel(const float* __restrict__ Z, const float* __restrict__ P, f
     float* st = smem + 2 * TILE_FLOATS;
     float su = 0.f, sv = 0.f, ss = 0.f;
     const int64_t vstride = g.sv * g.c;
+    const PanelLay plain = {g.c, g.c, 0};
     for (int64_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
         int64_t rb, c0;
         tile_coords(g, tile, rb, c0);
-        load_tile_async<NT>(zt, Z, g, rb, c0);
-        load_tile_async<NT>(pt, P, g, rb, c0);
+        load_tile_async<NT>(zt, Z, g, rb, c0, plain);
+        load_tile_async<NT>(pt, P, g, rb, c0, plain);
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads();
@@ -448,6 +462,20 @@ static bool make_geom(PairGeom& g, int d, const int64_t* h_g, int pair, int64_t 
     return true;
 }
 
+// h_lay: 3 int64 per operand (ld, cw, cstride), nullptr = every operand plain row-major [m, c]
+static bool make_lays(PanelLay* out, int n, const int64_t* h_lay, int64_t c) {
+    for (int i = 0; i < n; ++i) {
+        if (h_lay == nullptr) {
+            out[i] = PanelLay{c, c, 0};
+        } else {
+            out[i] = PanelLay{h_lay[3 * i], h_lay[3 * i + 1], h_lay[3 * i + 2]};
+            if (out[i].cw < CB || out[i].cw % CB != 0 || out[i].ld % 4 != 0 || out[i].cstride % 4 != 0 || out[i].ld < 1)
+                return false;
+        }
+    }
+    return true;
+}
+
 bool fused_supported(int d, const int64_t* h_g, int64_t c) {
     if (d < 2 || (d % 2) != 0 || c % CB != 0 || c < CB) return false;
     for (int i = 0; i < d; ++i)
@@ -471,7 +499,8 @@ int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, co
         float* dst = (p % 2 == 0) ? Y : work;
         if (int rc = set_coefficients(cols + (int64_t)(2 * p) * gmax, cols + (int64_t)(2 * p + 1) * gmax, st)) return rc;
         int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
-        kfn<<<(unsigned)grid, 256, smem, st>>>(src, dst, g);
+        const PanelLay plain = {c, c, 0};
+        kfn<<<(unsigned)grid, 256, smem, st>>>(src, dst, g, plain, plain);
         WISKI_CHECK_LAUNCH("kron_fused(pair_apply)");
         count_launches(1);
         src = dst;
@@ -481,15 +510,17 @@ int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, co
 
 // One forward pair pass: Y = (T_{2 pair} x T_{2 pair + 1}) X.
 int fused_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X, float* Y,
-                     int64_t c, cudaStream_t st) {
+                     int64_t c, cudaStream_t st, const int64_t* h_lay = nullptr) {
     PairGeom g;
     if (!make_geom(g, d, h_g, pair, c)) { set_error("kron_fused: unsupported shape"); return 3; }
+    PanelLay lay[2];
+    if (!make_lays(lay, 2, h_lay, c)) { set_error("kron_fused: bad operand layout"); return 1; }
     if (int rc = set_coefficients(cols + (int64_t)(2 * pair) * gmax, cols + (int64_t)(2 * pair + 1) * gmax, st)) return rc;
     size_t smem = 2 * TILE_FLOATS * sizeof(float);
     auto kfn = pair_apply_kernel<256>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
     int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
-    kfn<<<(unsigned)grid, 256, smem, st>>>(X, Y, g);
+    kfn<<<(unsigned)grid, 256, smem, st>>>(X, Y, g, lay[0], lay[1]);
     WISKI_CHECK_LAUNCH("kron_fused(pair_apply)");
     count_launches(1);
     return 0;
@@ -497,20 +528,23 @@ int fused_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax,
 
 // One backward pair pass (see pair_grad_kernel).  acc_u64 / acc_v64: g doubles each, accumulated.
 int fused_pair_grad(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z, const float* P,
-                    float* Zout, int64_t c, double* acc_u64, double* acc_v64, cudaStream_t st) {
+                    float* Zout, int64_t c, double* acc_u64, double* acc_v64, cudaStream_t st,
+                    const int64_t* h_lay = nullptr) {
     PairGeom g;
     if (!make_geom(g, d, h_g, pair, c)) { set_error("kron_fused: unsupported shape"); return 3; }
+    PanelLay lay[3];
+    if (!make_lays(lay, 3, h_lay, c)) { set_error("kron_fused: bad operand layout"); return 1; }
     if (int rc = set_coefficients(cols + (int64_t)(2 * pair) * gmax, cols + (int64_t)(2 * pair + 1) * gmax, st)) return rc;
     size_t smem = 3 * TILE_FLOATS * sizeof(float);
     int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
     if (Zout != nullptr) {
         auto kfn = pair_grad_kernel<true>;
         WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
-        kfn<<<(unsigned)grid, 256, smem, st>>>(Z, P, Zout, g, acc_u64, acc_v64);
+        kfn<<<(unsigned)grid, 256, smem, st>>>(Z, P, Zout, g, acc_u64, acc_v64, lay[0], lay[1], lay[2]);
     } else {
         auto kfn = pair_grad_kernel<false>;
         WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
-        kfn<<<(unsigned)grid, 256, smem, st>>>(Z, P, nullptr, g, acc_u64, acc_v64);
+        kfn<<<(unsigned)grid, 256, smem, st>>>(Z, P, nullptr, g, acc_u64, acc_v64, lay[0], lay[1], lay[2]);
     }
     WISKI_CHECK_LAUNCH("kron_fused(pair_grad)");
     count_launches(1);
@@ -566,6 +600,26 @@ int wiski_kron_fused_pair_apply_f32(const float* cols, int d, const int64_t* h_g
         return 3;
     }
     return wiski::fused_pair_apply(cols, d, h_g, gmax, pair, X, Y, c, wiski::as_stream(stream));
+}
+
+int wiski_kron_fused_pair_apply_lay_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair,
+                                        const float* X, float* Y, int64_t c, const int64_t* h_lay, void* stream) {
+    if (d < 2 || d > WISKI_MAX_DIMS || pair < 0 || 2 * pair + 1 >= d || X == Y || h_lay == nullptr) {
+        wiski::set_error("kron_fused_pair_apply_lay: unsupported shape");
+        return 3;
+    }
+    return wiski::fused_pair_apply(cols, d, h_g, gmax, pair, X, Y, c, wiski::as_stream(stream), h_lay);
+}
+
+int wiski_kron_fused_pair_grad_lay_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair,
+                                       const float* Z, const float* P, float* Zout, int64_t c, double* acc_u64,
+                                       double* acc_v64, const int64_t* h_lay, void* stream) {
+    if (d < 2 || d > WISKI_MAX_DIMS || pair < 0 || 2 * pair + 1 >= d || h_lay == nullptr) {
+        wiski::set_error("kron_fused_pair_grad_lay: unsupported shape");
+        return 3;
+    }
+    return wiski::fused_pair_grad(cols, d, h_g, gmax, pair, Z, P, Zout, c, acc_u64, acc_v64, wiski::as_stream(stream),
+                                  h_lay);
 }
 
 int wiski_kron_fused_pair_grad_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,

@@ -294,21 +294,52 @@ def _fused_supported(sizes, X):
     return bool(_lib.load().wiski_kron_fused_supported(len(sizes), h_g, X.shape[1]))
 
 
-def _fused_pair_apply(cols, sizes, pair, X):
+def _lay_array(c, *chunked):
+    """(ld, cw, cstride) per operand for the *_lay entry points; `chunked` item = None (plain [m, c]) or (W, m):
+    column-chunked [W, m, c / W] (block j = columns [j c/W, (j+1) c/W), row-major with pitch c / W)."""
+    vals = []
+    for ch in chunked:
+        if ch is None:
+            vals += [c, c, 0]
+        else:
+            W, m = ch
+            vals += [c // W, c // W, m * (c // W)]
+    return (c_int64 * len(vals))(*[int(v) for v in vals])
+
+
+def _fused_pair_apply(cols, sizes, pair, X, chunk_out=1):
+    """Y = (T_2p x T_2p+1) X for X [m, c].  chunk_out = W > 1: Y is written column-chunked, [W, m, c / W] (the send
+    buffer of the row -> column all-to-all of the sharded path: no transposing copy)."""
     d, gmax = cols.shape
-    Y = torch.empty_like(X)
+    m, c = X.shape
     h_g = (c_int64 * d)(*sizes)
+    if chunk_out > 1:
+        if c % (16 * chunk_out) != 0:
+            raise ValueError("column-chunked output needs c % (16 * chunks) == 0")
+        Y = torch.empty(chunk_out, m, c // chunk_out, dtype=X.dtype, device=X.device)
+        _call_fn("wiski_kron_fused_pair_apply", _lib.load().wiski_kron_fused_pair_apply_lay_f32, _ptr(cols), d, h_g, gmax,
+                 pair, _ptr(X), _ptr(Y), c, _lay_array(c, None, (chunk_out, m)), _stream())
+        return Y
+    Y = torch.empty_like(X)
     _call_fn("wiski_kron_fused_pair_apply", _lib.load().wiski_kron_fused_pair_apply_f32, _ptr(cols), d, h_g, gmax, pair,
-             _ptr(X), _ptr(Y), X.shape[1], _stream())
+             _ptr(X), _ptr(Y), c, _stream())
     return Y
 
 
-def _fused_pair_grad(cols, sizes, pair, Z, P, acc, store):
+def _fused_pair_grad(cols, sizes, pair, Z, P, acc, store, chunk_z=1):
+    """One backward pair pass (wiski_kron_fused_pair_grad).  chunk_z = W > 1: Z is given column-chunked [W, m, c / W]
+    (as received from the column -> row all-to-all); P and the returned Zout are plain [m, c]."""
     d, gmax = cols.shape
-    Zout = torch.empty_like(Z) if store else None
+    m, c = P.shape
+    Zout = torch.empty_like(P) if store else None
     h_g = (c_int64 * d)(*sizes)
+    if chunk_z > 1:
+        _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_fused_pair_grad_lay_f32, _ptr(cols), d, h_g, gmax,
+                 pair, _ptr(Z), _ptr(P), _ptr(Zout), c, _ptr(acc[2 * pair]), _ptr(acc[2 * pair + 1]),
+                 _lay_array(c, (chunk_z, m), None, None), _stream())
+        return Zout
     _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_fused_pair_grad_f32, _ptr(cols), d, h_g, gmax, pair,
-             _ptr(Z), _ptr(P), _ptr(Zout), Z.shape[1], _ptr(acc[2 * pair]), _ptr(acc[2 * pair + 1]), _stream())
+             _ptr(Z), _ptr(P), _ptr(Zout), c, _ptr(acc[2 * pair]), _ptr(acc[2 * pair + 1]), _stream())
     return Zout
 
 

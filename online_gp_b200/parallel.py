@@ -137,50 +137,58 @@ def _fused_ok(plan, X):
 
 
 class _ShardedKronFn(torch.autograd.Function):
-    """Y_loc = (K X)_loc for a row-sharded panel X (c divisible by world); complete gradient w.r.t. cols."""
+    """(K X)_loc for a row-sharded panel X (c divisible by world); complete gradient w.r.t. cols.
+
+    The result is returned as column *blocks* ``[nb, m_loc, c / nb]`` (block j = columns [j c/nb, (j+1) c/nb)):
+    on the fused path nb = world and the blocks are exactly the receive buffer of the column -> row all-to-all, so
+    neither side of either exchange needs a transposing copy (the pair kernels read / write the chunked layout
+    directly, ``wiski_kron_fused_pair_*_lay_f32``); otherwise nb = 1."""
 
     @staticmethod
     def forward(ctx, cols, X, plan, comm, dirs=None):
         cols = cols.contiguous()
         ctx.plan, ctx.comm = plan, comm
         ctx.fused = _fused_ok(plan, X)
-        ctx.dirs = None if (dirs is None or not ctx.fused) else dirs.detach().to(cols.dtype).contiguous()
+        ctx.dirs = None if (dirs is None or not ctx.fused or plan.world > 1) else dirs.detach().to(cols.dtype).contiguous()
+        W = plan.world
         if ctx.fused:
             # slab [g0/W, 32, 32, 32, c]: pair (2,3) is slab-local; pair (0,1) runs in the column-sharded layout
             slab = [plan.g0_loc] + plan.sizes[1:]
-            X23 = ops._fused_pair_apply(cols, slab, 1, X.contiguous())
-            X23c = _to_cols(X23, plan, comm)
+            cw = X.shape[1] // W
+            X23s = ops._fused_pair_apply(cols, slab, 1, X.contiguous(), chunk_out=W)         # [W, m_loc, cw] send layout
+            X23c = comm.all_to_all(X23s.view(W, plan.m_loc, cw)).view(W * plan.m_loc, cw)     # all rows of my columns
             Yc = ops._fused_pair_apply(cols, plan.sizes, 0, X23c)
             ctx.save_for_backward(cols, X, X23c)
-            return _to_rows(Yc, plan, comm)
+            return comm.all_to_all(Yc.view(W, plan.m_loc, cw))                                # [W, m_loc, cw] blocks
         ctx.save_for_backward(cols, X)
         Y = _apply_local_axes(X, cols, plan)
         Yc = _to_cols(Y, plan, comm)
         Yc = ops.kron_axis_apply(Yc, cols[0], plan.sizes[0], 1, Yc.numel() // plan.sizes[0])
-        return _to_rows(Yc, plan, comm)
+        return _to_rows(Yc, plan, comm).unsqueeze(0)
 
     @staticmethod
-    def backward(ctx, gY):
+    def backward(ctx, gYb):
         plan, comm = ctx.plan, ctx.comm
+        W = plan.world
         if ctx.fused:
             cols, X, X23c = ctx.saved_tensors
             d, gmax = cols.shape
             acc = torch.zeros(d, gmax, dtype=torch.float64, device=X.device)
             slab = [plan.g0_loc] + plan.sizes[1:]
-            Zc = _to_cols(gY.contiguous(), plan, comm)
-            if ctx.dirs is not None:
+            cw = X.shape[1] // W
+            Zc = comm.all_to_all(gYb.contiguous()).view(W * plan.m_loc, cw)
+            if ctx.dirs is not None:            # world == 1 only
                 out = torch.zeros(2, 3, dtype=torch.float64, device=X.device)
-                Z01c = ops._fused_pair_grad_dir(cols, ctx.dirs, plan.sizes, 0, Zc, X23c, out[0], store=True)
-                Z01 = _to_rows(Z01c, plan, comm)
+                Z01 = ops._fused_pair_grad_dir(cols, ctx.dirs, plan.sizes, 0, Zc, X23c, out[0], store=True)
                 ops._fused_pair_grad_dir(cols, ctx.dirs, slab, 1, Z01, X, out[1], store=False)
-                comm.allreduce_(out)
                 gcols = ops._surrogate_col_grad(cols, ctx.dirs, out[:, :2].reshape(-1), out[-1, 2])
                 return gcols, None, None, None, None
             Z01c = ops._fused_pair_grad(cols, plan.sizes, 0, Zc, X23c, acc, store=True)      # axes 0, 1 (+ Z01)
-            Z01 = _to_rows(Z01c, plan, comm)
-            ops._fused_pair_grad(cols, slab, 1, Z01, X, acc, store=False)                     # axes 2, 3
+            Z01b = comm.all_to_all(Z01c.view(W, plan.m_loc, cw))                               # chunked row layout
+            ops._fused_pair_grad(cols, slab, 1, Z01b, X, acc, store=False, chunk_z=W)          # axes 2, 3
             comm.allreduce_(acc)
             return acc.to(cols.dtype), None, None, None, None
+        gY = gYb[0]
         cols, X = ctx.saved_tensors
         d, gmax = cols.shape
         c = X.shape[1]
@@ -203,6 +211,26 @@ class _ShardedKronFn(torch.autograd.Function):
                 Pz = ops.kron_axis_apply(Pz, cols[i], g, outer, inner)
         comm.allreduce_(acc)
         return acc.to(cols.dtype), None, None, None, None
+
+
+class _ShardedGramBlocksFn(torch.autograd.Function):
+    """A_loc^T [B_0 | B_1 | ...] summed over ranks for column blocks Bb [nb, m_loc, cwb] (replicated r x (nb cwb)
+    result); gradient w.r.t. the sharded blocks only, returned in the same block layout."""
+
+    @staticmethod
+    def forward(ctx, A, Bb, comm):
+        ctx.save_for_backward(A)
+        ctx.nb, ctx.cwb = Bb.shape[0], Bb.shape[2]
+        G = ops.gram(A, Bb[0]) if ctx.nb == 1 else torch.cat([ops.gram(A, Bb[j]) for j in range(ctx.nb)], dim=1)
+        return comm.allreduce_(G)
+
+    @staticmethod
+    def backward(ctx, gG):
+        (A,) = ctx.saved_tensors
+        if ctx.nb == 1:
+            return None, ops.panel_rmul(A, gG.contiguous()).unsqueeze(0), None
+        gB = torch.stack([ops.panel_rmul(A, gG[:, j * ctx.cwb:(j + 1) * ctx.cwb].contiguous()) for j in range(ctx.nb)])
+        return None, gB, None
 
 
 class _ShardedGramFn(torch.autograd.Function):
@@ -313,9 +341,9 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         cols = cols * scale                                                       # Kuu / sigma^2 (:340)
         dirs = self.covar_module.base_kernel.grid_column_dirs(self.covar_module.grid) \
             if settings.kron_directional_grad.on() else None
-        KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm, dirs)             # :348
+        KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm, dirs)             # :348  column blocks [nb, m_loc, r / nb]
         r = self.L_loc.shape[1]
-        Q = _ShardedGramFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355
+        Q = _ShardedGramBlocksFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355
         b_full = comm.allgather(self.b_loc).reshape(plan.m, 1)
         Kb_full = ops.kron_toeplitz_matmul(cols, plan.sizes, b_full)              # :366
         Kb = _ShardSliceFn.apply(Kb_full, plan, comm)
@@ -336,12 +364,16 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             val = val.detach()
             idx_l, val_l = plan.localize(idx, val)
             a = torch.cholesky_solve(P["c"], P["Lq"])
-            mu_loc = P["Kb"] - ops.panel_rmul(P["KL"].detach(), a)                # :376
+            KLb = P["KL"].detach()
+            nb, cwb = KLb.shape[0], KLb.shape[2]
+            mu_loc = P["Kb"].detach().clone()
+            for j in range(nb):
+                mu_loc -= ops.panel_rmul(KLb[j], a[j * cwb:(j + 1) * cwb].contiguous())      # :376
             mean = comm.allreduce_(ops.left_interp(idx_l, val_l, mu_loc))         # :206-210
             q = x.shape[0]
             Wt = ops.left_t_interp(idx, val, torch.eye(q, dtype=self.dtype, device=x.device), plan.m)
             c1 = ops.left_interp(idx, val, ops.kron_toeplitz_matmul(P["cols"].detach(), plan.sizes, Wt))
-            T = comm.allreduce_(ops.left_interp(idx_l, val_l, P["KL"].detach())).t()
+            T = comm.allreduce_(torch.cat([ops.left_interp(idx_l, val_l, KLb[j]) for j in range(nb)], dim=1)).t()
             cov = (c1 - T.t() @ torch.cholesky_solve(T, P["Lq"])) * P["noise"]    # :222-228
             var = cov.diagonal().unsqueeze(-1) + P["noise"]                        # predict(): + second_noise
         return mean, var

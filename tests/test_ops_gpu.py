@@ -308,3 +308,31 @@ def test_kron_large_axes_forward_backward_tensor_core(sizes, c):
                 out2 = ops.kron_toeplitz_matmul(cg.detach(), sizes, X.to(DEV))
             assert torch.allclose(out2, out.detach(), rtol=1e-5, atol=1e-5 * float(ref.abs().max()))
     assert torch.allclose(grads[0], grads[1], rtol=1e-3, atol=1e-4 * float(grads[1].abs().max()))
+
+
+@pytest.mark.parametrize("slab,pair,c,W", [([8, 32, 32, 32], 1, 64, 4), ([32, 32, 32, 32], 1, 32, 2), ([32, 32], 0, 48, 3),
+                                            ([4, 32, 32, 32], 1, 128, 8)])
+def test_fused_pair_kernels_chunked_layouts(slab, pair, c, W):
+    """Column-chunked operand layouts of the fused pair kernels (send / receive buffers of the sharded path's
+    all-to-all): same numbers as the plain layout, bit for bit."""
+    ops = _ops()
+    d = len(slab)
+    m = int(np.prod(slab))
+    gen = torch.Generator().manual_seed(m + c + W)
+    cols = (torch.rand(d, 32, generator=gen) * 0.1 + torch.exp(-0.05 * torch.arange(32.0) ** 2)).to(DEV)
+    X = torch.randn(m, c, generator=gen).to(DEV)
+    Z = torch.randn(m, c, generator=gen).to(DEV)
+    Y = ops._fused_pair_apply(cols, slab, pair, X)
+    Yc = ops._fused_pair_apply(cols, slab, pair, X, chunk_out=W)
+    assert Yc.shape == (W, m, c // W)
+    assert torch.equal(Yc, Y.view(m, W, c // W).permute(1, 0, 2).contiguous())
+    acc0 = torch.zeros(d, 32, dtype=torch.float64, device=DEV)
+    acc1 = torch.zeros(d, 32, dtype=torch.float64, device=DEV)
+    Zo0 = ops._fused_pair_grad(cols, slab, pair, Z, X, acc0, store=True)
+    Zch = Z.view(m, W, c // W).permute(1, 0, 2).contiguous()
+    Zo1 = ops._fused_pair_grad(cols, slab, pair, Zch, X, acc1, store=True, chunk_z=W)
+    assert torch.equal(Zo0, Zo1)
+    assert torch.allclose(acc0, acc1, rtol=1e-12, atol=1e-12 * float(acc0.abs().max()))
+    acc2 = torch.zeros(d, 32, dtype=torch.float64, device=DEV)
+    assert ops._fused_pair_grad(cols, slab, pair, Zch, X, acc2, store=False, chunk_z=W) is None
+    assert torch.allclose(acc0, acc2, rtol=1e-12, atol=1e-12 * float(acc0.abs().max()))

@@ -33,6 +33,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_MIN_P2P_NCHANNELS", "32")
+        os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "64")
         dist.init_process_group("nccl", device_id=dev)
     from online_gp_b200 import settings as S
     from online_gp_b200.models import OnlineSKIRegression
@@ -85,8 +87,11 @@ def main():
         flag = torch.tensor([0 if ok else 1], device=dev)
         dist.broadcast(flag, 0)
         ok = int(flag.item()) == 0
-        dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+        sh.enable_cuda_graphs(False)
+        torch.cuda.synchronize()
+        dist.barrier()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)       # no process-group teardown under live CUDA-graph state (it can hang)
 
 
 if __name__ == "__main__":
