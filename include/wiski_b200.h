@@ -163,6 +163,16 @@ int wiski_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_
 int wiski_gram_f64(const double* A, const double* Bm, int64_t m, int64_t r, int64_t r2, double* G, double* work,
                    void* stream);
 
+/* Column-chunked forms of k10 / k7 for the row-sharded multi-GPU path, where K L and its gradient are kept as nblk
+ * column blocks [m, r2 / nblk] (block j = columns [j r2/nblk, (j+1) r2/nblk)) — the receive / send buffers of the
+ * row <-> column all-to-all:  G = A^T [B_0 | B_1 | ...]  and  [Out_0 | Out_1 | ...] = P M  in one tensor-core launch.
+ * fp32, (r2 / nblk) % 32 == 0; returns 3 for shapes the tensor-core path does not take (callers then go block by
+ * block through wiski_gram_f32 / wiski_panel_rmul_f32).  work as for wiski_gram_f32. */
+int wiski_gram_chunked_f32(const float* A, const float* Bb, int64_t m, int64_t r, int64_t r2, int64_t nblk, float* G,
+                           float* work, void* stream);
+int wiski_panel_rmul_chunked_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, int64_t nblk,
+                                 float* Outb, void* stream);
+
 /* ---- k11 (CG path): fused Q-MVM  w = v + L^T (KL v),  v,w [r,c]  — one pass over both panels
  * (the matmul closure GPyTorch's linear_cg calls when r > max_cholesky_size, App. A.5).
  * work = scratch of wiski_qmv_work_elems(m,r,c) elements. */

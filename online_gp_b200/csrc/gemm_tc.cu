@@ -122,6 +122,11 @@ struct Batching {
     int64_t n_batches;      // total number of batches (nb > 0)
     int nb, kbpb;
     int m_fastest;
+    // column-chunked operand / result (blocks of cw columns, block j a row-major [rows, cw] matrix; 0 = plain):
+    //   MN-major B given as a 2-D map over the stacked blocks [nblk * b_crows, b_cw]: column n -> (n % b_cw, k + (n / b_cw) * b_crows)
+    //   result written to out + (n / o_cw) * o_cstride + row * ld_out + n % o_cw
+    int64_t b_cw, b_crows;
+    int64_t o_cw, o_cstride;
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -236,6 +241,13 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     if (B_KMAJOR) {
                         tma_load_2d(sB, &tmB, &full_bar[stage], kB, nB);                     // box {BK k, BN rows}
+                    } else if (bt.b_cw > 0) {
+                        for (int j = 0; j < BN / 32; ++j) {
+                            const int n = nB + 32 * j;
+                            const int blk = n / (int)bt.b_cw;
+                            tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n - blk * (int)bt.b_cw,
+                                        kB + blk * (int)bt.b_crows);
+                        }
                     } else {
                         for (int j = 0; j < BN / 32; ++j)
                             tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], nB + 32 * j, kB);
@@ -339,8 +351,15 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int acc = (int)(it & 1);
             mbar_wait(&tmem_full_bar[acc], (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float* obase = out + z * slice_stride;
+            float* obase0 = out + z * slice_stride;
             for (int c0 = 0; c0 < BN; c0 += 32) {
+                float* obase = obase0;
+                int64_t ncol0 = n0 + c0;                 // column of this 32-wide group inside its block
+                if (bt.o_cw > 0) {
+                    const int64_t blk = ncol0 / bt.o_cw;
+                    obase += blk * bt.o_cstride;
+                    ncol0 -= blk * bt.o_cw;
+                }
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN + c0), v);
                 uint4* dst = reinterpret_cast<uint4*>(stg + lane * STG_PITCH);
@@ -353,7 +372,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int lr = rr + (lane >> 3), c4 = (lane & 7) * 4;
                     const int64_t row = m0 + wq * 32 + lr, col = n0 + c0 + c4;
                     if (row < Mdim && col < Ndim)                     // Ndim % 4 == 0 (tc_shape_ok)
-                        *reinterpret_cast<uint4*>(obase + row * ld_out + col) =
+                        *reinterpret_cast<uint4*>(obase + row * ld_out + ncol0 + c4) =
                             *reinterpret_cast<const uint4*>(stg + lr * STG_PITCH + c4);
                 }
                 __syncwarp();
@@ -431,7 +450,7 @@ template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, int64_t Mdim, int64_t Ndim, int64_t Kdim,
                   int bn, int ntiles, int64_t k_per_slice, int64_t nslices, int64_t ld_out, int64_t slice_stride,
                   cudaStream_t st, const char* name, const Batching* btp = nullptr) {
-    Batching bt = {k_per_slice, k_per_slice, 0, 0, 0, 0, 0, 0};
+    Batching bt = {k_per_slice, k_per_slice, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (btp != nullptr) bt = *btp;
     size_t smem = (size_t)STAGES * 2 * ((size_t)128 * BK * 4 + (size_t)bn * BK * 4) + 4 * 32 * 36 * 4 +
                   (3 * STAGES + 5) * 8 + 1024;
@@ -461,17 +480,22 @@ int64_t tc_gram_work_elems(int64_t m, int64_t r, int64_t r2) {
     return ceil_div(m, kGramSliceRows) * r * r2;
 }
 
+// nblk > 1: Bm is column-chunked, nblk blocks [m, r2 / nblk] stacked (block j = columns [j r2/nblk, (j+1) r2/nblk)).
 int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
-                cudaStream_t st) {
+                cudaStream_t st, int64_t nblk) {
     if (!tc_shape_ok(m, r, r2)) return 3;
+    if (nblk > 1 && (r2 % nblk != 0 || (r2 / nblk) % 32 != 0 || nblk * m >= (int64_t)1 << 31)) return 3;
     CUtensorMap tmA, tmB;
     if (int rc = make_map(&tmA, A, m, r, kGramBK, true)) return rc;
-    if (int rc = make_map(&tmB, Bm, m, r2, kGramBK, true)) return rc;
+    if (int rc = (nblk > 1 ? make_map(&tmB, Bm, nblk * m, r2 / nblk, kGramBK, true) : make_map(&tmB, Bm, m, r2, kGramBK, true)))
+        return rc;
     int ntiles;
     int bn = pick_bn(r2, &ntiles);
     int64_t nslices = ceil_div(m, kGramSliceRows);
+    Batching bt = {kGramSliceRows, kGramSliceRows, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (nblk > 1) { bt.b_cw = r2 / nblk; bt.b_crows = m; }
     if (int rc = launch<false, false, kGramBK, kGramStages>(tmA, tmB, work, r, r2, m, bn, ntiles, kGramSliceRows, nslices, r2,
-                                                     r * r2, st, "tc_gram"))
+                                                     r * r2, st, "tc_gram", &bt))
         return rc;
     int64_t n = r * r2;
     reduce_slices_kernel<float><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nslices, n, G);
@@ -480,14 +504,21 @@ int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r
     return 0;
 }
 
-int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st) {
+// nblk > 1: Out is written column-chunked, nblk blocks [m, r2 / nblk] stacked.
+int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st,
+                      int64_t nblk) {
     if (!tc_shape_ok(m, r, r2)) return 3;
+    if (nblk > 1 && (r2 % nblk != 0 || (r2 / nblk) % 32 != 0)) return 3;
     CUtensorMap tmA, tmB;
     if (int rc = make_map(&tmA, P, m, r, 128, false, kRmulBK)) return rc;   // K-major A: box {BK k, 128 rows}
     if (int rc = make_map(&tmB, M, r, r2, kRmulBK, true)) return rc;   // MN-major B: box {32 cols, BK rows}
     int ntiles;
     int bn = pick_bn(r2, &ntiles);
-    return launch<true, false, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, r2, 0, st, "tc_panel_rmul");
+    Batching bt = {r, r, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t ld_out = r2;
+    if (nblk > 1) { bt.o_cw = r2 / nblk; bt.o_cstride = m * (r2 / nblk); ld_out = r2 / nblk; }
+    return launch<true, false, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, ld_out, 0, st, "tc_panel_rmul",
+                                                     &bt);
 }
 
 // debug: Out = P @ Mt^T with Mt [r2 x r] row-major (both operands K-major)
@@ -575,7 +606,7 @@ int tc_axis_apply_f32(const float* X, float* Y, const float* col, int64_t g, int
     if (int rc = make_map(&tmB, X, outer * g, inner, kGramBK, true)) return rc;
     int ntiles;
     int bn = pick_bn(inner, &ntiles);
-    Batching bt = {0, g, 0, 0, 0, 0, 0, 1};
+    Batching bt = {0, g, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0};
     return launch<false, false, kGramBK, kGramStages>(tmA, tmB, Y, g, inner, g, bn, ntiles, g, outer, inner, g * inner, st,
                                                       "tc_axis_apply", &bt);
 }
@@ -591,8 +622,8 @@ int tc_axis_contract_f32(const float* Z, const float* P, int64_t g, int64_t oute
     CUtensorMap tmA, tmB;
     if (int rc = make_map(&tmA, Z, outer * g, inner, 128, false, kRmulBK)) return rc;
     if (int rc = make_map(&tmB, P, outer * g, inner, bn, false, kRmulBK)) return rc;
-    Batching bt = {kps, kps, 0, 0, 0, 0, 0, 0};
-    if (nb > 0) bt = Batching{0, 0, g, g, outer, nb, (int)ceil_div(inner, kRmulBK), 0};
+    Batching bt = {kps, kps, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (nb > 0) bt = Batching{0, 0, g, g, outer, nb, (int)ceil_div(inner, kRmulBK), 0, 0, 0, 0, 0};
     float* parts = work + g * g;
     if (int rc = launch<true, true, kRmulBK, kRmulStages>(tmA, tmB, parts, g, g, inner, bn, ntiles, kps, nslices, g, g * g,
                                                           st, "tc_axis_contract", &bt))

@@ -10,8 +10,9 @@ namespace wiski {
 
 // gemm_tc.cu (fp32, tcgen05): return 0 if handled, 3 if the shape is not supported by the tensor-core path.
 int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
-                cudaStream_t st);
-int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st);
+                cudaStream_t st, int64_t nblk = 1);
+int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st,
+                      int64_t nblk = 1);
 int64_t tc_gram_work_elems(int64_t m, int64_t r, int64_t r2);
 
 // ------------------------------------------------------------------ Out[M x N] = P[M x K] @ Mm[K x N]
@@ -633,6 +634,29 @@ int wiski_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_
 int wiski_gram_f64(const double* A, const double* Bm, int64_t m, int64_t r, int64_t r2, double* G, double* work,
                    void* stream) {
     return wiski::gram<double>(A, Bm, m, r, r2, G, work, stream);
+}
+/* Column-chunked variants for the row-sharded path (K L and its gradient live as the all-to-all's receive / send
+ * buffer: nblk blocks [m, r2 / nblk], block j = columns [j r2/nblk, (j+1) r2/nblk)).  One tensor-core launch when the
+ * shape allows it (fp32, (r2 / nblk) % 32 == 0), otherwise one plain call per block. */
+int wiski_gram_chunked_f32(const float* A, const float* Bb, int64_t m, int64_t r, int64_t r2, int64_t nblk, float* G,
+                           float* work, void* stream) {
+    WISKI_CHECK_ARG(nblk >= 1 && r2 % nblk == 0, "gram_chunked: r2=%lld not divisible into %lld blocks", (long long)r2,
+                    (long long)nblk);
+    int rc = wiski::tc_gram_f32(A, Bb, m, r, r2, G, work, wiski::as_stream(stream), nblk);
+    if (rc != 3) return rc;
+    wiski::set_error("gram_chunked: shape m=%lld r=%lld r2=%lld nblk=%lld not supported by the tensor-core path",
+                     (long long)m, (long long)r, (long long)r2, (long long)nblk);
+    return 3;
+}
+int wiski_panel_rmul_chunked_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, int64_t nblk,
+                                 float* Outb, void* stream) {
+    WISKI_CHECK_ARG(nblk >= 1 && r2 % nblk == 0, "panel_rmul_chunked: r2=%lld not divisible into %lld blocks",
+                    (long long)r2, (long long)nblk);
+    int rc = wiski::tc_panel_rmul_f32(P, m, r, M, r2, Outb, wiski::as_stream(stream), nblk);
+    if (rc != 3) return rc;
+    wiski::set_error("panel_rmul_chunked: shape m=%lld r=%lld r2=%lld nblk=%lld not supported by the tensor-core path",
+                     (long long)m, (long long)r, (long long)r2, (long long)nblk);
+    return 3;
 }
 int64_t wiski_qmv_work_elems(int64_t m, int64_t r, int64_t c) { return wiski::qmv_blocks(m) * r * c; }
 int wiski_q_matvec_f32(const float* L, const float* KL, int64_t m, int64_t r, const float* v, int64_t c, float* w,

@@ -503,6 +503,45 @@ def _gram(A, B):
     return G
 
 
+def gram_blocks(A, Bb):
+    """A^T [B_0 | B_1 | ...] for column blocks Bb [nb, m, cwb] -> [r, nb cwb] (no autograd)."""
+    _require_cuda(A, Bb)
+    nb, m, cwb = Bb.shape
+    r, r2 = A.shape[1], nb * cwb
+    if nb == 1:
+        return _gram(A, Bb[0])
+    if A.dtype == torch.float32 and cwb % 32 == 0:
+        A, Bb = A.contiguous(), Bb.contiguous()
+        lib = _lib.load()
+        work = torch.empty(max(int(lib.wiski_gram_work_elems(m, r, r2)), 1), dtype=A.dtype, device=A.device)
+        G = torch.empty(r, r2, dtype=A.dtype, device=A.device)
+        rc = lib.wiski_gram_chunked_f32(_ptr(A), _ptr(Bb), m, r, r2, nb, _ptr(G), _ptr(work), _stream())
+        if rc == 0:
+            return G
+        if rc != 3:
+            _lib.check(rc, "wiski_gram_chunked")
+    return torch.cat([_gram(A, Bb[j]) for j in range(nb)], dim=1)
+
+
+def rmul_blocks(P, M, nb):
+    """[Out_0 | Out_1 | ...] = P M returned as column blocks [nb, m, r2 / nb] (no autograd)."""
+    _require_cuda(P, M)
+    m, r = P.shape
+    r2 = M.shape[1]
+    cwb = r2 // nb
+    if nb == 1:
+        return _rmul(P, M).unsqueeze(0)
+    if P.dtype == torch.float32 and cwb % 32 == 0:
+        P, M = P.contiguous(), M.contiguous()
+        Out = torch.empty(nb, m, cwb, dtype=P.dtype, device=P.device)
+        rc = _lib.load().wiski_panel_rmul_chunked_f32(_ptr(P), m, r, _ptr(M), r2, nb, _ptr(Out), _stream())
+        if rc == 0:
+            return Out
+        if rc != 3:
+            _lib.check(rc, "wiski_panel_rmul_chunked")
+    return torch.stack([_rmul(P, M[:, j * cwb:(j + 1) * cwb].contiguous()) for j in range(nb)])
+
+
 class _RmulFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, P, M):

@@ -221,16 +221,12 @@ class _ShardedGramBlocksFn(torch.autograd.Function):
     def forward(ctx, A, Bb, comm):
         ctx.save_for_backward(A)
         ctx.nb, ctx.cwb = Bb.shape[0], Bb.shape[2]
-        G = ops.gram(A, Bb[0]) if ctx.nb == 1 else torch.cat([ops.gram(A, Bb[j]) for j in range(ctx.nb)], dim=1)
-        return comm.allreduce_(G)
+        return comm.allreduce_(ops.gram_blocks(A, Bb))
 
     @staticmethod
     def backward(ctx, gG):
         (A,) = ctx.saved_tensors
-        if ctx.nb == 1:
-            return None, ops.panel_rmul(A, gG.contiguous()).unsqueeze(0), None
-        gB = torch.stack([ops.panel_rmul(A, gG[:, j * ctx.cwb:(j + 1) * ctx.cwb].contiguous()) for j in range(ctx.nb)])
-        return None, gB, None
+        return None, ops.rmul_blocks(A, gG.contiguous(), ctx.nb), None
 
 
 class _ShardedGramFn(torch.autograd.Function):

@@ -336,3 +336,23 @@ def test_fused_pair_kernels_chunked_layouts(slab, pair, c, W):
     acc2 = torch.zeros(d, 32, dtype=torch.float64, device=DEV)
     assert ops._fused_pair_grad(cols, slab, pair, Zch, X, acc2, store=False, chunk_z=W) is None
     assert torch.allclose(acc0, acc2, rtol=1e-12, atol=1e-12 * float(acc0.abs().max()))
+
+
+@pytest.mark.parametrize("m,r,nb", [(4096, 128, 2), (8192, 448, 2), (6000, 512, 8), (4096, 256, 4), (2048, 96, 2)])
+def test_gram_and_rmul_on_column_blocks(m, r, nb):
+    """Column-chunked Gram / panel right-multiply (one tensor-core launch over the all-to-all's block layout, or the
+    per-block fallback when (r / nb) % 32 != 0) against fp64."""
+    ops = _ops()
+    gen = torch.Generator().manual_seed(m + r + nb)
+    A = torch.randn(m, r, generator=gen)
+    B = torch.randn(m, r, generator=gen)
+    M = torch.randn(r, r, generator=gen)
+    cwb = r // nb
+    Bb = B.view(m, nb, cwb).permute(1, 0, 2).contiguous()
+    G = ops.gram_blocks(A.to(DEV), Bb.to(DEV))
+    ref = A.double().t() @ B.double()
+    assert torch.allclose(G.cpu().double(), ref, rtol=2e-4, atol=2e-5 * float(ref.abs().max()))
+    Ob = ops.rmul_blocks(A.to(DEV), M.to(DEV), nb)
+    refO = (A.double() @ M.double()).view(m, nb, cwb).permute(1, 0, 2)
+    assert Ob.shape == (nb, m, cwb)
+    assert torch.allclose(Ob.cpu().double(), refO, rtol=2e-4, atol=2e-5 * float(refO.abs().max()))
