@@ -26,8 +26,12 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--q", type=int, default=1)
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--watchdog", type=float, default=0.0, help="dump all Python stacks and exit after this many seconds")
     ap.add_argument("--graphs", action="store_true", help="replay the sharded step as CUDA graphs (eager single-GPU reference)")
     args = ap.parse_args()
+    if args.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(args.watchdog, exit=True)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
