@@ -307,7 +307,7 @@ def _lay_array(c, *chunked):
     return (c_int64 * len(vals))(*[int(v) for v in vals])
 
 
-def _fused_pair_apply(cols, sizes, pair, X, chunk_out=1):
+def _fused_pair_apply(cols, sizes, pair, X, chunk_out=1, out=None):
     """Y = (T_2p x T_2p+1) X for X [m, c].  chunk_out = W > 1: Y is written column-chunked, [W, m, c / W] (the send
     buffer of the row -> column all-to-all of the sharded path: no transposing copy)."""
     d, gmax = cols.shape
@@ -316,22 +316,28 @@ def _fused_pair_apply(cols, sizes, pair, X, chunk_out=1):
     if chunk_out > 1:
         if c % (16 * chunk_out) != 0:
             raise ValueError("column-chunked output needs c % (16 * chunks) == 0")
-        Y = torch.empty(chunk_out, m, c // chunk_out, dtype=X.dtype, device=X.device)
+        Y = torch.empty(chunk_out, m, c // chunk_out, dtype=X.dtype, device=X.device) if out is None else out
+        if Y.shape != (chunk_out, m, c // chunk_out) or not Y.is_contiguous() or Y.dtype != X.dtype:
+            raise ValueError("_fused_pair_apply: bad `out`")
         _call_fn("wiski_kron_fused_pair_apply", _lib.load().wiski_kron_fused_pair_apply_lay_f32, _ptr(cols), d, h_g, gmax,
                  pair, _ptr(X), _ptr(Y), c, _lay_array(c, None, (chunk_out, m)), _stream())
         return Y
-    Y = torch.empty_like(X)
+    Y = torch.empty_like(X) if out is None else out
+    if Y.shape != X.shape or not Y.is_contiguous() or Y.dtype != X.dtype or Y.data_ptr() == X.data_ptr():
+        raise ValueError("_fused_pair_apply: bad `out`")
     _call_fn("wiski_kron_fused_pair_apply", _lib.load().wiski_kron_fused_pair_apply_f32, _ptr(cols), d, h_g, gmax, pair,
              _ptr(X), _ptr(Y), c, _stream())
     return Y
 
 
-def _fused_pair_grad(cols, sizes, pair, Z, P, acc, store, chunk_z=1):
+def _fused_pair_grad(cols, sizes, pair, Z, P, acc, store, chunk_z=1, zout=None):
     """One backward pair pass (wiski_kron_fused_pair_grad).  chunk_z = W > 1: Z is given column-chunked [W, m, c / W]
     (as received from the column -> row all-to-all); P and the returned Zout are plain [m, c]."""
     d, gmax = cols.shape
     m, c = P.shape
-    Zout = torch.empty_like(P) if store else None
+    Zout = (torch.empty_like(P) if zout is None else zout) if store else None
+    if Zout is not None and (Zout.shape != P.shape or not Zout.is_contiguous() or Zout.data_ptr() in (Z.data_ptr(), P.data_ptr())):
+        raise ValueError("_fused_pair_grad: bad `zout`")
     h_g = (c_int64 * d)(*sizes)
     if chunk_z > 1:
         _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_fused_pair_grad_lay_f32, _ptr(cols), d, h_g, gmax,
@@ -523,7 +529,7 @@ def gram_blocks(A, Bb):
     return torch.cat([_gram(A, Bb[j]) for j in range(nb)], dim=1)
 
 
-def rmul_blocks(P, M, nb):
+def rmul_blocks(P, M, nb, out=None):
     """[Out_0 | Out_1 | ...] = P M returned as column blocks [nb, m, r2 / nb] (no autograd)."""
     _require_cuda(P, M)
     m, r = P.shape
@@ -533,13 +539,14 @@ def rmul_blocks(P, M, nb):
         return _rmul(P, M).unsqueeze(0)
     if P.dtype == torch.float32 and cwb % 32 == 0:
         P, M = P.contiguous(), M.contiguous()
-        Out = torch.empty(nb, m, cwb, dtype=P.dtype, device=P.device)
+        Out = torch.empty(nb, m, cwb, dtype=P.dtype, device=P.device) if out is None else out
         rc = _lib.load().wiski_panel_rmul_chunked_f32(_ptr(P), m, r, _ptr(M), r2, nb, _ptr(Out), _stream())
         if rc == 0:
             return Out
         if rc != 3:
             _lib.check(rc, "wiski_panel_rmul_chunked")
-    return torch.stack([_rmul(P, M[:, j * cwb:(j + 1) * cwb].contiguous()) for j in range(nb)])
+    res = torch.stack([_rmul(P, M[:, j * cwb:(j + 1) * cwb].contiguous()) for j in range(nb)])
+    return res if out is None else out.copy_(res)
 
 
 class _RmulFn(torch.autograd.Function):

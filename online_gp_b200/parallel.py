@@ -21,6 +21,8 @@ Mirrors, for one output and an Identity stem, ``OnlineSKIRegression.evaluate`` /
 (``online_gp/models/online_ski_regression.py:64-78,113-146``) on top of the same kernels as the single-GPU path.
 """
 import math
+import os
+import warnings
 
 import torch
 import torch.distributed as dist
@@ -57,10 +59,69 @@ class Comm:
             dist.all_gather(list(out.unbind(0)), t.contiguous(), group=self.group)
         return out
 
+    # ---- peer-memory exchange (NVLink / NVSwitch): the all-to-all of the row <-> column layout change as direct
+    # pulls from the peers' send buffers instead of NCCL's send/recv kernel (measured on 2 x B200: 208 GB/s per
+    # direction for NCCL's all_to_all of 470 MB, far below what the copy engines reach over NVLink 5).
+    # The send buffer is ONE symmetric allocation per model, mapped into every rank's address space
+    # (torch.distributed._symmetric_memory); producers (fused pair kernels, panel GEMM) write straight into it.
+    def enable_peer_exchange(self, numel, dtype, device):
+        """Collective.  Returns the local symmetric send buffer (flat, `numel` elements) or None when peer memory is
+        unavailable (then ``all_to_all`` goes through NCCL).  Every rank gets the same answer."""
+        self.xbuf = self._xhdl = self._xpeers = None
+        if self.world == 1 or not self._a2a_ok or os.environ.get("WISKI_PEER_EXCHANGE", "1") == "0":
+            return None
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            gname = group.group_name
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    symm.enable_symm_mem_for_group(gname)
+            except Exception:                       # noqa: BLE001 - newer torch enables groups implicitly
+                pass
+            buf = symm.empty(numel, dtype=dtype, device=device)
+            hdl = symm.rendezvous(buf, gname)
+            peers = [hdl.get_buffer(p, (numel,), dtype) for p in range(self.world)]
+            if any(pv.device != buf.device for pv in peers):
+                ok = 0
+        except Exception as err:                    # noqa: BLE001
+            warnings.warn(f"peer-memory exchange unavailable ({type(err).__name__}: {err}); using NCCL all_to_all")
+            ok = 0
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return None
+        self.xbuf, self._xhdl, self._xpeers = buf, hdl, peers
+        return buf
+
+    def send_buffer(self, numel, like):
+        """The symmetric send buffer if it is set up and fits (numel elements of like's dtype), else None."""
+        xb = getattr(self, "xbuf", None)
+        if xb is None or xb.dtype != like.dtype or xb.numel() < numel:
+            return None
+        return xb[:numel]
+
+    def peer_exchange(self, shape):
+        """All-to-all of the symmetric send buffer viewed as ``shape`` = [world, rows, cw] (chunk j goes to rank j):
+        barrier (every rank's producer has finished), pull my chunk from every peer, barrier (buffer reusable)."""
+        W, rank = self.world, self.rank
+        self._xhdl.barrier(0)
+        n = shape[0] * shape[1] * shape[2]
+        recv = torch.empty(shape, dtype=self.xbuf.dtype, device=self.xbuf.device)
+        for k in range(W):
+            p = (rank + k) % W                      # start with the local chunk, then stagger the peers
+            recv[p].copy_(self._xpeers[p][:n].view(shape)[rank])
+        self._xhdl.barrier(0)
+        return recv
+
     def all_to_all(self, send):
         """send [world, ...] (chunk j goes to rank j) -> recv [world, ...] (chunk i came from rank i)."""
         if self.world == 1:
             return send
+        if getattr(self, "xbuf", None) is not None and send.untyped_storage().data_ptr() == self.xbuf.untyped_storage().data_ptr():
+            return self.peer_exchange(tuple(send.shape))
         send = send.contiguous()
         if self._a2a_ok:
             recv = torch.empty_like(send)
@@ -155,9 +216,11 @@ class _ShardedKronFn(torch.autograd.Function):
             # slab [g0/W, 32, 32, 32, c]: pair (2,3) is slab-local; pair (0,1) runs in the column-sharded layout
             slab = [plan.g0_loc] + plan.sizes[1:]
             cw = X.shape[1] // W
-            X23s = ops._fused_pair_apply(cols, slab, 1, X.contiguous(), chunk_out=W)         # [W, m_loc, cw] send layout
+            xb = comm.send_buffer(W * plan.m_loc * cw, X)            # symmetric (peer-mapped) send buffer or None
+            X23s = ops._fused_pair_apply(cols, slab, 1, X.contiguous(), chunk_out=W,
+                                         out=None if xb is None else xb.view(W, plan.m_loc, cw))   # send layout
             X23c = comm.all_to_all(X23s.view(W, plan.m_loc, cw)).view(W * plan.m_loc, cw)     # all rows of my columns
-            Yc = ops._fused_pair_apply(cols, plan.sizes, 0, X23c)
+            Yc = ops._fused_pair_apply(cols, plan.sizes, 0, X23c, out=None if xb is None else xb.view(W * plan.m_loc, cw))
             ctx.save_for_backward(cols, X, X23c)
             return comm.all_to_all(Yc.view(W, plan.m_loc, cw))                                # [W, m_loc, cw] blocks
         ctx.save_for_backward(cols, X)
@@ -176,6 +239,9 @@ class _ShardedKronFn(torch.autograd.Function):
             acc = torch.zeros(d, gmax, dtype=torch.float64, device=X.device)
             slab = [plan.g0_loc] + plan.sizes[1:]
             cw = X.shape[1] // W
+            xb = comm.send_buffer(W * plan.m_loc * cw, X)
+            if xb is not None and gYb.untyped_storage().data_ptr() != xb.untyped_storage().data_ptr():
+                gYb = xb.view(W, plan.m_loc, cw).copy_(gYb)         # (the Gram backward normally writes it there itself)
             Zc = comm.all_to_all(gYb.contiguous()).view(W * plan.m_loc, cw)
             if ctx.dirs is not None:            # world == 1 only
                 out = torch.zeros(2, 3, dtype=torch.float64, device=X.device)
@@ -183,7 +249,8 @@ class _ShardedKronFn(torch.autograd.Function):
                 ops._fused_pair_grad_dir(cols, ctx.dirs, slab, 1, Z01, X, out[1], store=False)
                 gcols = ops._surrogate_col_grad(cols, ctx.dirs, out[:, :2].reshape(-1), out[-1, 2])
                 return gcols, None, None, None, None
-            Z01c = ops._fused_pair_grad(cols, plan.sizes, 0, Zc, X23c, acc, store=True)      # axes 0, 1 (+ Z01)
+            Z01c = ops._fused_pair_grad(cols, plan.sizes, 0, Zc, X23c, acc, store=True,
+                                        zout=None if xb is None else xb.view(W * plan.m_loc, cw))   # axes 0, 1 (+ Z01)
             Z01b = comm.all_to_all(Z01c.view(W, plan.m_loc, cw))                               # chunked row layout
             ops._fused_pair_grad(cols, slab, 1, Z01b, X, acc, store=False, chunk_z=W)          # axes 2, 3
             comm.allreduce_(acc)
@@ -220,13 +287,16 @@ class _ShardedGramBlocksFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, Bb, comm):
         ctx.save_for_backward(A)
+        ctx.comm = comm
         ctx.nb, ctx.cwb = Bb.shape[0], Bb.shape[2]
         return comm.allreduce_(ops.gram_blocks(A, Bb))
 
     @staticmethod
     def backward(ctx, gG):
         (A,) = ctx.saved_tensors
-        return None, ops.rmul_blocks(A, gG.contiguous(), ctx.nb), None
+        xb = ctx.comm.send_buffer(A.shape[0] * gG.shape[1], A) if ctx.nb > 1 else None
+        out = None if xb is None else xb.view(ctx.nb, A.shape[0], ctx.cwb)
+        return None, ops.rmul_blocks(A, gG.contiguous(), ctx.nb, out=out), None
 
 
 class _ShardedGramFn(torch.autograd.Function):
@@ -278,6 +348,8 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         self.gp_optimizer = torch.optim.Adam(self.parameters(), lr=lr)
         self._init_caches(init_x, init_y[:, 0], torch.ones_like(init_y[:, 0]))
         self._pieces = None
+        if self.comm.world > 1 and init_x.is_cuda and _fused_ok(self.plan, self.L_loc):
+            self.comm.enable_peer_exchange(self.L_loc.numel(), self.dtype, init_x.device)
         self._graphs = None          # opt-in CUDA-graph replay: enable_cuda_graphs()
         self._n_t = None             # device-side copy of num_data (graph mode)
 
