@@ -67,7 +67,7 @@ class Comm:
     def enable_peer_exchange(self, numel, dtype, device):
         """Collective.  Returns the local symmetric send buffer (flat, `numel` elements) or None when peer memory is
         unavailable (then ``all_to_all`` goes through NCCL).  Every rank gets the same answer."""
-        self.xbuf = self._xhdl = self._xpeers = None
+        self.xbuf = self._xhdl = self._xpeers = self._xstreams = None
         if self.world == 1 or not self._a2a_ok or os.environ.get("WISKI_PEER_EXCHANGE", "1") == "0":
             return None
         ok = 1
@@ -110,9 +110,32 @@ class Comm:
         self._xhdl.barrier(0)
         n = shape[0] * shape[1] * shape[2]
         recv = torch.empty(shape, dtype=self.xbuf.dtype, device=self.xbuf.device)
-        for k in range(W):
-            p = (rank + k) % W                      # start with the local chunk, then stagger the peers
-            recv[p].copy_(self._xpeers[p][:n].view(shape)[rank])
+        # one copy engine does not fill NVLink (measured: 367 GB/s for a single 235 MB pull), so the pulls are cut
+        # into pieces issued on side streams (fork / join with events: also valid under CUDA-graph capture)
+        cur = torch.cuda.current_stream()
+        if self._xstreams is None:
+            self._xstreams = [torch.cuda.Stream(device=self.xbuf.device) for _ in range(8)]
+        pieces = []
+        nsplit = max(1, 8 // max(1, W - 1))
+        for k in range(1, W):
+            p = (rank + k) % W                      # stagger the peers
+            src, dst = self._xpeers[p][:n].view(shape)[rank].reshape(-1), recv[p].reshape(-1)
+            step = -(-src.numel() // nsplit)
+            pieces += [(dst[o:o + step], src[o:o + step]) for o in range(0, src.numel(), step)]
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        joins = []
+        for i, (dst, src) in enumerate(pieces):
+            st = self._xstreams[i % len(self._xstreams)]
+            st.wait_event(fork)
+            with torch.cuda.stream(st):
+                dst.copy_(src)
+                ev = torch.cuda.Event()
+                ev.record(st)
+            joins.append(ev)
+        recv[rank].copy_(self._xpeers[rank][:n].view(shape)[rank])          # local chunk on the main stream
+        for ev in joins:
+            cur.wait_event(ev)
         self._xhdl.barrier(0)
         return recv
 
