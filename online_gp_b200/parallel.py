@@ -350,6 +350,48 @@ class _ShardSliceFn(torch.autograd.Function):
         return ctx.comm.allgather(g.contiguous()).reshape(-1, g.shape[-1]), None, None
 
 
+def sharded_q_matvec(L_loc, KLb, v, comm):
+    """w = (I + L^T K L) v for a replicated v [r, c] with row-sharded panels: every rank runs one pass over its slabs
+    of K L (column blocks KLb [nb, m_loc, r / nb]) and L, then ONE all-reduce of r x c elements — the matmul closure
+    of the CG solve (GPyTorch ``linear_cg``)."""
+    nb, cwb = KLb.shape[0], KLb.shape[2]
+    t = ops.panel_rmul(KLb[0], v[:cwb].contiguous())
+    for j in range(1, nb):
+        t = t + ops.panel_rmul(KLb[j], v[j * cwb:(j + 1) * cwb].contiguous())
+    return v + comm.allreduce_(ops.gram(L_loc, t))
+
+
+def sharded_cg_solve(L_loc, KLb, rhs, comm, tol=1e-2, max_iter=1000, check_every=4):
+    """Solve (I + L^T K L) x = rhs by conjugate gradients with ``sharded_q_matvec``; GPyTorch ``linear_cg`` rules:
+    columns L2-normalised first and rescaled at the end, stop when the mean residual norm < tol and at least
+    min(10, max_iter - 1) iterations ran.  The r-sized recurrences are replicated (identical on every rank, so no
+    further synchronisation); the residual is read back every ``check_every`` iterations.
+    Returns (x, iterations, residual)."""
+    with torch.no_grad():
+        norm = rhs.norm(dim=0, keepdim=True).clamp_min(1e-10)
+        b = rhs / norm
+        x = torch.zeros_like(b)
+        res = b.clone()
+        p = res.clone()
+        rz = (res * res).sum(0, keepdim=True)
+        min_iter = min(10, max_iter - 1)
+        it, resid = 0, 1.0
+        while it < max_iter:
+            Ap = sharded_q_matvec(L_loc, KLb, p, comm)
+            alpha = rz / (p * Ap).sum(0, keepdim=True).clamp_min(1e-30)
+            x = x + alpha * p
+            res = res - alpha * Ap
+            rz_new = (res * res).sum(0, keepdim=True)
+            p = res + (rz_new / rz.clamp_min(1e-30)) * p
+            rz = rz_new
+            it += 1
+            if it % check_every == 0 or it == max_iter:
+                resid = float(res.norm(dim=0).mean())
+                if it >= min_iter and resid < tol:
+                    break
+        return x * norm, it, resid
+
+
 # ---------------------------------------------------------------------------------------------- the sharded model
 class ShardedOnlineSKIRegression(torch.nn.Module):
     """Row-sharded counterpart of ``OnlineSKIRegression`` (Identity stem, one output, learnable noise)."""
@@ -454,9 +496,9 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             idx, val = self.covar_module._compute_grid(x)
             val = val.detach()
             idx_l, val_l = plan.localize(idx, val)
-            a = torch.cholesky_solve(P["c"], P["Lq"])
             KLb = P["KL"].detach()
             nb, cwb = KLb.shape[0], KLb.shape[2]
+            a = self._q_solve(P, P["c"].detach())
             mu_loc = P["Kb"].detach().clone()
             for j in range(nb):
                 mu_loc -= ops.panel_rmul(KLb[j], a[j * cwb:(j + 1) * cwb].contiguous())      # :376
@@ -465,9 +507,23 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             Wt = ops.left_t_interp(idx, val, torch.eye(q, dtype=self.dtype, device=x.device), plan.m)
             c1 = ops.left_interp(idx, val, ops.kron_toeplitz_matmul(P["cols"].detach(), plan.sizes, Wt))
             T = comm.allreduce_(torch.cat([ops.left_interp(idx_l, val_l, KLb[j]) for j in range(nb)], dim=1)).t()
-            cov = (c1 - T.t() @ torch.cholesky_solve(T, P["Lq"])) * P["noise"]    # :222-228
+            cov = (c1 - T.t() @ self._q_solve(P, T)) * P["noise"]                  # :222-228
             var = cov.diagonal().unsqueeze(-1) + P["noise"]                        # predict(): + second_noise
         return mean, var
+
+    def _q_solve(self, P, rhs):
+        """Q^-1 rhs: Cholesky up to ``max_cholesky_size`` (every shipped config), otherwise the sharded CG driver — one
+        pass over the local panel slabs and one all-reduce per iteration (eval-only, like the single-GPU CG path)."""
+        if rhs.shape[0] <= settings.max_cholesky_size.value():
+            return torch.cholesky_solve(rhs, P["Lq"])
+        tol = settings.eval_cg_tolerance.value()
+        x, iters, resid = sharded_cg_solve(self.L_loc, P["KL"].detach(), rhs, self.comm, tol=tol,
+                                           max_iter=settings.max_cg_iterations.value())
+        if resid > tol:
+            warnings.warn(f"CG terminated in {iters} iterations with average residual norm {resid:.3e} which is larger "
+                          f"than the tolerance of {tol} specified by eval_cg_tolerance.", RuntimeWarning)
+        self.last_cg = (iters, resid)
+        return x
 
     def _evaluate_stats(self, x, y):
         mean, var = self.predict(x)

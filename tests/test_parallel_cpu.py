@@ -30,7 +30,9 @@ def _worker(rank, world, port, d, g, n0, steps, ret):
     X = torch.rand(n0 + steps * 2, d, generator=gen) * 2 - 1
     y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps * 2, generator=gen)).unsqueeze(-1)
     out = []
-    with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64):
+    # max_cholesky_size(0): low-rank initial root AND every Q solve of predict() through the sharded CG driver (one
+    # all-reduce per iteration); a tight tolerance makes it comparable with the oracle's dense solves
+    with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64), S.eval_cg_tolerance(1e-13):
         model = ShardedOnlineSKIRegression(X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0, comm=Comm())
         for t in range(steps):
             xt, yt = X[n0 + 2 * t:n0 + 2 * t + 2], y[n0 + 2 * t:n0 + 2 * t + 2]
@@ -38,6 +40,7 @@ def _worker(rank, world, port, d, g, n0, steps, ret):
             _, loss = model.update(xt, yt)
             out.append((rmse, nll, loss, float(model._noise())))
         ls = model.covar_module.base_kernel.base_kernel.lengthscale.detach().reshape(-1).tolist()
+    assert model.last_cg[0] >= 10 and model.last_cg[1] < 1e-12          # the CG path really ran and converged
     ret[rank] = (out, ls, model.L_loc.shape)
     dist.barrier()
     dist.destroy_process_group()
