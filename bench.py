@@ -181,11 +181,13 @@ def run_gpu(args):
         # come from an eager pass of the same steps on the same state, right before the timed region
         KP = min(K, 5)
         ops.PROFILE = {"names": prof_names, "events": {}}
+        phases = _PhaseTimer(model)
         torch.cuda.synchronize()
         for _ in range(KP):
             one_step(model, *batch_dev(t))
             t += 1
         torch.cuda.synchronize()
+        phase_ms = phases.stop(KP)
         prof, ops.PROFILE = ops.PROFILE, None
         model.enable_cuda_graphs(True, warmup_calls=1)
         for _ in range(3):                       # 1 eager, 1 capture + first replay, 1 replay: all untimed
@@ -194,6 +196,7 @@ def run_gpu(args):
         use_graphs = model._graphs is not None and not model._graphs.failed and model._graphs.upd is not None
     else:
         ops.PROFILE = {"names": prof_names, "events": {}}
+        phase_ms = None
     # ---- device-resident timing (value)
     clocks = ClockSampler(local_rank)
     launches0 = lib.wiski_launch_count() + model.graph_launches
@@ -282,12 +285,56 @@ def run_gpu(args):
         "roofline": roof,
         "per_op_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(per_op.items())},
     }
+    if phase_ms:
+        # the reference scripts' sub-timings (wiski_regression.py:125-148): mll_time = MLL forward + backward + Adam,
+        # fantasy_time = condition_on_observations; device time (CUDA events) of the eager pass, ms per step
+        out["phase_ms_per_step_eager"] = phase_ms
     out["cg_mvm"] = cg_mvm_roofline(model, m, r, b, hbm_peak, peak_src)
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, budget_s=args.cpu_budget)
     for c in ctx:
         c.__exit__(None, None, None)
     print(json.dumps(out))
+
+
+class _PhaseTimer:
+    """CUDA-event timing of the three phases of a streaming step on the eager path (never fatal for the bench)."""
+
+    def __init__(self, model):
+        self.model, self.events, self.saved = model, {"evaluate": [], "mll_time": [], "fantasy_time": []}, []
+        try:
+            self._wrap(model, "evaluate", "evaluate")
+            self._wrap(model, "_update_gp_tensor", "mll_time")
+            self._wrap(model.gp, "condition_on_observations", "fantasy_time")
+        except Exception:                         # noqa: BLE001
+            self.stop(1)
+
+    def _wrap(self, obj, name, key):
+        fn = getattr(obj, name)
+        events = self.events[key]
+
+        def timed(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            res = fn(*a, **k)
+            e1.record()
+            events.append((e0, e1))
+            return res
+
+        self.saved.append((obj, name))
+        setattr(obj, name, timed)
+
+    def stop(self, steps):
+        for obj, name in self.saved:
+            try:
+                delattr(obj, name)                # drop the instance attribute: the class method is visible again
+            except Exception:                     # noqa: BLE001
+                pass
+        self.saved = []
+        try:
+            return {k: round(sum(a.elapsed_time(b) for a, b in v) / steps, 4) for k, v in self.events.items() if v}
+        except Exception:                         # noqa: BLE001
+            return None
 
 
 def cg_mvm_roofline(model, m, r, b, hbm_peak, peak_src, reps=20):
