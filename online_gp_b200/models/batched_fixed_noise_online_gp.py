@@ -547,6 +547,36 @@ class FixedNoiseOnlineSKIGP(GP):
         if self._num_data_t is not None:
             self._num_data_t.fill_(float(self.num_data))
 
+    # ------------------------------------------------------------------ state (de)serialisation
+    # The reference keeps the WISKI caches outside ``state_dict`` (a reloaded model silently loses every
+    # observation).  Here they travel as the module's extra state, so ``model.state_dict()`` /
+    # ``load_state_dict()`` round-trip the full posterior: caches, root / inverse-root panels and the counter.
+    def get_extra_state(self):
+        wtw = self._kernel_cache["WtW"]
+        cpu = lambda t: None if t is None else t.detach().to("cpu", copy=True)     # a snapshot, never a view
+        return {
+            "num_data": int(self.num_data),
+            "response_cache": cpu(self._kernel_cache["response_cache"]),
+            "interpolation_cache": cpu(self._kernel_cache["interpolation_cache"]),
+            "D_logdet": cpu(self._kernel_cache["D_logdet"]),
+            "WtW": {"tensor": cpu(wtw.tensor), "root": cpu(wtw.root), "inv_root": cpu(wtw.inv_root)},
+        }
+
+    def set_extra_state(self, state):
+        dev = self._kernel_cache["interpolation_cache"].device
+        mv = lambda t: None if t is None else t.to(dev, copy=True)
+        self._kernel_cache = {
+            "response_cache": mv(state["response_cache"]),
+            "interpolation_cache": mv(state["interpolation_cache"]),
+            "WtW": UpdatedRootLazyTensor(mv(state["WtW"]["tensor"]), initial_is_root=False, root=mv(state["WtW"]["root"]),
+                                         inv_root=mv(state["WtW"]["inv_root"])),
+            "D_logdet": mv(state["D_logdet"]),
+        }
+        self.num_data = int(state["num_data"])
+        if self._num_data_t is not None:
+            self._num_data_t.fill_(float(self.num_data))
+        self._dump_caches()
+
     def to(self, *args, **kwargs):
         device = args[0] if args else kwargs.get("device")
         if torch.is_tensor(device):

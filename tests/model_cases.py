@@ -558,3 +558,38 @@ def test_deferred_bounds_check_raises_from_evaluate():
         from online_gp_b200 import ops
         assert not ops._PENDING_BOUNDS
         reg.evaluate(X[:1], y[:1])                            # and the model keeps working afterwards
+
+
+def test_state_dict_round_trips_the_posterior():
+    """``state_dict()`` carries the WISKI caches and root panels (extra state): a freshly built model that loads it
+    predicts like the streamed one (the reference loses the caches on reload)."""
+    M = _mods()
+    d, g, n0 = 2, 10, 25
+    gen = torch.Generator().manual_seed(4)
+    X = (torch.rand(n0 + 6, d, generator=gen) * 2 - 1).to(_dev())
+    y = torch.sin(3 * X.sum(-1, keepdim=True))
+    Xs = (torch.rand(5, d, generator=gen) * 2 - 1).to(_dev())
+    for mcs in (2048, 0):                                   # Cholesky regime (dense A kept) and matrix-free regime
+        with warnings.catch_warnings(), M["S"].max_cholesky_size(mcs), M["S"].max_root_decomposition_size(32):
+            warnings.simplefilter("ignore")
+            reg = M["OnlineSKIRegression"](M["Identity"](d), X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0)
+        with warnings.catch_warnings(), M["S"].max_cholesky_size(2048), M["S"].max_root_decomposition_size(32):
+            warnings.simplefilter("ignore")
+            for t in range(n0, n0 + 6):
+                reg.update(X[t:t + 1], y[t:t + 1])
+            mean, var = reg.predict(Xs)
+            sd = reg.state_dict()
+            assert "gp._extra_state" in sd
+        with warnings.catch_warnings(), M["S"].max_cholesky_size(mcs), M["S"].max_root_decomposition_size(32):
+            warnings.simplefilter("ignore")
+            fresh = M["OnlineSKIRegression"](M["Identity"](d), X[:3], y[:3], lr=1e-2, grid_size=g, grid_bound=1.0)
+        with warnings.catch_warnings(), M["S"].max_cholesky_size(2048), M["S"].max_root_decomposition_size(32):
+            warnings.simplefilter("ignore")
+            fresh.load_state_dict(sd)
+            assert fresh.gp.num_data == n0 + 6
+            mean2, var2 = fresh.predict(Xs)
+            assert torch.allclose(mean, mean2, rtol=1e-10, atol=1e-12) and torch.allclose(var, var2, rtol=1e-10, atol=1e-12)
+            # and it keeps streaming from there
+            l1 = reg.update(X[:1], y[:1])[1]
+            l2 = fresh.update(X[:1], y[:1])[1]
+            assert abs(l1 - l2) <= 1e-9 * max(1.0, abs(l1))
