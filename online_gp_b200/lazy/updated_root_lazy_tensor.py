@@ -202,6 +202,36 @@ class UpdatedRootLazyTensor(LazyTensor):
             return self
         return UpdatedRootLazyTensor(tensor, initial_is_root=False, root=root, inv_root=inv_root)
 
+    def fold_in_sparse(self, idx, vval, chunk=4096):
+        """Projected update with MANY stencil vectors at once (initial data beyond the root rank), in place.
+
+        The sequence of projected rank-q updates telescopes: with L_k = L_0 G_k, B_k = B_0 G_k^-T one has
+        p_k = B_k^T v_k = G_k^-1 (B_0^T v_k), hence  L_n L_n^T = L_0 (I + P P^T) L_0^T  with  P = B_0^T [v_1 .. v_n]
+        (r x n).  So instead of n / 32 passes over both panels: gather P in chunks (row gathers of B_0), form
+        M = I + P P^T (r x r, accumulated in double), factor M = F F^T and apply  L <- L_0 F,  B <- B_0 F^-T  with ONE
+        tensor-core panel GEMM each.  Same L L^T / B B^T as ``update_sparse`` applied point by point."""
+        self.root_decomposition()
+        self.root_inv_decomposition()
+        if self.tensor is not None or idx.shape[0] == 0:
+            return self.update_sparse(idx, vval, inplace=True)
+        Ls, Bs = self._panels(self.root), self._panels(self.inv_root)
+        vvs = [vval] * len(Bs) if vval.dim() == 2 else list(vval.reshape(-1, *vval.shape[-2:]))
+        newL, newB = [], []
+        for L, B, vv in zip(Ls, Bs, vvs):
+            r = B.shape[-1]
+            M = torch.eye(r, dtype=torch.float64, device=B.device)
+            for s0 in range(0, idx.shape[0], chunk):
+                Pc = ops.left_interp(idx[s0:s0 + chunk], vv[s0:s0 + chunk].contiguous(), B).double()     # [chunk, r]
+                M = M + Pc.t() @ Pc
+            F = torch.linalg.cholesky(M)                                        # M >= I: always positive definite
+            Finv_t = torch.linalg.solve_triangular(F, torch.eye(r, dtype=torch.float64, device=B.device),
+                                                   upper=False).t()
+            newL.append(ops.panel_rmul(L, F.to(L.dtype).contiguous()))
+            newB.append(ops.panel_rmul(B, Finv_t.to(B.dtype).contiguous()))
+        self.root = self._restack(newL, self.root)
+        self.inv_root = self._restack(newB, self.inv_root)
+        return self
+
     def collect_vector(self, vector):
         """(updated_root, updated_inv_root) for a dense ``vector`` — reference signature (:69)."""
         self.root_decomposition()

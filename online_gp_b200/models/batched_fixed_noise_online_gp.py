@@ -102,8 +102,8 @@ def _initialize_caches(targets, noise_diagonal, stencils, m, create_w_cache=True
             pad = lambda P: torch.nn.functional.pad(P, (0, rmax - P.shape[1]))
             wtw = UpdatedRootLazyTensor(None, initial_is_root=False, root=torch.stack([pad(L) for L in roots]),
                                         inv_root=torch.stack([pad(B) for B in invs]))
-            for s0 in range(n1, n, 32):
-                wtw.update_sparse(idx[s0:s0 + 32], vvals[:, s0:s0 + 32].contiguous(), inplace=True)
+            if n > n1:          # initial points beyond the root rank: one batched projected update (fold_in_sparse)
+                wtw.fold_in_sparse(idx[n1:], vvals[:, n1:].contiguous())
             cache["WtW"] = wtw
     cache["D_logdet"] = noise_diagonal.log().sum(-1)    # :55
     return cache

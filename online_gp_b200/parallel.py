@@ -450,8 +450,23 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         scale[:r_eff] = 1.0 / lam
         self.L_loc = ops.panel_rmul(V1, Upad)
         self.B_loc = (self.L_loc * scale).contiguous()
-        for s0 in range(n1, n0, 32):
-            self._root_update(idx[s0:s0 + 32], vval[s0:s0 + 32])
+        if n0 > n1:
+            self._fold_in(idx[n1:], vval[n1:])
+
+    def _fold_in(self, idx_l, vval_l, chunk=4096):
+        """Batched projected update for the initial points beyond the root rank — the sharded form of
+        ``UpdatedRootLazyTensor.fold_in_sparse``: P = B^T V (all-reduced partial row gathers), M = I + P P^T factored
+        once (replicated), one local panel GEMM per panel."""
+        r = self.B_loc.shape[1]
+        M = torch.eye(r, dtype=torch.float64, device=self.B_loc.device)
+        for s0 in range(0, idx_l.shape[0], chunk):
+            Pc = self.comm.allreduce_(ops.left_interp(idx_l[s0:s0 + chunk], vval_l[s0:s0 + chunk].contiguous(),
+                                                      self.B_loc)).double()
+            M = M + Pc.t() @ Pc
+        F = torch.linalg.cholesky(M)
+        Finv_t = torch.linalg.solve_triangular(F, torch.eye(r, dtype=torch.float64, device=M.device), upper=False).t()
+        self.L_loc = ops.panel_rmul(self.L_loc, F.to(self.dtype).contiguous())
+        self.B_loc = ops.panel_rmul(self.B_loc, Finv_t.to(self.dtype).contiguous())
 
     def _root_update(self, idx_l, vval_l):
         """collect_vector (updated_root_lazy_tensor.py:69-119), symmetric-square-root form, panels updated in place."""

@@ -593,3 +593,39 @@ def test_state_dict_round_trips_the_posterior():
             l1 = reg.update(X[:1], y[:1])[1]
             l2 = fresh.update(X[:1], y[:1])[1]
             assert abs(l1 - l2) <= 1e-9 * max(1.0, abs(l1))
+
+
+@pytest.mark.parametrize("d,g,n0,max_root", [(2, 24, 90, 32), (3, 10, 150, 48)])
+def test_initial_points_beyond_root_rank_fold_in(d, g, n0, max_root):
+    """n0 > max_root_decomposition_size: the initial points beyond the root rank are folded in with ONE batched
+    projected update (``fold_in_sparse``); the oracle folds them in point by point.  Same posterior and MLL, and the
+    same root Gram as the sequential ``update_sparse`` path."""
+    M = _mods()
+    dt = torch.float64
+    orc, model, X, y, hyp = _oracle_and_model(M, d, g, n0, dt, 0, "sym", "rbf", seed=3, max_root=max_root)
+    Xs = (torch.rand(7, d, dtype=torch.float64, generator=torch.Generator().manual_seed(8)) * 2 - 1)
+    with M["S"].max_cholesky_size(800), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.eval()
+        dist = model(Xs.to(_dev()))
+        mo, co = orc.predict(Xs)
+        assert np.allclose(dist.mean.detach().cpu().numpy(), mo.detach().numpy(), rtol=1e-6, atol=1e-8)
+        assert np.allclose(dist.variance.detach().cpu().numpy(), co.diagonal().detach().numpy(), rtol=1e-6, atol=1e-9)
+        model.train()
+        val = M["BatchedWoodburyMarginalLogLikelihood"](model.likelihood, model)(model(None), None)
+        assert np.allclose(val.item(), orc.mll().item(), rtol=1e-7)
+    # sequential reference on the same panels
+    from online_gp_b200.models.batched_fixed_noise_online_gp import _lowrank_initial_roots
+    from online_gp_b200.lazy import UpdatedRootLazyTensor
+    lk = model.covar_module(X[:n0].to(_dev())).evaluate_kernel()
+    idx, val_ = lk.left_interp_indices, lk.left_interp_values.detach()
+    L0, B0, n1 = _lowrank_initial_roots(idx, val_.contiguous(), model.covar_module.num_inducing, max_root)
+    seq = UpdatedRootLazyTensor(None, initial_is_root=False, root=L0.clone(), inv_root=B0.clone())
+    for s0 in range(n1, n0, 32):
+        seq.update_sparse(idx[s0:s0 + 32], val_[s0:s0 + 32].contiguous(), inplace=True)
+    Lb = model._kernel_cache["WtW"].root[0]
+    Bb = model._kernel_cache["WtW"].inv_root[0]
+    G1, G2 = Lb @ Lb.t(), seq.root @ seq.root.t()
+    assert torch.allclose(G1, G2, rtol=1e-8, atol=1e-10 * float(G2.abs().max()))
+    H1, H2 = Bb @ Bb.t(), seq.inv_root @ seq.inv_root.t()
+    assert torch.allclose(H1, H2, rtol=1e-7, atol=1e-9 * float(H2.abs().max()))

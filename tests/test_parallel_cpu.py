@@ -76,7 +76,7 @@ def _oracle_loop(d, g, n0, steps):
     return out, hyp.lengthscale.detach().tolist()
 
 
-@pytest.mark.parametrize("d,g,n0", [(2, 8, 20), (3, 6, 30)])
+@pytest.mark.parametrize("d,g,n0", [(2, 8, 20), (3, 6, 30), (2, 10, 90)])   # last: n0 > root rank (batched fold-in)
 def test_sharded_stream_matches_unsharded_oracle(d, g, n0):
     world, steps = 2, 3
     mgr = mp.Manager()
