@@ -179,6 +179,7 @@ class UpdatedRootLazyTensor(LazyTensor):
         """v = W^T D^-1/2 given by its stencils: idx [q,s] (shared by all outputs), vval [q,s] or [t,q,s]."""
         self.root_decomposition()
         self.root_inv_decomposition()
+        vval = vval.detach()             # the panels are state, not part of any autograd graph
         Bs = self._panels(self.inv_root)
         vvs = [vval] * len(Bs) if vval.dim() == 2 else list(vval.reshape(-1, *vval.shape[-2:]))
         tensor = self.tensor

@@ -398,8 +398,19 @@ class FixedNoiseOnlineSKIGP(GP):
                                                                      inner[o], scale) for b in range(xb.numel())]))
                 pred_cov = BatchLazyTensor(covs)
             else:
-                raise NotImplementedError("fast_pred_samples: Lanczos root of the predictive covariance (:229-243) "
-                                          "is a 'next' row (SURVEY §8f-1)")
+                # fast_pred_samples (:229-243): the reference samples from a Lanczos root of the m x m grid-space
+                # covariance truncated to q* columns (random start vector, approximate).  The q* x q* test covariance
+                # is formed exactly here anyway, so the root handed to the sampler is its exact Cholesky factor.
+                from ..lazy.lazy_tensor import psd_safe_cholesky
+                covs = []
+                n = idx.shape[-2]
+                for o in range(t):
+                    scale = self._second_noise(o) if self.has_learnable_noise else None
+                    blocks = [PredictiveCovar(idx2[b * n:(b + 1) * n], val2[b * n:(b + 1) * n], inner[o], scale,
+                                              T=Ts[o] if len(xb) == 0 else None) for b in range(max(1, xb.numel()))]
+                    roots = [RootLazyTensor(psd_safe_cholesky(blk.evaluate())) for blk in blocks]
+                    covs.append(roots[0] if len(xb) == 0 else BatchLazyTensor(roots))
+                pred_cov = BatchLazyTensor(covs)
         else:
             pred_cov = ZeroLazyTensor(*lazy_kernel.shape, dtype=val.dtype, device=val.device)
 
