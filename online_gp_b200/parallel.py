@@ -13,9 +13,17 @@ Exchange steps per streaming step
     *column-sharded* layout reached by one all-to-all each way (m r b / G bytes per rank each);
   * hyper-gradient (column gradient of the Kronecker operator): the same exchange for the prefix chain and for the
     axis-0 contraction, then one all-reduce of the d x g column gradient;
-  * ``K b`` for the m-vector ``b``: all-gather of b (m b bytes), replicated MVM.
+  * ``K b`` for the m-vector ``b``: all-gather of b (m b bytes), replicated MVM;
+  * CG path (r > max_cholesky_size): one all-reduce of r x c per iteration (``sharded_cg_solve``).
 Every autograd Function below returns *complete* (replicated) gradients for replicated inputs, so hyper-parameter
 updates need no extra synchronisation.
+
+The all-to-all (fused 32^4 path): ``K L`` and its gradient live as ``world`` column blocks ``[world, m_loc, r / world]``
+— the receive buffer of one exchange and the send buffer of the next — which the pair kernels and the tensor-core
+Gram / panel GEMM read and write in place (no transposing copies).  When symmetric memory is available the send
+buffer is peer-mapped and every rank *pulls* its chunks over NVLink (``Comm.peer_exchange``); otherwise NCCL's
+``all_to_all_single`` moves the same buffers.  ``enable_cuda_graphs()`` replays the whole step, collectives included,
+from two captured CUDA graphs.
 
 Mirrors, for one output and an Identity stem, ``OnlineSKIRegression.evaluate`` / ``.update``
 (``online_gp/models/online_ski_regression.py:64-78,113-146``) on top of the same kernels as the single-GPU path.
