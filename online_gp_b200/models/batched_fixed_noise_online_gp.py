@@ -15,7 +15,9 @@ re-designed matrix-free on CUDA:
 Initial root beyond the Cholesky regime (the reference leaves this to GPyTorch's randomly started Lanczos,
 SURVEY.md §7-H2): with V1 = W1^T D1^-1/2 of the first n1 = min(n0, max_root_decomposition_size) points and
 G = V1^T V1 = U diag(lam) U^T, keep lam_j > tol lam_max:  L = V1 U,  B = L diag(1/lam); remaining initial points
-are folded in with the projected rank-q update.  (The CPU oracle ``oracle/wiski_matfree.py`` states the same rule.)
+are folded in with the projected update — all at once (``UpdatedRootLazyTensor.fold_in_sparse``: the point-by-point
+projected updates telescope to one r x r factor and one panel GEMM per panel).  The CPU oracle
+``oracle/wiski_matfree.py`` states the same rule point by point.
 """
 import torch
 from torch import nn
