@@ -243,9 +243,10 @@ def run_gpu(args):
         "wiski_gram": ("tensor", 2.0 * m * r * r),                           # flops
         "wiski_panel_rmul": ("tensor", 2.0 * m * r * r),
     }
-    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_ncu_kernels_*.md), bytes
-    ncu_traffic = {"wiski_kron_fused_pair_grad": 0.5 * (5.41e9 + 3.64e9), "wiski_kron_fused_pair_apply": 3.60e9,
-                   "wiski_gram": 4.02e9, "wiski_panel_rmul": 5.41e9, "wiski_panel_lowrank_update": 3.57e9}
+    # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full`
+    # capture profiles/r01_ncu_kernels_v2.md, bytes; the two launches per step of the pair kernels are averaged
+    ncu_traffic = {"wiski_kron_fused_pair_grad": 0.5 * (5.41e9 + 3.63e9), "wiski_kron_fused_pair_apply": 0.5 * (4.08e9 + 3.58e9),
+                   "wiski_gram": 4.41e9, "wiski_panel_rmul": 3.58e9, "wiski_panel_lowrank_update": 3.56e9}
     roof = None
     if dom in alg:
         bound, work = alg[dom]
