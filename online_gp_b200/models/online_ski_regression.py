@@ -298,12 +298,16 @@ class OnlineSKIRegression(torch.nn.Module):
                 self._graph_fail(err)
                 G.phase = None
                 return self.update(inputs, targets)
-        (gp_loss,) = G.replay(G.upd)
-        G.phase = None
-        self.gp.num_data = n_before + inputs.shape[0]
-        self.gp._dump_caches()
-        self._raw_inputs = [torch.cat([*self._raw_inputs, inputs])]
-        self.eval()
+        try:
+            (gp_loss,) = G.replay(G.upd)
+        finally:
+            # also when the replay reports out-of-bounds inputs: the device-side state has already moved on (the
+            # batch went in with clamped stencils), so the host-side bookkeeping must follow before the error surfaces
+            G.phase = None
+            self.gp.num_data = n_before + inputs.shape[0]
+            self.gp._dump_caches()
+            self._raw_inputs = [torch.cat([*self._raw_inputs, inputs])]
+            self.eval()
         return 0., gp_loss
 
     @property

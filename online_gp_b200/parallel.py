@@ -665,10 +665,12 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
                 G.phase = None
                 self._pieces = None
                 return self.update(x, y)
-        (loss,) = G.replay(G.upd)
-        G.phase = None
-        self.num_data = n_before + x.shape[0]
-        self._pieces = None
+        try:
+            (loss,) = G.replay(G.upd)
+        finally:                     # keep the host bookkeeping in step with the device even if the replay raises
+            G.phase = None
+            self.num_data = n_before + x.shape[0]
+            self._pieces = None
         return 0.0, loss
 
     @property
