@@ -52,6 +52,7 @@ class Comm:
         self.world = dist.get_world_size(group) if self.enabled else 1
         self.rank = dist.get_rank(group) if self.enabled else 0
         self._a2a_ok = self.enabled and dist.get_backend(group) != "gloo"
+        self.xbuf = self._xhdl = self._xpeers = self._xstreams = None      # peer-memory exchange (enable_peer_exchange)
 
     def allreduce_(self, t):
         if self.world > 1:
@@ -106,7 +107,7 @@ class Comm:
 
     def send_buffer(self, numel, like):
         """The symmetric send buffer if it is set up and fits (numel elements of like's dtype), else None."""
-        xb = getattr(self, "xbuf", None)
+        xb = self.xbuf
         if xb is None or xb.dtype != like.dtype or xb.numel() < numel:
             return None
         return xb[:numel]
@@ -151,7 +152,7 @@ class Comm:
         """send [world, ...] (chunk j goes to rank j) -> recv [world, ...] (chunk i came from rank i)."""
         if self.world == 1:
             return send
-        if getattr(self, "xbuf", None) is not None and send.untyped_storage().data_ptr() == self.xbuf.untyped_storage().data_ptr():
+        if self.xbuf is not None and send.untyped_storage().data_ptr() == self.xbuf.untyped_storage().data_ptr():
             return self.peer_exchange(tuple(send.shape))
         send = send.contiguous()
         if self._a2a_ok:
