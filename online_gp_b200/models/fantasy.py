@@ -141,3 +141,126 @@ def condition_on_target_batch(model, X, Y, noise):
     if model.training is False:
         fm.eval()
     return fm
+
+
+# ------------------------------------------------------------------------------------------------ batched fantasy inputs
+def posterior_cross_cov(model, o, idx_a, val_a, idx_b, val_b):
+    """Latent posterior covariance  W_a M W_b^T * scale  between two stencil sets for output o ([qa, qb]), with
+    M = K - K L Q^-1 L^T K the grid-space predictive covariance (``_make_predictive_covar``, :385-404) and
+    scale = sigma^2 when the model has the learnable noise factor (:227-228).  Differentiable w.r.t. the
+    interpolation values (acquisition optimisation back-propagates into the candidate inputs)."""
+    from ..lazy.lazy_tensor import _scatter_dense
+    m = model.covar_module.num_inducing
+    cache = model.prediction_cache
+    K, KL, Q = model.Kuu.items[o].detach(), cache["KL"][o].detach(), model.current_qmatrix.items[o]
+    eye = torch.eye(idx_b.shape[0], dtype=val_b.dtype, device=val_b.device)
+    grad = torch.is_grad_enabled() and val_b.requires_grad
+    Wb_t = _scatter_dense(idx_b, val_b, eye, m) if grad else ops.left_t_interp(idx_b, val_b, eye, m)      # [m, qb]
+    c1 = ops.left_interp(idx_a, val_a, K._matmul(Wb_t))                                                    # [qa, qb]
+    Ta = ops.left_interp(idx_a, val_a, KL)                                                                 # [qa, r]
+    Tb = ops.left_interp(idx_b, val_b, KL)                                                                 # [qb, r]
+    Lq = Q.cholesky().detach()
+    cov = c1 - Ta @ torch.cholesky_solve(Tb.t(), Lq)
+    if model.has_learnable_noise:
+        cov = cov * model._second_noise(o).detach()
+    return cov
+
+
+class PredictiveSpaceFantasy:
+    """Fantasy models for candidate batches X [b, q, d] that differ per batch element (BoTorch ``fantasize`` inside
+    ``optimize_acqf``: look-ahead acquisition functions such as qNIPV, ``experiments/active_learning``).
+
+    The reference gives every batch element its own copy of the dense ``WtW`` and of both root panels and updates each
+    (``_expand_batch`` repeats them, ``updated_root_lazy_tensor.py:139-159``).  A fantasy is only ever *queried* —
+    posterior mean / variance at test points — so it is represented here in predictive space instead: with the
+    current posterior's latent covariance C(.,.) (``posterior_cross_cov``) and S_b = C(X_b, X_b) + sigma^2 D_b,
+
+        mean_b(x*) = mean(x*) + C(x*, X_b) S_b^-1 (y_b - mean(X_b)),   var_b(x*) = C(x*, x*) - C(x*, X_b) S_b^-1 C(X_b, x*).
+
+    This is the exact Gaussian conditional under the SKI kernel; it coincides with conditioning the WISKI caches
+    whenever the root is exact (r = m: every configuration below ``max_cholesky_size``, i.e. all BO / active-learning
+    setups of the reference), and no m-sized state is copied.  Y may be None (variance-only acquisition functions)."""
+
+    def __init__(self, model, X, Y=None, noise=None):
+        if X.dim() != 3:
+            raise ValueError("X must be [b, q, d]")
+        self.model = model.eval()
+        self.b, self.q, _ = X.shape
+        self.t = model._num_models
+        self._X_flat = X.reshape(-1, X.shape[-1])
+        lazy_kernel = model.covar_module(self._X_flat).evaluate_kernel()
+        self.idx_b, self.val_b = lazy_kernel.left_interp_indices, lazy_kernel.left_interp_values
+        if noise is None:
+            noise = torch.ones(self.b, self.q, self.t, dtype=X.dtype, device=X.device)
+        self.noise = noise.expand(self.b, self.q, self.t)
+        self.Y = None if Y is None else (Y if Y.dim() == 4 else Y.unsqueeze(0))          # [nf, b, q, t]
+        self.num_fantasies = None if self.Y is None else self.Y.shape[0]
+        self.num_data = model.num_data + self.q
+        self.num_outputs = model.num_outputs
+        self._chol = {}
+
+    def eval(self):
+        return self
+
+    def _solve_setup(self, o):
+        """Cholesky factors of S_b = C(X_b, X_b) + sigma^2 D_b for every batch element: [b, q, q]."""
+        if o not in self._chol:
+            m = self.model
+            C = posterior_cross_cov(m, o, self.idx_b, self.val_b, self.idx_b, self.val_b)            # [bq, bq]
+            blocks = torch.stack([C[i * self.q:(i + 1) * self.q, i * self.q:(i + 1) * self.q] for i in range(self.b)])
+            obs = self.noise[..., o]
+            if m.has_learnable_noise:
+                obs = obs * m._second_noise(o).detach()
+            self._chol[o] = torch.linalg.cholesky(blocks + torch.diag_embed(obs))
+        return self._chol[o]
+
+    def __call__(self, X_test):
+        """X_test [q*, d] -> MultivariateNormal-like with mean [(nf,) b, (t,) q*] and variance of the same trailing
+        shape (diagonal only: look-ahead acquisition functions read ``.variance`` / ``.mean``)."""
+        m = self.model
+        if X_test.dim() != 2:
+            raise NotImplementedError("test inputs must be [q*, d]")
+        lk = m.covar_module(X_test).evaluate_kernel()
+        idx_s, val_s = lk.left_interp_indices, lk.left_interp_values.detach()
+        base = m(X_test)
+        base_mean = base.mean.reshape(self.t, -1)
+        base_var = base.variance.reshape(self.t, -1)
+        base_at_b = m(self.idx_to_inputs()) if self.Y is not None else None
+        means, variances = [], []
+        for o in range(self.t):
+            Lb = self._solve_setup(o)                                                               # [b, q, q]
+            Csb = posterior_cross_cov(m, o, idx_s, val_s, self.idx_b, self.val_b)                   # [q*, bq]
+            Csb = Csb.reshape(-1, self.b, self.q).permute(1, 0, 2)                                  # [b, q*, q]
+            gain_t = torch.cholesky_solve(Csb.transpose(-1, -2), Lb)                                # [b, q, q*] = S^-1 C(X_b, x*)
+            variances.append(base_var[o].unsqueeze(0) - (Csb.transpose(-1, -2) * gain_t).sum(-2))   # [b, q*]
+            if self.Y is not None:
+                resid = self.Y[..., o] - base_at_b.mean.reshape(self.t, self.b, self.q)[o]          # [nf, b, q]
+                means.append(base_mean[o] + torch.einsum("fbq,bqs->fbs", resid, gain_t))            # [nf, b, q*]
+        var = torch.stack(variances, dim=1)                                                         # [b, t, q*]
+        if self.Y is None:
+            mean = base_mean.unsqueeze(0).expand(self.b, self.t, -1)
+        else:
+            mean = torch.stack(means, dim=2)                                                        # [nf, b, t, q*]
+            var = var.unsqueeze(0).expand(self.num_fantasies, *var.shape)
+        if self.t == 1:
+            mean, var = mean.squeeze(-2), var.squeeze(-2)
+        return _DiagNormal(mean, var.clamp_min(0.0))
+
+    def idx_to_inputs(self):
+        return self._X_flat
+
+    def posterior(self, X, observation_noise=False, **kwargs):
+        from .online_ski_botorch_model import GPyTorchPosterior
+        return GPyTorchPosterior(self(X))
+
+
+class _DiagNormal:
+    """Mean / variance container with the members ``GPyTorchPosterior`` reads."""
+
+    def __init__(self, mean, variance):
+        self.mean, self.variance = mean, variance
+
+    def rsample(self, sample_shape=torch.Size(), base_samples=None):
+        eps = torch.randn(*sample_shape, *self.mean.shape, dtype=self.mean.dtype, device=self.mean.device) \
+            if base_samples is None else base_samples
+        return self.mean + self.variance.sqrt() * eps

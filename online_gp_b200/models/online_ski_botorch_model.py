@@ -9,7 +9,7 @@ small ``GPyTorchPosterior`` stand-in with the members acquisition functions read
 import torch
 
 from .batched_fixed_noise_online_gp import FixedNoiseOnlineSKIGP
-from .fantasy import condition_on_target_batch
+from .fantasy import PredictiveSpaceFantasy, condition_on_target_batch
 
 
 class GPyTorchPosterior:
@@ -61,6 +61,13 @@ class OnlineSKIBotorchModel(FixedNoiseOnlineSKIGP):
         return super().forward(X, **kwargs)
 
     def condition_on_observations(self, X, Y, noise=None, inplace=False):
+        # candidate batches that differ per element (X [b, q, d]): predictive-space fantasies, no m-sized copies
+        if X.dim() == 3:
+            if inplace:
+                raise RuntimeError("a batch of candidate sets cannot be conditioned on in place")
+            if noise is not None and noise.dim() == 4:
+                noise = noise[0]
+            return PredictiveSpaceFantasy(self, X, Y, noise)
         # a batch of target draws at the same inputs (what ``fantasize`` produces): shared panels, batched caches
         if Y.dim() == X.dim() + 1 and X.dim() == 2:
             if inplace:

@@ -166,3 +166,53 @@ def test_dirichlet_ski_classifier_online_learned_features():
         assert clf.gp.num_data == 40
         assert not torch.equal(w0, clf.stem[0].weight.detach())           # the stem really trained
         assert clf.predict(train_x).shape == (40,)
+
+
+@pytest.mark.parametrize("t,learn", [(1, True), (1, False)])
+def test_predictive_space_fantasies_for_batched_candidates(t, learn):
+    """X [b, q, d] with different candidates per batch element: the predictive-space fantasy (exact Gaussian
+    conditional) equals explicitly conditioning the WISKI caches per element when the root is exact (Cholesky
+    regime) — means per draw and the look-ahead variances qNIPV integrates."""
+    model, X, Y, gen = _model(t=t, learn=learn, g=6)            # m = 36 <= max_cholesky_size: r = m
+    b, q, nf, d = 3, 2, 4, X.shape[-1]
+    Xc = torch.rand(b, q, d, generator=gen)
+    Yf = torch.randn(nf, b, q, t, generator=gen)
+    noise = 0.3 * torch.ones(b, q, t)
+    Xs = torch.rand(7, d, generator=gen)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.eval()
+        fm = model.condition_on_observations(Xc, Yf, noise)
+        out = fm(Xs)
+        assert out.mean.shape == (nf, b, 7) and out.variance.shape == (nf, b, 7)
+        for i in range(b):
+            for f in range(nf):
+                one = model.condition_on_observations(Xc[i], Yf[f, i], noise[i], inplace=False)
+                one.eval()
+                ref = one(Xs)
+                assert torch.allclose(out.mean[f, i], ref.mean.reshape(-1), rtol=1e-7, atol=1e-9), (i, f)
+                assert torch.allclose(out.variance[f, i], ref.variance.reshape(-1), rtol=1e-6, atol=1e-9), (i, f)
+        # variance-only form (no targets): what qNegIntegratedPosteriorVariance needs
+        vo = model.condition_on_observations(Xc, None, noise)(Xs)
+        assert torch.allclose(vo.variance, out.variance[0], rtol=1e-12)
+        # differentiable w.r.t. the candidates (acquisition optimisation)
+        Xg = Xc.clone().requires_grad_(True)
+        val = model.condition_on_observations(Xg, None, noise)(Xs).variance.sum()
+        val.backward()
+        assert Xg.grad is not None and bool(torch.isfinite(Xg.grad).all()) and float(Xg.grad.abs().sum()) > 0
+
+
+def test_fantasize_with_batched_candidates_end_to_end():
+    """``fantasize(X [b, q, d], sampler)`` -> look-ahead posterior at MC points, shapes as BoTorch's qNIPV reads them."""
+    from online_gp_b200.models.fantasy import PredictiveSpaceFantasy
+    model, X, Y, gen = _model(t=1, learn=True, g=6)
+    Xc = torch.rand(4, 3, 2, generator=gen)
+    mc = torch.rand(11, 2, generator=gen)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fm = model.fantasize(Xc, lambda post: post.rsample(torch.Size([5])))
+        assert isinstance(fm, PredictiveSpaceFantasy) and fm.num_fantasies == 5
+        post = fm.posterior(mc)
+        assert post.mean.shape == (5, 4, 11, 1) and post.variance.shape == (5, 4, 11, 1)
+        v0 = model.posterior(mc).variance.reshape(-1)
+        assert bool((post.variance[0, :, :, 0] <= v0 + 1e-10).all())          # conditioning never increases the variance
