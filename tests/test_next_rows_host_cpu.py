@@ -216,3 +216,72 @@ def test_fantasize_with_batched_candidates_end_to_end():
         assert post.mean.shape == (5, 4, 11, 1) and post.variance.shape == (5, 4, 11, 1)
         v0 = model.posterior(mc).variance.reshape(-1)
         assert bool((post.variance[0, :, :, 0] <= v0 + 1e-10).all())          # conditioning never increases the variance
+
+
+def test_bayesopt_loop_plumbing_ackley3d():
+    """BASELINE config 4 in miniature (experiments/bayesopt/bayesopt.py:65-101,176-230): Ackley-3D on the unit cube,
+    WISKI with a 10^3 grid, Matern-5/2 product kernel with Gamma priors and Interval constraints, UCB over random
+    candidates, q = 3, the model re-hydrated from the previous kernel cache every step and conditioned out of place."""
+    import math
+    from online_gp_b200 import settings as S
+    from online_gp_b200.kernels import GammaPrior, Interval, MaternKernel, ScaleKernel
+    from online_gp_b200.mlls import BatchedWoodburyMarginalLogLikelihood
+    from online_gp_b200.models import OnlineSKIBotorchModel
+
+    def ackley(u):                       # negated Ackley on [-32.768, 32.768]^3, inputs in the unit cube
+        x = (u * 2 - 1) * 32.768
+        a, b, c = 20.0, 0.2, 2 * math.pi
+        val = -a * torch.exp(-b * x.pow(2).mean(-1).sqrt()) - torch.exp(torch.cos(c * x).mean(-1)) + a + math.e
+        return -val
+
+    gen = torch.Generator().manual_seed(0)
+    torch.manual_seed(0)
+    d, q = 3, 3
+    X = torch.rand(10, d, generator=gen)
+    raw = ackley(X)
+    mu, sd = raw.mean(), raw.std()
+    Y = ((raw - mu) / sd).unsqueeze(-1)
+    noise = (4.0 / float(sd)) ** 2 * 1e-4 * torch.ones_like(Y)
+    bounds = torch.tensor([[0.0, 1.0]] * d)
+    model, best0 = None, float(Y.max())
+    with warnings.catch_warnings(), S.cholesky_jitter(1e-3), S.max_cholesky_size(2048):
+        warnings.simplefilter("ignore")
+        for step in range(4):
+            if model is None:
+                covar = ScaleKernel(MaternKernel(nu=2.5, lengthscale_prior=GammaPrior(3.0, 6.0),
+                                                 lengthscale_constraint=Interval(1e-4, 12.0)),
+                                    outputscale_prior=GammaPrior(2.0, 0.15), outputscale_constraint=Interval(1e-4, 12.0))
+                cache = None
+            else:
+                covar, cache = model.covar_module, model._kernel_cache
+            model = OnlineSKIBotorchModel(X, Y, train_noise_term=noise, grid_bounds=bounds, grid_size=10,
+                                          learn_additional_noise=True, kernel_cache=cache, covar_module=covar).to(X)
+            mll = BatchedWoodburyMarginalLogLikelihood(model.likelihood, model, clear_caches_every_iteration=True)
+            opt = torch.optim.Adam(model.parameters(), lr=0.05)
+            model.train()
+            for _ in range(5):                                  # stands in for fit_gpytorch_model (L-BFGS in BoTorch)
+                opt.zero_grad()
+                loss = -mll(model(X), Y).sum()
+                loss.backward()
+                opt.step()
+                assert bool(torch.isfinite(loss))
+            model.zero_grad()
+            cand = torch.rand(64, q, d, generator=gen)           # 64 candidate sets of q points (batched posterior)
+            post = model.posterior(cand)
+            ucb = (post.mean + math.sqrt(2.0) * post.variance.clamp_min(0).sqrt()).squeeze(-1).max(-1)[0]
+            new_x = cand[ucb.argmax()]
+            new_y = ((ackley(new_x) - mu) / sd).unsqueeze(-1)
+            new_noise = noise[:q]
+            X, Y, noise = torch.cat([X, new_x]), torch.cat([Y, new_y]), torch.cat([noise, new_noise])
+            model = model.condition_on_observations(X=new_x, Y=new_y, noise=new_noise)
+            assert model.num_data == X.shape[0]
+        assert model._kernel_cache["interpolation_cache"].shape[-2] == 1000
+        assert float(Y.max()) >= best0
+        # the streamed model still agrees with one built from scratch on all the data (same hyper-parameters)
+        scratch = OnlineSKIBotorchModel(X, Y, train_noise_term=noise, grid_bounds=bounds, grid_size=10,
+                                        learn_additional_noise=True, covar_module=model.covar_module).to(X)
+        scratch.likelihood = model.likelihood
+        Xs = torch.rand(9, d, generator=gen)
+        a, b = model.posterior(Xs), scratch.posterior(Xs)
+        assert torch.allclose(a.mean.reshape(-1), b.mean.reshape(-1), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(a.variance.reshape(-1), b.variance.reshape(-1), rtol=1e-4, atol=1e-7)
