@@ -285,3 +285,34 @@ def test_bayesopt_loop_plumbing_ackley3d():
         a, b = model.posterior(Xs), scratch.posterior(Xs)
         assert torch.allclose(a.mean.reshape(-1), b.mean.reshape(-1), rtol=1e-5, atol=1e-6)
         assert torch.allclose(a.variance.reshape(-1), b.variance.reshape(-1), rtol=1e-4, atol=1e-7)
+
+
+def test_qnipv_active_learning_plumbing():
+    """BASELINE config 5 in miniature (experiments/active_learning/qnIPV_experiment.py:85-105,137-212): Matern-1/2,
+    heteroskedastic fixed noise, no learnable noise; candidate sets of q = 6 scored by the negative integrated posterior
+    variance over MC points through variance-only predictive-space fantasies; the chosen set is conditioned on and the
+    integrated variance really drops to the look-ahead value."""
+    from online_gp_b200 import settings as S
+    from online_gp_b200.kernels import MaternKernel, ScaleKernel
+    from online_gp_b200.models import OnlineSKIBotorchModel
+    gen = torch.Generator().manual_seed(3)
+    d, q = 2, 6
+    X = torch.rand(10, d, generator=gen)
+    Y = torch.sin(6 * X[:, :1]) * torch.cos(4 * X[:, 1:])
+    D = torch.rand(10, 1, generator=gen) * 0.09 + 0.01 + 1e-6            # data.py:71
+    with warnings.catch_warnings(), S.max_cholesky_size(2048), S.skip_posterior_variances(False):
+        warnings.simplefilter("ignore")
+        model = OnlineSKIBotorchModel(X, Y, train_noise_term=D, grid_bounds=torch.tensor([[0.0, 1.0]] * d), grid_size=16,
+                                      learn_additional_noise=False, covar_module=ScaleKernel(MaternKernel(nu=0.5)))
+        mc = torch.rand(200, d, generator=gen)
+        ipv0 = float(model.posterior(mc).variance.mean())
+        cand = torch.rand(12, q, d, generator=gen)
+        cand_noise = 0.05 * torch.ones(12, q, 1)
+        look = model.condition_on_observations(cand, None, cand_noise).posterior(mc).variance.mean(dim=(-2, -1))   # [12]
+        assert look.shape == (12,) and bool((look <= ipv0 + 1e-12).all())
+        best = int(look.argmin())
+        new_y = torch.sin(6 * cand[best][:, :1]) * torch.cos(4 * cand[best][:, 1:])
+        model2 = model.condition_on_observations(X=cand[best], Y=new_y, noise=cand_noise[best])
+        ipv1 = float(model2.posterior(mc).variance.mean())
+        assert abs(ipv1 - float(look[best])) <= 1e-8 * max(1.0, ipv0)        # look-ahead value == realised value
+        assert ipv1 < ipv0
