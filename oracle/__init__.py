@@ -16,6 +16,7 @@ in ``tests/golden/`` together with the generating script ``oracle/make_golden.py
 
 Modules
   interp      - GPyTorch ``create_grid`` / ``Interpolation.interpolate`` / ``left_interp`` restated
+  interp_np   - the same stencils a second time, numpy scalar loops, no torch (independent check of the bit-exact indices)
   gridkernel  - per-dimension Toeplitz columns of K_uu and the Kronecker-Toeplitz MVM
   exact_gp    - dense exact GP on the SKI kernel  W K W^T + sigma^2 D   (the independent check)
   wiski_ref   - reference-literal restatement (dense W^T D^-1 W, Cholesky dispatch, SVD root update)

@@ -144,3 +144,32 @@ def test_matfree_lowrank_is_projected_update():
         PV = L0 @ (B0.t() @ V)
         assert torch.allclose(mf.L @ mf.L.t(), L0 @ L0.t() + PV @ PV.t(), atol=1e-9)
         assert torch.allclose(mf.B.t() @ mf.L, torch.eye(L0.shape[1], dtype=T64), atol=1e-8)
+
+
+def test_numpy_index_oracle_agrees_with_torch_oracle_and_golden(golden_dir):
+    """Second, torch-free restatement of the interpolation stencils (oracle/interp_np.py): indices identical to the
+    torch oracle and to the frozen golden vectors, values equal to rounding (the tap weights multiply in a different
+    association order)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle.interp import create_grid, interpolate
+    from oracle.interp_np import interpolate_np
+    z = np.load(os.path.join(golden_dir, "g0_interp.npz"))
+    for name in ("d1", "d2", "d3", "d4"):
+        grid = create_grid(z[f"{name}_sizes"].tolist(), [tuple(b) for b in z[f"{name}_bounds"].tolist()])
+        grids_np = [g.numpy() for g in grid]
+        for tag in ("f32", "f64"):
+            x = z[f"{name}_{tag}_x"][:6]
+            idx_np, val_np = interpolate_np(grids_np, x)
+            assert np.array_equal(idx_np, z[f"{name}_{tag}_idx"][:6]), (name, tag)
+            idx_t, val_t = interpolate(grid, torch.from_numpy(x))
+            assert np.array_equal(idx_np, idx_t.numpy())
+            eps = np.finfo(x.dtype).eps
+            assert np.allclose(val_np, z[f"{name}_{tag}_val"][:6], rtol=16 * eps, atol=16 * eps)
+    # boundary stencils (one-hot on the nearest of the first / last four grid points)
+    grid = create_grid([10], [(0.0, 1.0)])
+    x = np.array([[-0.12], [1.12], [0.5]], dtype=np.float64)
+    idx_np, val_np = interpolate_np([grid[0].numpy()], x)
+    idx_t, val_t = interpolate(grid, torch.from_numpy(x))
+    assert np.array_equal(idx_np, idx_t.numpy()) and np.allclose(val_np, val_t.numpy(), atol=1e-12)
