@@ -385,7 +385,8 @@ def run_gpu_sharded(args, rank, world, device, dtype):
     torch.set_default_dtype(dtype)
     x, y = synth_stream(d, n_init + 4096)
     x, y = x.to(dtype), y.to(dtype)
-    ctx = (S.max_root_decomposition_size(MAX_ROOT), S.max_cholesky_size(MAX_CHOL), S.cg_tolerance(CG_TOL))
+    ctx = (S.max_root_decomposition_size(MAX_ROOT), S.max_cholesky_size(MAX_CHOL), S.cg_tolerance(CG_TOL),
+           S.sharded_dual_layout(bool(args.dual_layout)))
     for c in ctx:
         c.__enter__()
     model = ShardedOnlineSKIRegression(x[:n_init].to(device), y[:n_init].to(device), lr=5e-3, grid_size=g,
@@ -459,7 +460,8 @@ def run_gpu_sharded(args, rank, world, device, dtype):
                        "rows_per_gpu": m // world,
                        "l2": "per-GPU panel slab (%.2f GB) larger than L2" % (m // world * r * b / 1e9),
                        "step": "evaluate + update (Adam step on Woodbury MLL + condition_on_observations)",
-                       "cuda_graphs": bool(use_graphs)},
+                       "cuda_graphs": bool(use_graphs), "dual_layout": bool(args.dual_layout),
+                       "exchange": "peer memory" if model.comm.xbuf is not None else "nccl all_to_all"},
             "clocks": clk,
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": q * (d + 1) * b,
                     "d2h_bytes_per_step": 3 * b},
@@ -565,6 +567,8 @@ def main():
     ap.add_argument("--workload", default="powerplant_4d_g32", choices=sorted(WORKLOADS))
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dual-layout", action="store_true",
+                    help="N > 1: settings.sharded_dual_layout (two row <-> column exchanges per step instead of four)")
     ap.add_argument("--no-graphs", action="store_true", help="run the timed steps eagerly instead of replaying CUDA graphs")
     ap.add_argument("--cpu-budget", type=float, default=30.0, help="seconds of CPU work for the cpu_baseline leg")
     args = ap.parse_args()

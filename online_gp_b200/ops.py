@@ -374,15 +374,21 @@ class _KronFn(torch.autograd.Function):
     keeps the suffix products S_i = T_{i+1} .. T_{d-1} X, so the backward only runs the prefix chain on the incoming
     gradient plus one contraction per axis (d-1 axis passes instead of 2(d-1))."""
 
+    #: optional destination of the next forward's result (set by ``kron_toeplitz_matmul(out=...)``; kept out of the
+    #: autograd inputs so that the result is an ordinary fresh output as far as autograd is concerned)
+    _next_out = None
+
     @staticmethod
     def forward(ctx, cols, X, sizes, dirs=None):
+        out, _KronFn._next_out = _KronFn._next_out, None
         cols = cols.contiguous()
         ctx.sizes = sizes
         ctx.dirs = None
         if not ctx.needs_input_grad[0]:
             ctx.save_for_backward(cols, X)
             ctx.suffix = None
-            return _kron_mm(cols, sizes, X)
+            Y = _kron_mm(cols, sizes, X)
+            return Y if out is None else out.copy_(Y)
         if _fused_supported(sizes, X):
             # pairs applied last to first; M[p] = (pairs > p) applied to X is what the backward pair pass p needs
             npairs = len(sizes) // 2
@@ -390,7 +396,7 @@ class _KronFn(torch.autograd.Function):
             M[-1] = X.contiguous()
             for p in range(npairs - 1, 0, -1):
                 M[p - 1] = _fused_pair_apply(cols, sizes, p, M[p])
-            Y = _fused_pair_apply(cols, sizes, 0, M[0])
+            Y = _fused_pair_apply(cols, sizes, 0, M[0], out=out)       # `out`: e.g. the send buffer of an exchange
             ctx.save_for_backward(cols, *M)
             ctx.suffix = "fused"
             ctx.dirs = None if dirs is None else dirs.detach().to(cols.dtype).contiguous()
@@ -405,7 +411,7 @@ class _KronFn(torch.autograd.Function):
         Y = kron_axis_apply(S[0], cols[0], g, outer, inner)
         ctx.save_for_backward(cols, *S)
         ctx.suffix = True
-        return Y
+        return Y if out is None else out.copy_(Y)
 
     @staticmethod
     def backward(ctx, gY):
@@ -444,7 +450,7 @@ class _KronFn(torch.autograd.Function):
         return acc.to(cols.dtype), gX, None, None
 
 
-def kron_toeplitz_matmul(cols, sizes, X, dirs=None):
+def kron_toeplitz_matmul(cols, sizes, X, dirs=None, out=None):
     """(T(cols[0]) x ... x T(cols[d-1])) @ X for X [m,c]; cols [d,gmax] (row i valid in its first sizes[i] entries).
     Differentiable w.r.t. cols and X.  ``dirs`` [d,gmax] (optional): d cols[i] / d lengthscale_i; when given (and the
     fused fp32 path applies) the backward returns a *surrogate* column gradient that is exact for parameters moving
@@ -454,8 +460,13 @@ def kron_toeplitz_matmul(cols, sizes, X, dirs=None):
     if cols.dtype != X.dtype:
         raise TypeError("kron_toeplitz_matmul: cols and X must share a dtype")
     if torch.is_grad_enabled() and (cols.requires_grad or X.requires_grad):
-        return _KronFn.apply(cols, X, tuple(sizes), dirs)
-    return _kron_mm(cols.detach().contiguous(), tuple(sizes), X.detach())
+        _KronFn._next_out = out
+        try:
+            return _KronFn.apply(cols, X, tuple(sizes), dirs)
+        finally:
+            _KronFn._next_out = None
+    Y = _kron_mm(cols.detach().contiguous(), tuple(sizes), X.detach())
+    return Y if out is None else out.copy_(Y)
 
 
 def kron_axis_apply(X, col, g, outer, inner):

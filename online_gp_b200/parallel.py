@@ -331,6 +331,34 @@ class _ShardedGramBlocksFn(torch.autograd.Function):
         return None, ops.rmul_blocks(A, gG.contiguous(), ctx.nb, out=out), None
 
 
+class _AllReduceGradFn(torch.autograd.Function):
+    """Identity on a replicated tensor whose consumers are rank-local: the backward sums the per-rank gradients."""
+
+    @staticmethod
+    def forward(ctx, t, comm):
+        ctx.comm = comm
+        return t.view_as(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.comm.allreduce_(g.contiguous().clone()), None
+
+
+class _ColsToRowBlocksFn(torch.autograd.Function):
+    """Column-sharded panel [m, cw] (all rows of my columns) -> row-sharded column blocks [world, m_loc, cw] (my rows of
+    every column block): one exchange; the backward is the inverse exchange."""
+
+    @staticmethod
+    def forward(ctx, Yc, plan, comm):
+        ctx.plan, ctx.comm = plan, comm
+        return comm.all_to_all(Yc.view(plan.world, plan.m_loc, Yc.shape[1]))
+
+    @staticmethod
+    def backward(ctx, gB):
+        plan = ctx.plan
+        return ctx.comm.all_to_all(gB.contiguous()).view(plan.world * plan.m_loc, gB.shape[2]), None, None
+
+
 class _ShardedGramFn(torch.autograd.Function):
     """A_loc^T B_loc summed over ranks (replicated result); gradient w.r.t. the sharded B_loc only."""
 
@@ -420,7 +448,11 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         self.plan = ShardPlan(sizes, self.comm.world, self.comm.rank)
         self.dtype = init_y.dtype
         self.gp_optimizer = torch.optim.Adam(self.parameters(), lr=lr)
+        self._dual = settings.sharded_dual_layout.on()
+        self.Lc = None
         self._init_caches(init_x, init_y[:, 0], torch.ones_like(init_y[:, 0]))
+        if self._dual:
+            self.Lc = self._rows_to_cols(self.L_loc)           # [m, r / world]: all rows of my columns
         self._pieces = None
         if self.comm.world > 1 and init_x.is_cuda and _fused_ok(self.plan, self.L_loc):
             self.comm.enable_peer_exchange(self.L_loc.numel(), self.dtype, init_x.device)
@@ -477,13 +509,27 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         self.L_loc = ops.panel_rmul(self.L_loc, F.to(self.dtype).contiguous())
         self.B_loc = ops.panel_rmul(self.B_loc, Finv_t.to(self.dtype).contiguous())
 
+    def _rows_to_cols(self, P_loc):
+        """Row slab [m_loc, r] -> column block [m, r / world] (one all-to-all; used once, at construction)."""
+        W, plan = self.comm.world, self.plan
+        cw = P_loc.shape[1] // W
+        send = P_loc.view(plan.m_loc, W, cw).permute(1, 0, 2).contiguous()
+        return self.comm.all_to_all(send).reshape(W * plan.m_loc, cw).contiguous()
+
     def _root_update(self, idx_l, vval_l):
         """collect_vector (updated_root_lazy_tensor.py:69-119), symmetric-square-root form, panels updated in place."""
         for s0 in range(0, idx_l.shape[0], 32):
             pT = self.comm.allreduce_(ops.left_interp(idx_l[s0:s0 + 32], vval_l[s0:s0 + 32], self.B_loc))
             p = pT.t().contiguous()
             C, Cp = _sym_factors(p)
-            ops.panel_lowrank_update_(self.L_loc, p, C @ p.t())
+            CpT = C @ p.t()
+            if self.Lc is not None:
+                # the same update on the column-sharded copy: L p for ALL rows (all-gather of an m x q vector), then
+                # Lc += (L p) (C p^T)[:, my columns]
+                cw = self.Lc.shape[1]
+                t_full = self.comm.allgather(ops.panel_rmul(self.L_loc, p)).reshape(self.plan.m, p.shape[1])
+                self.Lc.addmm_(t_full, CpT[:, self.comm.rank * cw:(self.comm.rank + 1) * cw])
+            ops.panel_lowrank_update_(self.L_loc, p, CpT)
             ops.panel_lowrank_update_(self.B_loc, p, Cp @ p.t())
 
     # ---- pieces with grad (Kuu / sigma^2, K L, Q, K b, c)  — batched_fixed_noise_online_gp.py:334-366
@@ -498,7 +544,16 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         cols = cols * scale                                                       # Kuu / sigma^2 (:340)
         dirs = self.covar_module.base_kernel.grid_column_dirs(self.covar_module.grid) \
             if settings.kron_directional_grad.on() else None
-        KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm, dirs)             # :348  column blocks [nb, m_loc, r / nb]
+        if self.Lc is not None:
+            # dual layout: K L on the column-sharded copy is the ordinary (single-device) Kronecker MVM with its own
+            # autograd; one exchange brings it to row-sharded column blocks, the backward sends the gradient back
+            cw = self.Lc.shape[1]
+            xb = comm.send_buffer(plan.m * cw, self.Lc)
+            KLc = ops.kron_toeplitz_matmul(_AllReduceGradFn.apply(cols, comm), plan.sizes, self.Lc, dirs=None,
+                                           out=None if xb is None else xb.view(plan.m, cw))
+            KL = _ColsToRowBlocksFn.apply(KLc, plan, comm)
+        else:
+            KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm, dirs)         # :348  column blocks [nb, m_loc, r / nb]
         r = self.L_loc.shape[1]
         Q = _ShardedGramBlocksFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355
         b_full = comm.allgather(self.b_loc).reshape(plan.m, 1)

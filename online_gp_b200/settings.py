@@ -146,6 +146,15 @@ class kron_tensor_core_axes(_feature_flag):
     _state = True
 
 
+class sharded_dual_layout(_feature_flag):
+    """Row-sharded model: additionally keep the root panel in the column-sharded layout (all rows of r / world
+    columns, maintained by the rank-q update with one all-gather of an m x q vector).  ``K L`` is then a purely local
+    Kronecker MVM and the hyper-gradient a purely local column-gradient pass, which halves the row <-> column
+    exchanges per step (2 instead of 4) at the price of one more slab-sized panel per rank.  Logic covered by the
+    world-2 gloo tests; off by default until it has been timed on multi-GPU hardware."""
+    _state = False
+
+
 class defer_interp_bounds_check(_feature_flag):
     """Queue the out-of-bounds flag of ``ops.interpolate`` (async copy to pinned memory + event) instead of reading
     it back at once; ``ops.flush_bounds_checks()`` raises later without stalling the stream.  Used by

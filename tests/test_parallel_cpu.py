@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
-def _worker(rank, world, port, d, g, n0, steps, ret):
+def _worker(rank, world, port, d, g, n0, steps, ret, dual=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -32,7 +32,8 @@ def _worker(rank, world, port, d, g, n0, steps, ret):
     out = []
     # max_cholesky_size(0): low-rank initial root AND every Q solve of predict() through the sharded CG driver (one
     # all-reduce per iteration); a tight tolerance makes it comparable with the oracle's dense solves
-    with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64), S.eval_cg_tolerance(1e-13):
+    with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64), S.eval_cg_tolerance(1e-13), \
+            S.sharded_dual_layout(dual):
         model = ShardedOnlineSKIRegression(X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0, comm=Comm())
         for t in range(steps):
             xt, yt = X[n0 + 2 * t:n0 + 2 * t + 2], y[n0 + 2 * t:n0 + 2 * t + 2]
@@ -41,6 +42,9 @@ def _worker(rank, world, port, d, g, n0, steps, ret):
             out.append((rmse, nll, loss, float(model._noise())))
         ls = model.covar_module.base_kernel.base_kernel.lengthscale.detach().reshape(-1).tolist()
     assert model.last_cg[0] >= 10 and model.last_cg[1] < 1e-12          # the CG path really ran and converged
+    assert (model.Lc is not None) == dual
+    if dual:        # the column-sharded copy followed every rank-q update: it equals the exchanged row slab
+        assert torch.allclose(model.Lc, model._rows_to_cols(model.L_loc), rtol=1e-10, atol=1e-12)
     ret[rank] = (out, ls, model.L_loc.shape)
     dist.barrier()
     dist.destroy_process_group()
@@ -77,12 +81,15 @@ def _oracle_loop(d, g, n0, steps):
 
 
 @pytest.mark.parametrize("d,g,n0", [(2, 8, 20), (3, 6, 30), (2, 10, 90)])   # last: n0 > root rank (batched fold-in)
-def test_sharded_stream_matches_unsharded_oracle(d, g, n0):
+@pytest.mark.parametrize("dual", [False, True])
+def test_sharded_stream_matches_unsharded_oracle(d, g, n0, dual):
+    """dual = True: ``settings.sharded_dual_layout`` (K L and its gradient computed on a column-sharded copy of the
+    root panel: two exchanges per step instead of four)."""
     world, steps = 2, 3
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, d, g, n0, steps, ret), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + (7 if dual else 0)
+    mp.spawn(_worker, args=(world, port, d, g, n0, steps, ret, dual), nprocs=world, join=True)
     ref, ls_ref = _oracle_loop(d, g, n0, steps)
     for rank in range(world):
         out, ls, shape = ret[rank]

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--q", type=int, default=1)
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--watchdog", type=float, default=0.0, help="dump all Python stacks and exit after this many seconds")
+    ap.add_argument("--dual", action="store_true", help="settings.sharded_dual_layout")
     ap.add_argument("--graphs", action="store_true", help="replay the sharded step as CUDA graphs (eager single-GPU reference)")
     args = ap.parse_args()
     if args.watchdog > 0:
@@ -52,7 +53,7 @@ def main():
     X = (torch.rand(n, args.d, generator=gen) * 2 - 1).to(dtype).to(dev)
     y = torch.sin(3 * X.sum(-1, keepdim=True)) + 0.1 * torch.randn(n, 1, generator=gen).to(dtype).to(dev)
     rows = []
-    with S.max_root_decomposition_size(512), S.max_cholesky_size(2048):
+    with S.max_root_decomposition_size(512), S.max_cholesky_size(2048), S.sharded_dual_layout(args.dual):
         sh = ShardedOnlineSKIRegression(X[:args.n0], y[:args.n0], lr=1e-2, grid_size=args.g, grid_bound=1.0, comm=Comm())
         if args.graphs:
             sh.enable_cuda_graphs(True, warmup_calls=1)
