@@ -116,3 +116,134 @@ def test_shard_plan_and_layout_roundtrip():
     one = ShardPlan([4, 4], world=1, rank=0)
     X = torch.randn(16, 3)
     assert torch.equal(_to_rows(_to_cols(X, one, Comm()), one, Comm()), X)
+
+
+# ---- the fused (default multi-GPU) orchestration of _ShardedKronFn on CPU: the pair kernels are emulated for small
+# axes (4 points instead of 32), including the column-chunked layouts of the all-to-all send / receive buffers
+def _toeplitz(col, g):
+    ar = torch.arange(g)
+    return col[(ar.unsqueeze(0) - ar.unsqueeze(1)).abs()]
+
+
+def _install_fused_emulation(ops, parallel, axis):
+    def pair_views(sizes, pair, X):
+        c = X.shape[1]
+        u, v = sizes[2 * pair], sizes[2 * pair + 1]
+        before = 1
+        for s in sizes[:2 * pair]:
+            before *= s
+        after = X.shape[0] // (before * u * v)
+        return X.reshape(before, u, v, after, c), u, v
+
+    def unchunk(Zb):                        # [W, m, cw] -> [m, W cw]
+        W, m, cw = Zb.shape
+        return Zb.permute(1, 0, 2).reshape(m, W * cw)
+
+    def pair_apply(cols, sizes, pair, X, chunk_out=1, out=None):
+        V, u, v = pair_views(sizes, pair, X)
+        Tu, Tv = _toeplitz(cols[2 * pair], u), _toeplitz(cols[2 * pair + 1], v)
+        Y = torch.einsum("ab,cd,obdwk->oacwk", Tu, Tv, V).reshape(X.shape)
+        if chunk_out > 1:
+            m, c = X.shape
+            Y = Y.view(m, chunk_out, c // chunk_out).permute(1, 0, 2).contiguous()
+        return Y if out is None else out.copy_(Y)
+
+    def pair_grad(cols, sizes, pair, Z, P, acc, store, chunk_z=1, zout=None):
+        if chunk_z > 1:
+            Z = unchunk(Z)
+        Zv, u, v = pair_views(sizes, pair, Z)
+        Pv, _, _ = pair_views(sizes, pair, P)
+        Tu, Tv = _toeplitz(cols[2 * pair], u), _toeplitz(cols[2 * pair + 1], v)
+        TvP = torch.einsum("cd,obdwk->obcwk", Tv, Pv)
+        TuZ = torch.einsum("ab,obdwk->oadwk", Tu, Zv)
+        Su = torch.einsum("oadwk,obdwk->ab", Zv.double(), TvP.double())
+        Sv = torch.einsum("oadwk,oaewk->de", TuZ.double(), Pv.double())
+        for S, g, slot in ((Su, u, 2 * pair), (Sv, v, 2 * pair + 1)):
+            ar = torch.arange(g)
+            off = (ar.unsqueeze(0) - ar.unsqueeze(1)).abs().reshape(-1)
+            acc[slot][:g] += torch.zeros(g, dtype=torch.float64).index_add_(0, off, S.reshape(-1))
+        if not store:
+            return None
+        Zo = torch.einsum("cd,oadwk->oacwk", Tv, TuZ).reshape(P.shape)
+        return Zo if zout is None else zout.copy_(Zo)
+
+    saved = (ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok)
+    ops._fused_pair_apply, ops._fused_pair_grad = pair_apply, pair_grad
+    parallel._fused_ok = lambda plan, X: plan.d == 4 and all(s == axis for s in plan.sizes) and \
+        X.shape[1] % (16 * plan.world) == 0
+    return saved
+
+
+def _fused_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_default_dtype(torch.float64)
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cpu_ops_mock
+    from online_gp_b200 import ops, parallel, settings as S
+    warnings.simplefilter("ignore")
+    gen = torch.Generator().manual_seed(3)
+    d, g, n0, steps = 4, 4, 40, 3
+    X = torch.rand(n0 + steps, d, generator=gen) * 2 - 1
+    y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen)).unsqueeze(-1)
+    out = []
+    with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64), S.eval_cg_tolerance(1e-13):
+        saved = _install_fused_emulation(ops, parallel, g)
+        try:
+            model = parallel.ShardedOnlineSKIRegression(X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0,
+                                                        comm=parallel.Comm())
+            assert parallel._fused_ok(model.plan, model.L_loc)
+            for t in range(steps):
+                xt, yt = X[n0 + t:n0 + t + 1], y[n0 + t:n0 + t + 1]
+                rmse, nll = model.evaluate(xt, yt)
+                P = model.pieces()
+                assert P["KL"].shape == (world, model.plan.m_loc, model.L_loc.shape[1] // world)     # column blocks
+                _, loss = model.update(xt, yt)
+                out.append((rmse, nll, loss, float(model._noise())))
+        finally:
+            ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok = saved
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_fused_sharded_orchestration_matches_unsharded_oracle():
+    """The default multi-GPU path (slab-local pair, exchange, column-sharded pair, column blocks through Gram / rmul /
+    gathers, chunked operands in the backward) with the pair kernels emulated on a 4^4 grid."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29500 + (os.getpid() % 2000) + 13
+    mp.spawn(_fused_worker, args=(world, port, ret), nprocs=world, join=True)
+    from oracle.gridkernel import Hypers
+    from oracle.interp import create_grid
+    from oracle.wiski_matfree import WiskiMatFree
+    torch.set_default_dtype(torch.float64)
+    gen = torch.Generator().manual_seed(3)
+    d, g, n0, steps = 4, 4, 40, 3
+    X = torch.rand(n0 + steps, d, generator=gen) * 2 - 1
+    y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen)).unsqueeze(-1)
+    hyp = Hypers(d, learn_noise=True)
+    orc = WiskiMatFree(create_grid([g] * d, [(-1.1, 1.1)] * d), hyp, X[:n0], y[:n0, 0], torch.ones(n0),
+                       max_cholesky_size=0, max_root=64, update_mode="svd")
+    opt = torch.optim.Adam(hyp.params(), lr=1e-2)
+    for t in range(steps):
+        xt, yt = X[n0 + t:n0 + t + 1], y[n0 + t:n0 + t + 1, 0]
+        with torch.no_grad():
+            mo, co = orc.predict(xt)
+            var = co.diagonal() + hyp.noise
+            rmse_o = float((mo - yt).pow(2).mean().sqrt())
+            nll_o = float(-torch.distributions.Normal(mo, var.sqrt()).log_prob(yt).mean())
+        opt.zero_grad()
+        (-orc.mll()).backward()
+        opt.step()
+        orc.condition_on_observations(xt, yt, torch.ones(1))
+        for rank in range(world):
+            rmse, nll, loss, noise = ret[rank][t]
+            assert abs(rmse - rmse_o) <= 1e-6 * max(1.0, abs(rmse_o)) and abs(nll - nll_o) <= 1e-6 * max(1.0, abs(nll_o))
+            assert abs(noise - float(hyp.noise)) <= 1e-8            # complete hyper-gradients on every rank
+    torch.set_default_dtype(torch.float32)
+    assert ret[0] == ret[1]
