@@ -13,48 +13,42 @@ from torch import nn
 
 
 class BatchedWoodburyMarginalLogLikelihood(nn.Module):
+    """``mll(distro, targets)`` -> tensor of shape ``batch_shape`` (one value per GP output), already divided by the
+    number of observations.  Both arguments are ignored: everything comes from the model's caches."""
+
     def __init__(self, likelihood, model, clear_caches_every_iteration=False):
         super().__init__()
-        self.likelihood = likelihood
-        self.model = model
-        self.has_learnable_noise = self.likelihood.second_noise_covar is not None
+        self.likelihood, self.model = likelihood, model
         self.clear_caches_every_iteration = clear_caches_every_iteration
+        self.has_learnable_noise = likelihood.second_noise_covar is not None
 
     def named_priors(self):
         yield from self.model.named_priors()
 
     def forward(self, distro, targets, *args):
+        gp = self.model
         if self.clear_caches_every_iteration:
-            self.model.zero_grad()  # for the time being to clear caches
+            gp.zero_grad()                       # the BO loop refits from scratch every step (bayesopt.py:98-100)
+        caches = gp._kernel_cache
 
-        current_cache = self.model._kernel_cache
+        # quadratic form  y^T D^-1 y - b^T K b + c^T Q^-1 c  and  log|Q| + log|D|,  Q = I + L^T K L
+        quad_q, logdet_q = gp.current_qmatrix.inv_quad_logdet(inv_quad_rhs=gp.root_space_projection, logdet=True)
+        b = caches["interpolation_cache"]
+        b_K_b = b.transpose(-1, -2).matmul(gp.Kuu_response)
+        quad = (caches["response_cache"] - b_K_b).sum((-2, -1)) + quad_q
+        logdet = logdet_q + caches["D_logdet"]
 
-        # I + L'KL
-        inner_qmat = self.model.current_qmatrix
-        inner_qform, inner_logdet = inner_qmat.inv_quad_logdet(
-            inv_quad_rhs=self.model.root_space_projection, logdet=True
-        )
-        inducing_qform = current_cache["interpolation_cache"].transpose(-1, -2).matmul(self.model.Kuu_response)
-        inv_quad_term = (current_cache["response_cache"] - inducing_qform).sum((-2, -1)) + inner_qform
-        logdet_term = inner_logdet + current_cache["D_logdet"]
-
-        num_data = self.model.num_data
-        if getattr(self.model, "_num_data_t", None) is not None:
-            num_data = self.model._num_data_t       # device-side counter (CUDA-graph mode): same value, no host constant
-
-        # add in add'l noise
-        final_term = num_data * math.log(2 * math.pi)
+        # n: a Python int, or the device-side counter in CUDA-graph mode (same value, no host constant in the graph)
+        n = gp.num_data if getattr(gp, "_num_data_t", None) is None else gp._num_data_t
+        const = n * math.log(2 * math.pi)
         if self.has_learnable_noise:
-            noise = self.likelihood.second_noise_covar.noise.to(inv_quad_term.dtype).reshape(-1)   # one per output
-            inv_quad_term = inv_quad_term / noise
-            # should only be an `n` term here when the logdet is calculated b/c
-            # \log |\sigma^{-2} Kuu| = \log Kuu - m \log \sigma^{-2}
-            # which is computed in the `logdet_term` in the forwards
-            final_term = num_data * noise.log() + final_term
+            # K is stored as K_uu / sigma^2, so only the n log sigma^2 term and the 1 / sigma^2 on the quadratic form
+            # remain here (one noise value per output)
+            sigma2 = self.likelihood.second_noise_covar.noise.to(quad.dtype).reshape(-1)
+            quad = quad / sigma2
+            const = n * sigma2.log() + const
 
-        res = -0.5 * (inv_quad_term + logdet_term + final_term)
-
+        value = -0.5 * (quad + logdet + const)
         for _, prior, closure, _ in self.named_priors():
-            res = res + prior.log_prob(closure()).sum()
-
-        return res / num_data
+            value = value + prior.log_prob(closure()).sum()
+        return value / n

@@ -17,117 +17,112 @@ from .batched_fixed_noise_online_gp import FixedNoiseOnlineSKIGP
 
 
 class OnlineSKIRegression(torch.nn.Module):
+    """Public surface of the reference class: ``OnlineSKIRegression(stem, init_x, init_y, lr, grid_size, grid_bound,
+    covar_module=None)`` with ``fit / update / predict / evaluate / set_lr / set_train_data / noise`` and the
+    attributes ``gp``, ``mll``, ``stem``, ``gp_optimizer``, ``stem_optimizer``, ``target_dim``."""
+
+    REPLAY_BATCH = 1024        # replay minibatch for BatchNorm statistics; also the chunk size of evaluate()
+
     def __init__(self, stem, init_x, init_y, lr, grid_size, grid_bound, covar_module=None, **kwargs):
         super().__init__()
-        self.stem = stem.to(init_x.device)
         assert init_y.ndim == 2, "targets must have explicit output dimension"
-        if init_y.size(-1) == 1:
-            target_batch_shape = []
-        else:
-            target_batch_shape = torch.Size([init_y.size(-1)])
-        features = self.stem(init_x).detach()
-        noise_term = torch.ones_like(init_y)
-        grid_bound += 1e-1
+        n_out = init_y.size(-1)
+        self.stem = stem.to(init_x.device)
+        half_width = grid_bound + 1e-1                     # the grid reaches a little beyond the stated feature range
+        dims = stem.output_dim
         self.gp = FixedNoiseOnlineSKIGP(
-            features,
-            init_y,
-            noise_term,
+            self.stem(init_x).detach(), init_y, torch.ones_like(init_y),
             covar_module=covar_module,
-            grid_bounds=torch.tensor([[-grid_bound, grid_bound]] * stem.output_dim),
-            grid_size=[grid_size] * stem.output_dim,
+            grid_bounds=torch.tensor([[-half_width, half_width]] * dims),
+            grid_size=[grid_size] * dims,
             learn_additional_noise=True,
         )
         self.mll = BatchedWoodburyMarginalLogLikelihood(self.gp.likelihood, self.gp)
-        self.gp_optimizer = torch.optim.Adam(self.gp.parameters(), lr=lr)
-        self.stem_optimizer = torch.optim.Adam(self.stem.parameters(), lr=lr)
-        self._target_batch_shape = target_batch_shape
-        self.target_dim = init_y.size(-1)
+        self._new_optimizers(lr, lr)
+        self.target_dim = n_out
+        self._target_batch_shape = [] if n_out == 1 else torch.Size([n_out])
         self._raw_inputs = [init_x]
         self._graphs = None          # opt-in CUDA-graph replay of evaluate() / update(): enable_cuda_graphs()
 
+    def _new_optimizers(self, gp_lr, stem_lr):
+        self.gp_optimizer = torch.optim.Adam(self.gp.parameters(), lr=gp_lr)
+        self.stem_optimizer = torch.optim.Adam(self.stem.parameters(), lr=stem_lr)
+
+    # ------------------------------------------------------------------ prediction
     def forward(self, inputs):
-        inputs = inputs.view(-1, self.stem.input_dim)
-        features = self.stem(inputs)
-        return self.gp(features)
+        return self.gp(self.stem(inputs.view(-1, self.stem.input_dim)))
 
     def _reshape_targets(self, targets):
-        targets = targets.view(-1, self.target_dim)
-        if targets.size(-1) == 1:
-            targets = targets.squeeze(-1)
-        else:
-            targets = targets.t()
-        return targets
+        flat = targets.view(-1, self.target_dim)
+        return flat.squeeze(-1) if self.target_dim == 1 else flat.t()
+
+    def _columns(self, t):
+        """[t, q] (or [q]) model output -> [q, target_dim]."""
+        return t.reshape(-1, 1) if self.target_dim == 1 else t.t().reshape(-1, self.target_dim)
 
     def predict(self, inputs):
+        """(mean, variance incl. the learned noise), each [q, target_dim]."""
         self.eval()
-        pred_dist = self(inputs)
-        pred_mean = pred_dist.mean.reshape(-1, self.target_dim) if self.target_dim == 1 \
-            else pred_dist.mean.t().reshape(-1, self.target_dim)
-        pred_var = pred_dist.variance.reshape(-1, self.target_dim) if self.target_dim == 1 \
-            else pred_dist.variance.t().reshape(-1, self.target_dim)
-        pred_var = pred_var + self.gp.likelihood.second_noise.to(pred_var.dtype).reshape(1, -1)
-        return pred_mean, pred_var
+        dist = self(inputs)
+        var = self._columns(dist.variance)
+        return self._columns(dist.mean), var + self.gp.likelihood.second_noise.to(var.dtype).reshape(1, -1)
 
     def _evaluate_stats(self, input_batch, target_batch):
         """[rmse, nll] of one chunk as a device tensor (no host read)."""
-        pred_mean, pred_var = self.predict(input_batch)
-        rmse = (pred_mean - target_batch).pow(2).mean().sqrt()
-        diag_dist = torch.distributions.Normal(pred_mean, pred_var.sqrt(), validate_args=False)
-        nll = -diag_dist.log_prob(target_batch).mean()
-        return torch.stack([rmse, nll])
+        mean, var = self.predict(input_batch)
+        err = mean - target_batch
+        gauss = torch.distributions.Normal(mean, var.sqrt(), validate_args=False)
+        return torch.stack([err.pow(2).mean().sqrt(), -gauss.log_prob(target_batch).mean()])
 
     def evaluate(self, inputs, targets):
+        """(rmse, nll) as Python floats.  Runs with autograd on: the caches built here are the ones the following
+        ``update`` differentiates (``online_ski_regression.py:64-78``)."""
         inputs = inputs.view(-1, self.stem.input_dim)
         targets = targets.view(-1, self.target_dim)
         if self._graph_usable(inputs):
             return self._evaluate_graphed(inputs, targets)
         self._graph_phase(None)
-        # Don't use `torch.no_grad` here, caches will be used for training
         self.eval()
-        chunks = list(zip(inputs.split(1024), targets.split(1024)))
         # one device->host read for the whole call: the per-chunk statistics stay on the device and the interpolation
-        # bounds flags are read back after them (the reference reads rmse and nll with one .item() each, :72-77)
+        # bounds flags are read back after them (the reference reads rmse and nll with one .item() each)
         with settings.defer_interp_bounds_check(inputs.is_cuda):
-            stats = [self._evaluate_stats(input_batch, target_batch) for input_batch, target_batch in chunks]
+            stats = [self._evaluate_stats(xb, yb)
+                     for xb, yb in zip(inputs.split(self.REPLAY_BATCH), targets.split(self.REPLAY_BATCH))]
             rmse, nll = torch.stack(stats).mean(0).tolist()
         ops.flush_bounds_checks()
         return rmse, nll
 
+    # ------------------------------------------------------------------ batch (pre-)training
     def fit(self, inputs, targets, num_epochs, test_dataset=None):
+        """``num_epochs`` joint Adam steps on stem + GP hyper-parameters with cosine-annealed rates; the WISKI caches
+        are rebuilt from the current features after every step (``:80-111``).  Returns one record per epoch."""
         self._graph_phase(None)
-        records = []
-        gp_lr_sched = CosineAnnealingLR(self.gp_optimizer, num_epochs, 1e-4)
-        stem_lr_sched = CosineAnnealingLR(self.stem_optimizer, num_epochs, 1e-4)
+        optimizers = (self.stem_optimizer, self.gp_optimizer)
+        schedules = [CosineAnnealingLR(opt, num_epochs, 1e-4) for opt in optimizers]
+        history = []
         features = self._refresh_features(inputs, targets)
-        for epoch in range(num_epochs):
+        for epoch in range(1, num_epochs + 1):
             self.train()
             self.mll.train()
-            self.stem_optimizer.zero_grad()
-            self.gp_optimizer.zero_grad()
-            train_dist = self.gp(features)
-            loss = -self.mll(train_dist, targets).sum()
+            for opt in optimizers:
+                opt.zero_grad()
+            loss = -self.mll(self.gp(features), targets).sum()
             loss.backward()
-            self.stem_optimizer.step()
-            self.gp_optimizer.step()
-            stem_lr_sched.step()
-            gp_lr_sched.step()
+            for stepper in (*optimizers, *schedules):
+                stepper.step()
             features = self._refresh_features(inputs, targets)
-
-            rmse = nll = float("NaN")
-            if test_dataset is not None:
-                test_x, test_y = test_dataset[:]
-                rmse, nll = self.evaluate(test_x, test_y)
-            records.append({"epoch": epoch + 1, "train_loss": loss.item(),
-                            "test_rmse": rmse, "test_nll": nll,
+            rmse, nll = (float("NaN"), float("NaN")) if test_dataset is None else self.evaluate(*test_dataset[:])
+            history.append({"epoch": epoch, "train_loss": loss.item(), "test_rmse": rmse, "test_nll": nll,
                             "noise": self.gp.likelihood.second_noise_covar.noise.mean().item()})
-
         with detach_interp_coeff(True):
             self._refresh_features(inputs, targets)
-
         self.eval()
-        return records
+        return history
 
+    # ------------------------------------------------------------------ streaming
     def update(self, inputs, targets, update_stem=True, update_gp=True):
+        """One streaming step (``:113-130``): stem step on the Sherman-Morrison partial MLL, hyper-parameter step on
+        the Woodbury MLL, then the new batch is conditioned on in place.  Returns (stem_loss, gp_loss)."""
         inputs = inputs.view(-1, self.stem.input_dim)
         targets = targets.view(-1, self.target_dim)
         if update_gp and self._graph_usable(inputs) and self._graphs.phase == "evaluated":
@@ -136,37 +131,31 @@ class OnlineSKIRegression(torch.nn.Module):
 
         stem_loss = self._update_stem(inputs, targets) if update_stem else 0.
         gp_loss = self._update_gp_tensor(inputs, targets) if update_gp else 0.
-
         with torch.no_grad():
-            features = self.stem(inputs)
-            noise_term = torch.ones_like(targets)
-            self.gp.condition_on_observations(features, targets, noise_term, inplace=True)
+            self.gp.condition_on_observations(self.stem(inputs), targets, torch.ones_like(targets), inplace=True)
             self._raw_inputs = [torch.cat([*self._raw_inputs, inputs])]
             self.stem.train()
             if update_stem and self._stem_has_batchnorm():
                 self._get_features(inputs)
-
         self.eval()
         # the loss is read back only now, with the conditioning kernels already queued behind the hyper-parameter step
         return stem_loss, (gp_loss.item() if torch.is_tensor(gp_loss) else gp_loss)
 
     def _stem_has_batchnorm(self):
-        # `_get_features` only exists to refresh BatchNorm statistics (:133-134); without such layers it is a no-op
+        # `_get_features` only exists to refresh BatchNorm statistics; without such layers it is a no-op
         return any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in self.stem.modules())
 
     def _update_gp_tensor(self, inputs, targets):
+        """Adam step on -MLL (logdet value skipped, gradient kept); returns the loss as a detached device tensor."""
         self.gp_optimizer.zero_grad()
-
         self.gp.train()
         self.mll.train()
         with settings.skip_logdet_forward(True):
-            features = self.stem(inputs)
-            train_dist = self.gp(features.detach())
-            loss = -self.mll(train_dist, targets).sum()
+            dummy = self.gp(self.stem(inputs).detach())
+            loss = -self.mll(dummy, targets).sum()
         loss.backward()
         self.gp_optimizer.step()
-
-        self.gp.zero_grad()
+        self.gp.zero_grad()              # also drops the caches that depended on the old hyper-parameters
         self.gp.eval()
         return loss.detach()
 
@@ -174,54 +163,43 @@ class OnlineSKIRegression(torch.nn.Module):
         return self._update_gp_tensor(inputs, targets).item()
 
     def _update_stem(self, inputs, targets):
+        """Stem step on the one-point Sherman-Morrison MLL increment (``:148-162``); 0 for a stem without parameters."""
         self.stem_optimizer.zero_grad()
-        num_seen = self.gp.num_data
-
-        self.stem.eval()  # we want deterministic features, so BatchNorm should be in eval mode
-        new_features = self.stem(inputs)
-        if new_features.requires_grad is False:
+        seen = self.gp.num_data
+        self.stem.eval()                 # deterministic features: BatchNorm uses its running statistics
+        feats = self.stem(inputs)
+        if feats.requires_grad is False:
             return 0
-
-        targets = targets.transpose(-1, -2).unsqueeze(-1)
-        loss = -sm_partial_mll(self.gp, new_features, targets, num_seen).sum()
+        loss = -sm_partial_mll(self.gp, feats, targets.transpose(-1, -2).unsqueeze(-1), seen).sum()
         loss.backward()
         self.stem_optimizer.step()
-
         return loss.item()
 
     def _get_features(self, inputs):
-        # update batch norm stats
+        """Stem forward on the new points plus a random replay minibatch (refreshes BatchNorm statistics)."""
         inputs = inputs.view(-1, self.stem.input_dim)
-        num_inputs = inputs.size(0)
-        num_seen = self._raw_inputs[0].size(0)
-        batch_size = 1024
-        batch_idxs = torch.randint(0, num_seen, (batch_size,))
-        input_batch = self._raw_inputs[0][batch_idxs]
-        input_batch = torch.cat([inputs, input_batch])
-        features = self.stem(input_batch)
-        return features[:num_inputs]
+        seen = self._raw_inputs[0]
+        replay = seen[torch.randint(0, seen.size(0), (self.REPLAY_BATCH,))]
+        return self.stem(torch.cat([inputs, replay]))[:inputs.size(0)]
 
     def _refresh_features(self, inputs, targets):
-        features = self.stem(inputs)
-        self.set_train_data(features, targets)
-        self.gp.zero_grad()  # dump W-related caches
-        return features
+        feats = self.stem(inputs)
+        self.set_train_data(feats, targets)
+        self.gp.zero_grad()              # dump the caches built on the previous features
+        return feats
 
     def set_train_data(self, inputs, targets):
         self._graph_phase(None)
-        noise = torch.ones_like(targets)
-        self.gp.set_train_data(inputs, targets, noise)
+        self.gp.set_train_data(inputs, targets, torch.ones_like(targets))
 
     def set_lr(self, gp_lr, stem_lr=None, bn_mom=None):
-        stem_lr = gp_lr if stem_lr is None else stem_lr
         if self._graphs is not None:
             self.enable_cuda_graphs(True, warmup_calls=self._graphs.warm0)     # captured graphs hold the old optimiser
-        self.gp_optimizer = torch.optim.Adam(self.gp.parameters(), lr=gp_lr)
-        self.stem_optimizer = torch.optim.Adam(self.stem.parameters(), lr=stem_lr)
+        self._new_optimizers(gp_lr, gp_lr if stem_lr is None else stem_lr)
         if bn_mom is not None:
-            for m in self.stem.modules():
-                if isinstance(m, torch.nn.BatchNorm1d):
-                    m.momentum = bn_mom
+            for mod in self.stem.modules():
+                if isinstance(mod, torch.nn.BatchNorm1d):
+                    mod.momentum = bn_mom
 
     @property
     def noise(self):
