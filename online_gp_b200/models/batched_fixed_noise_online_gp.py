@@ -465,9 +465,17 @@ class FixedNoiseOnlineSKIGP(GP):
                 f"Unsupported batch shapes: The target batch shape ({target_batch_shape}) must have either the "
                 f"same dimension as or one more dimension than the input batch shape ({input_batch_shape})"
             )
-        if ibdim > 0:
-            raise NotImplementedError("batched fantasy inputs (``_expand_batch`` of the root panels, :139-159) are a "
-                                      "'next' row (SURVEY §8f-1)")
+        if ibdim > 1:
+            raise RuntimeError(f"Unsupported batch shapes: fantasy inputs may carry one batch dimension, got {input_batch_shape}")
+        if ibdim == 1:
+            # candidate sets that differ per batch element: predictive-space fantasy (fantasy.py) instead of the
+            # reference's per-element copies of WtW and both root panels (``_expand_batch``, :139-159)
+            from .fantasy import PredictiveSpaceFantasy
+            Y = targets.unsqueeze(-1)                                            # [(nf,) b, q, 1]  (:328)
+            noise = noise_term if noise_term.dim() == Y.dim() else noise_term.unsqueeze(-1)
+            if noise.dim() == 4:
+                noise = noise[0]
+            return PredictiveSpaceFantasy(self, inputs, Y, noise)
         return self.condition_on_observations(inputs, targets.reshape(inputs.shape[-2], -1), noise_term, inplace=False)
 
     # ------------------------------------------------------------------ cached properties (``:334-383``)

@@ -316,3 +316,30 @@ def test_qnipv_active_learning_plumbing():
         ipv1 = float(model2.posterior(mc).variance.mean())
         assert abs(ipv1 - float(look[best])) <= 1e-8 * max(1.0, ipv0)        # look-ahead value == realised value
         assert ipv1 < ipv0
+
+
+def test_get_fantasy_model_with_batched_inputs():
+    """``get_fantasy_model(inputs [b, q, d], targets [b, q], noise)`` (batched_fixed_noise_online_gp.py:287-332) through the
+    predictive-space fantasy: per-element posterior == explicit conditioning (exact root)."""
+    model, X, Y, gen = _model(t=1, learn=True, g=6)
+    b, q = 3, 2
+    Xc = torch.rand(b, q, 2, generator=gen)
+    Yc = torch.randn(b, q, generator=gen)
+    noise = 0.2 * torch.ones(b, q)
+    Xs = torch.rand(5, 2, generator=gen)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model.eval()
+        fm = super(type(model), model).get_fantasy_model(Xc, Yc, noise)
+        out = fm(Xs)
+        assert out.mean.shape == (1, b, 5)
+        for i in range(b):
+            one = model.condition_on_observations(Xc[i], Yc[i].unsqueeze(-1), noise[i].unsqueeze(-1), inplace=False)
+            one.eval()
+            ref = one(Xs)
+            assert torch.allclose(out.mean[0, i], ref.mean.reshape(-1), rtol=1e-7, atol=1e-9)
+            assert torch.allclose(out.variance[0, i], ref.variance.reshape(-1), rtol=1e-6, atol=1e-9)
+        with pytest.raises(RuntimeError, match="Unsupported batch shapes"):
+            model.get_fantasy_model(torch.rand(2, 3, 2, 2), torch.rand(2, 3, 2), torch.ones(2, 3, 2))
+        with pytest.raises(RuntimeError, match="Unsupported batch shapes"):
+            super(type(model), model).get_fantasy_model(Xc, torch.rand(2, 2, b, q), noise)
