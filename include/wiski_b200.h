@@ -115,7 +115,7 @@ int wiski_kron_axis_contract_tc_f32(const float* Z, const float* P, int64_t g, i
  * the pair-level entry points let the autograd layer keep the intermediate panel of the forward pass.
  *   pair p covers grid axes (2p, 2p+1);   pair_apply: Y = (T_2p x T_2p+1) X;
  *   pair_grad: acc_u += contract_{2p}(Z, T_2p+1 P), acc_v += contract_{2p+1}(T_2p Z, P), Zout = T_2p+1 T_2p Z (or NULL).
- * Not re-entrant across streams (coefficients live in __constant__ memory). */
+ * The SIMT form is not re-entrant across streams (coefficients live in __constant__ memory); the tensor-core form is. */
 int wiski_kron_fused_supported(int d, const int64_t* h_g, int64_t c);
 int wiski_kron_fused_pair_apply_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X,
                                     float* Y, int64_t c, void* stream);
@@ -142,6 +142,17 @@ int wiski_kron_fused_pair_grad_dir_f32(const float* cols, const float* dirs, int
                                        int pair, const float* Z, const float* P, float* Zout, int64_t c, double* out3,
                                        void* stream);
 
+/* Directional pass with explicit operand layouts (h_lay: (ld, cw, cstride) for Z, P, Zout as for pair_grad_lay). */
+int wiski_kron_fused_pair_grad_dir_lay_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,
+                                           int pair, const float* Z, const float* P, float* Zout, int64_t c, double* out3,
+                                           const int64_t* h_lay, void* stream);
+/* The pair_apply / pair_grad_dir entry points above run on the tensor pipe by default (csrc/kron_tc.cu: tcgen05.mma
+ * kind::tf32 with 3xTF32 split operands, the panel tile as the TMEM-resident A operand, TMA loads and stores through
+ * 5-D tensor maps) and fall back to the SIMT kernels only for shapes / layouts the tensor maps cannot describe.
+ * wiski_kron_tc_enable(0 / 1) switches the tensor-core form off / on (returns the previous setting; the environment
+ * variable WISKI_KRON_TC=0 sets the initial state) — used by the A/B timings of bench.py and the parity tests. */
+int wiski_kron_tc_enable(int on);
+
 /* ---- k7: panel right-multiply  Out = P @ M,  P,Out [m,r], M [r,r2], Out [m,r2]  (Out must not alias P)
  * (replaces current_root.matmul(inner_root) / current_inv_root^T.matmul(inner_inv_root),
  * updated_root_lazy_tensor.py:97-100,115-117, and Kuu_Lmat @ qmat_solve, batched_fixed_noise_online_gp.py:376). */
@@ -154,6 +165,15 @@ int wiski_panel_lowrank_update_f32(float* P, int64_t m, int64_t r, const float* 
                                    void* stream);
 int wiski_panel_lowrank_update_f64(double* P, int64_t m, int64_t r, const double* U, const double* Vt, int64_t q,
                                    void* stream);
+
+/* Both panels of the rank-q root update in ONE launch: P0 <- P0 + (P0 @ U) @ Vt0, P1 <- P1 + (P1 @ U) @ Vt1 (root L
+ * and inverse root B share U = p = B^T v and differ in Vt = C p^T / C' p^T).  U and both Vt are staged in shared
+ * memory and a warp updates several rows at a time, so the pass stays HBM-bound for q up to 32 (the per-row form above
+ * re-reads the coefficients from L1 for every row).  P1 / Vt1 may be NULL. */
+int wiski_panel_lowrank_update2_f32(float* P0, float* P1, int64_t m, int64_t r, const float* U, const float* Vt0,
+                                    const float* Vt1, int64_t q, void* stream);
+int wiski_panel_lowrank_update2_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
+                                    const double* Vt1, int64_t q, void* stream);
 
 /* ---- k10: Gram  G = A^T @ Bm,  A [m,r], Bm [m,r2], G [r,r2]  (Q - I = L^T (K L), and L^T (K b);
  * batched_fixed_noise_online_gp.py:352-355,360-361).  work = scratch of wiski_gram_work_elems(m,r,r2) elements. */

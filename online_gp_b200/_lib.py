@@ -30,6 +30,7 @@ def _sigs(real, realp):
         "wiski_kron_axis_contract": [_P, _P, c_int64, c_int64, c_int64, _P, _S],
         "wiski_panel_rmul": [_P, c_int64, c_int64, _P, c_int64, _P, _S],
         "wiski_panel_lowrank_update": [_P, c_int64, c_int64, _P, _P, c_int64, _S],
+        "wiski_panel_lowrank_update2": [_P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _S],
         "wiski_gram": [_P, _P, c_int64, c_int64, c_int64, _P, _P, _S],
         "wiski_q_matvec": [_P, _P, c_int64, c_int64, _P, c_int64, _P, _P, _S],
         "wiski_cg_solve": [_P, _P, c_int64, c_int64, _P, c_int64, real, c_int, c_int, _P, POINTER(c_int), realp, _P, _S],
@@ -41,7 +42,8 @@ EXPORTED = ["wiski_last_error", "wiski_abi_version", "wiski_launch_count", "wisk
             "wiski_kron_fused_pair_apply_f32", "wiski_kron_fused_pair_grad_f32", "wiski_kron_fused_pair_grad_dir_f32", "wiski_gram_work_elems", "wiski_qmv_work_elems",
             "wiski_cg_work_elems", "wiski_kron_toeplitz_bwd_work_elems", "wiski_kron_axis_tc_work_elems",
             "wiski_kron_axis_apply_tc_f32", "wiski_kron_axis_contract_tc_f32", "wiski_kron_fused_pair_apply_lay_f32",
-            "wiski_kron_fused_pair_grad_lay_f32", "wiski_gram_chunked_f32", "wiski_panel_rmul_chunked_f32"] + [
+            "wiski_kron_fused_pair_grad_lay_f32", "wiski_gram_chunked_f32", "wiski_panel_rmul_chunked_f32",
+            "wiski_kron_fused_pair_grad_dir_lay_f32", "wiski_kron_tc_enable"] + [
     f"{n}_{sfx}" for n in _sigs(c_float, POINTER(c_float)) for sfx in ("f32", "f64")]
 
 
@@ -74,6 +76,10 @@ def load():
     lib.wiski_kron_fused_pair_grad_f32.argtypes = [_P, c_int, _I64P, c_int64, c_int, _P, _P, _P, c_int64, _P, _P, _S]
     lib.wiski_kron_fused_pair_grad_dir_f32.restype = c_int
     lib.wiski_kron_fused_pair_grad_dir_f32.argtypes = [_P, _P, c_int, _I64P, c_int64, c_int, _P, _P, _P, c_int64, _P, _S]
+    lib.wiski_kron_fused_pair_grad_dir_lay_f32.restype = c_int
+    lib.wiski_kron_fused_pair_grad_dir_lay_f32.argtypes = [_P, _P, c_int, _I64P, c_int64, c_int, _P, _P, _P, c_int64, _P, _I64P, _S]
+    lib.wiski_kron_tc_enable.restype = c_int
+    lib.wiski_kron_tc_enable.argtypes = [c_int]
     lib.wiski_kron_fused_pair_apply_lay_f32.restype = c_int
     lib.wiski_kron_fused_pair_apply_lay_f32.argtypes = [_P, c_int, _I64P, c_int64, c_int, _P, _P, c_int64, _I64P, _S]
     lib.wiski_kron_fused_pair_grad_lay_f32.restype = c_int

@@ -16,7 +16,25 @@
 // layer uses torch's current stream, like the reference's single default stream).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace wiski {
+
+// kron_tc.cu: the same two passes on the tensor pipe (tcgen05 / TMEM / TMA); return 3 for shapes they do not take
+int tc_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X, float* Y,
+                  int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof);
+int tc_pair_grad_dir(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,
+                     const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st, const int64_t* h_lay);
+
+// tensor-core pair kernels on (default) / off (SIMT kernels of this file): env WISKI_KRON_TC=0 or wiski_kron_tc_enable(0)
+static int g_use_tc = -1;
+static bool use_tc() {
+    if (g_use_tc < 0) {
+        const char* e = getenv("WISKI_KRON_TC");
+        g_use_tc = (e != nullptr && e[0] == '0') ? 0 : 1;
+    }
+    return g_use_tc != 0;
+}
 
 constexpr int G = 32;          // grid points per fused axis
 constexpr int H = 16;          // half
@@ -505,6 +523,11 @@ int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, co
         if (!make_geom(g, d, h_g, p, c)) { set_error("kron_fused: unsupported shape"); return 3; }
         // passes remaining after this one: p ; the last pass (p == 0) must write Y
         float* dst = (p % 2 == 0) ? Y : work;
+        if (use_tc()) {
+            const int rc = tc_pair_apply(cols, d, h_g, gmax, p, src, dst, c, st, nullptr, nullptr);
+            if (rc == 0) { src = dst; continue; }
+            if (rc != 3) return rc;
+        }
         if (int rc = set_coefficients(cols + (int64_t)(2 * p) * gmax, cols + (int64_t)(2 * p + 1) * gmax, st)) return rc;
         int64_t grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
         const PanelLay plain = {c, c, 0};
@@ -519,6 +542,10 @@ int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, co
 // One forward pair pass: Y = (T_{2 pair} x T_{2 pair + 1}) X.
 int fused_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X, float* Y,
                      int64_t c, cudaStream_t st, const int64_t* h_lay = nullptr) {
+    if (use_tc()) {
+        const int rc = tc_pair_apply(cols, d, h_g, gmax, pair, X, Y, c, st, h_lay, nullptr);
+        if (rc != 3) return rc;
+    }
     PairGeom g;
     if (!make_geom(g, d, h_g, pair, c)) { set_error("kron_fused: unsupported shape"); return 3; }
     PanelLay lay[2];
@@ -561,7 +588,13 @@ int fused_pair_grad(const float* cols, int d, const int64_t* h_g, int64_t gmax, 
 
 // Directional backward pair pass (see pair_grad_jvp_kernel).  out3: 3 doubles, accumulated.
 int fused_pair_grad_jvp(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int pair,
-                        const float* Z, const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st) {
+                        const float* Z, const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st,
+                        const int64_t* h_lay = nullptr) {
+    if (use_tc()) {
+        const int rc = tc_pair_grad_dir(cols, dirs, d, h_g, gmax, pair, Z, P, Zout, c, out3, st, h_lay);
+        if (rc != 3) return rc;
+    }
+    if (h_lay != nullptr) { set_error("kron_fused: the SIMT directional pass takes plain row-major operands only"); return 3; }
     PairGeom g;
     if (!make_geom(g, d, h_g, pair, c)) { set_error("kron_fused: unsupported shape"); return 3; }
     if (int rc = set_coefficients(cols + (int64_t)(2 * pair) * gmax, cols + (int64_t)(2 * pair + 1) * gmax, st,
@@ -586,6 +619,22 @@ int fused_pair_grad_jvp(const float* cols, const float* dirs, int d, const int64
 }  // namespace wiski
 
 extern "C" {
+int wiski_kron_tc_enable(int on) {
+    const int prev = wiski::use_tc() ? 1 : 0;
+    wiski::g_use_tc = on ? 1 : 0;
+    return prev;
+}
+
+int wiski_kron_fused_pair_grad_dir_lay_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,
+                                           int pair, const float* Z, const float* P, float* Zout, int64_t c, double* out3,
+                                           const int64_t* h_lay, void* stream) {
+    if (d < 2 || d > WISKI_MAX_DIMS || pair < 0 || 2 * pair + 1 >= d || dirs == nullptr || h_lay == nullptr) {
+        wiski::set_error("kron_fused_pair_grad_dir_lay: unsupported shape");
+        return 3;
+    }
+    return wiski::fused_pair_grad_jvp(cols, dirs, d, h_g, gmax, pair, Z, P, Zout, c, out3, wiski::as_stream(stream), h_lay);
+}
+
 int wiski_kron_fused_pair_grad_dir_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,
                                        int pair, const float* Z, const float* P, float* Zout, int64_t c, double* out3,
                                        void* stream) {

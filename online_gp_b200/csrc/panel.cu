@@ -135,6 +135,103 @@ __global__ void lowrank_update_kernel(T* __restrict__ P, int64_t m, int64_t r, c
     }
 }
 
+// ------------------------------------------------------------------ two panels, one launch, coefficients in smem
+// P_k[i,:] += (P_k[i,:] @ U) @ Vt_k  for k = 0, 1 (root L and inverse root B of the rank-q update share U = p and differ
+// in Vt: C p^T / C' p^T; updated_root_lazy_tensor.py:97-117).  U [r][q] and both Vt [q][r] are staged in shared memory
+// ([QP][r] each, t-major: lane j reads word j -> conflict free); a warp owns ROWS rows at a time so that every
+// coefficient read from shared memory feeds ROWS FMAs (q = 8: 2 x 8 FMA per element against 8 B of HBM traffic — the
+// per-row kernel above re-reads U and Vt from L1 for every row and is L1-bound for q > 2).
+// The ROWS x QP partial dots are reduced across the warp by recursive halving (N - 1 shuffles for N values).
+template <typename T, int QP, int ROWS>
+__global__ void __launch_bounds__(256) lowrank_update2_kernel(T* __restrict__ P0, T* __restrict__ P1, int64_t m, int64_t r,
+                                                              const T* __restrict__ U, const T* __restrict__ Vt0,
+                                                              const T* __restrict__ Vt1, int q) {
+    extern __shared__ __align__(16) unsigned char smem_lr[];
+    T* Us = reinterpret_cast<T*>(smem_lr);          // [QP][r]
+    T* Vs = Us + (int64_t)QP * r;                    // [2][QP][r]
+    T* red = Vs + (int64_t)2 * QP * r;               // [8 warps][ROWS * QP]
+    constexpr int N = ROWS * QP;
+    const int npanels = P1 != nullptr ? 2 : 1;
+    for (int64_t e = threadIdx.x; e < (int64_t)QP * r; e += blockDim.x) {
+        const int t = (int)(e / r);
+        const int64_t j = e - (int64_t)t * r;
+        Us[e] = t < q ? U[j * q + t] : T(0);
+        Vs[e] = t < q ? Vt0[(int64_t)t * r + j] : T(0);
+        if (npanels == 2) Vs[(int64_t)QP * r + e] = t < q ? Vt1[(int64_t)t * r + j] : T(0);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    T* myred = red + wib * N;
+    const int64_t groups_per_panel = (m + ROWS - 1) / ROWS;
+    const int64_t ngroups = groups_per_panel * npanels;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t gidx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; gidx < ngroups; gidx += nwarps) {
+        const int k = gidx >= groups_per_panel ? 1 : 0;
+        const int64_t row0 = (gidx - (int64_t)k * groups_per_panel) * ROWS;
+        T* base = (k ? P1 : P0) + row0 * r;
+        const T* Vk = Vs + (int64_t)k * QP * r;
+        const int nvalid = (int)((m - row0) < ROWS ? (m - row0) : ROWS);
+        T dot[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) dot[i] = T(0);
+        for (int64_t j = lane; j < r; j += 32) {
+            T x[ROWS];
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) x[rr] = rr < nvalid ? base[(int64_t)rr * r + j] : T(0);
+#pragma unroll
+            for (int t = 0; t < QP; ++t) {
+                const T u = Us[(int64_t)t * r + j];
+#pragma unroll
+                for (int rr = 0; rr < ROWS; ++rr) dot[rr * QP + t] += x[rr] * u;
+            }
+        }
+        // recursive halving: afterwards every lane holds the warp total of value `idx`
+        int idx = 0;
+        {
+            int n = N;
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+                if (n > 1) {
+                    const int half = n / 2;
+                    const bool upper = (lane & o) != 0;
+#pragma unroll
+                    for (int i = 0; i < N / 2; ++i) {
+                        if (i < half) {
+                            const T keep = upper ? dot[i + half] : dot[i];
+                            const T send = upper ? dot[i] : dot[i + half];
+                            dot[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                        }
+                    }
+                    if (upper) idx += half;
+                    n = half;
+                } else {
+                    dot[0] += __shfl_xor_sync(0xffffffffu, dot[0], o);
+                }
+            }
+        }
+        __syncwarp();
+        myred[idx] = dot[0];             // lanes holding the same idx hold the same total
+        __syncwarp();
+        T dsum[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) dsum[i] = myred[i];
+        for (int64_t j = lane; j < r; j += 32) {
+            T x[ROWS];
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr) x[rr] = rr < nvalid ? base[(int64_t)rr * r + j] : T(0);
+#pragma unroll
+            for (int t = 0; t < QP; ++t) {
+                const T v = Vk[(int64_t)t * r + j];
+#pragma unroll
+                for (int rr = 0; rr < ROWS; ++rr) x[rr] += dsum[rr * QP + t] * v;
+            }
+#pragma unroll
+            for (int rr = 0; rr < ROWS; ++rr)
+                if (rr < nvalid) base[(int64_t)rr * r + j] = x[rr];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ Gram: G[r x r2] = A^T Bm, split over rows
 template <typename T>
 __global__ void __launch_bounds__(256) gram_tile_kernel(const T* __restrict__ A, const T* __restrict__ Bm, int64_t m,
@@ -455,6 +552,41 @@ static int lowrank_update(T* P, int64_t m, int64_t r, const T* U, const T* Vt, i
     return 0;
 }
 
+// P1 / Vt1 may be NULL (single panel).  Falls back to the per-row kernel when U and Vt do not fit in shared memory.
+template <typename T>
+static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const T* Vt0, const T* Vt1, int64_t q, void* stream) {
+    WISKI_CHECK_ARG(m >= 0 && r >= 1 && q >= 1 && q <= 32, "panel_lowrank_update2: need 1 <= q <= 32 (q=%lld)", (long long)q);
+    WISKI_CHECK_ARG((P1 == nullptr) == (Vt1 == nullptr), "panel_lowrank_update2: P1 and Vt1 go together");
+    if (m == 0) return 0;
+    const int qp = q == 1 ? 1 : q <= 2 ? 2 : q <= 4 ? 4 : q <= 8 ? 8 : q <= 16 ? 16 : 32;
+    const size_t smem = ((size_t)3 * qp * r + 8 * 32) * sizeof(T);
+    if (smem > 200 * 1024) {
+        if (int rc = lowrank_update<T>(P0, m, r, U, Vt0, q, stream)) return rc;
+        return P1 != nullptr ? lowrank_update<T>(P1, m, r, U, Vt1, q, stream) : 0;
+    }
+    cudaStream_t st = as_stream(stream);
+#define LR2(QP, ROWS)                                                                                                        \
+    do {                                                                                                                     \
+        auto kfn = lowrank_update2_kernel<T, QP, ROWS>;                                                                      \
+        WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lowrank2(attr)"); \
+        int64_t groups = ceil_div(m, ROWS) * (P1 != nullptr ? 2 : 1);                                                        \
+        int per_sm = smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 4;                                                       \
+        int64_t blocks = ceil_div(groups, 8);                                                                                \
+        if (blocks > (int64_t)kNumSMs * per_sm) blocks = (int64_t)kNumSMs * per_sm;                                          \
+        kfn<<<(unsigned)blocks, 256, smem, st>>>(P0, P1, m, r, U, Vt0, Vt1, (int)q);                                         \
+    } while (0)
+    if (qp == 1) LR2(1, 8);
+    else if (qp == 2) LR2(2, 8);
+    else if (qp == 4) LR2(4, 8);
+    else if (qp == 8) LR2(8, 4);
+    else if (qp == 16) LR2(16, 2);
+    else LR2(32, 1);
+#undef LR2
+    WISKI_CHECK_LAUNCH("panel_lowrank_update2");
+    count_launches(1);
+    return 0;
+}
+
 static inline int64_t gram_splits(int64_t m, int64_t r, int64_t r2) {
     int64_t tiles = ceil_div(r, 64) * ceil_div(r2, 64);
     int64_t ks = ceil_div((int64_t)kNumSMs * 4, tiles);
@@ -615,6 +747,14 @@ int wiski_panel_rmul_f64(const double* P, int64_t m, int64_t r, const double* M,
 int wiski_panel_lowrank_update_f32(float* P, int64_t m, int64_t r, const float* U, const float* Vt, int64_t q,
                                    void* stream) {
     return wiski::lowrank_update<float>(P, m, r, U, Vt, q, stream);
+}
+int wiski_panel_lowrank_update2_f32(float* P0, float* P1, int64_t m, int64_t r, const float* U, const float* Vt0,
+                                    const float* Vt1, int64_t q, void* stream) {
+    return wiski::lowrank_update2<float>(P0, P1, m, r, U, Vt0, Vt1, q, stream);
+}
+int wiski_panel_lowrank_update2_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
+                                    const double* Vt1, int64_t q, void* stream) {
+    return wiski::lowrank_update2<double>(P0, P1, m, r, U, Vt0, Vt1, q, stream);
 }
 int wiski_panel_lowrank_update_f64(double* P, int64_t m, int64_t r, const double* U, const double* Vt, int64_t q,
                                    void* stream) {

@@ -170,9 +170,7 @@ class UpdatedRootLazyTensor(LazyTensor):
         tensor = None
         if self.tensor is not None:
             tensor = self.tensor + vector @ vector.transpose(-1, -2)
-        vs = self._batched(vector)
-        ps = [ops.gram(B, v.contiguous()) for B, v in zip(self._panels(self.inv_root), vs)]
-        root, inv_root = self._apply(ps, inplace=False)
+        root, inv_root = self.collect_vector(vector)
         return UpdatedRootLazyTensor(tensor, initial_is_root=False, root=root, inv_root=inv_root)
 
     def update_sparse(self, idx, vval, inplace=False):
@@ -237,8 +235,16 @@ class UpdatedRootLazyTensor(LazyTensor):
         """(updated_root, updated_inv_root) for a dense ``vector`` — reference signature (:69)."""
         self.root_decomposition()
         self.root_inv_decomposition()
-        ps = [ops.gram(B, v.contiguous()) for B, v in zip(self._panels(self.inv_root), self._batched(vector))]
-        return self._apply(ps, inplace=False)
+        vs = self._batched(vector)
+        q = vs[0].shape[-1]
+        step = 32 if settings.root_update_mode.value() == "sym" else q      # the row-local kernel takes q <= 32
+        root, inv_root = self.root, self.inv_root
+        for s0 in range(0, max(q, 1), step):
+            # B^T v_k with the inverse root as updated by the earlier column blocks (the same sequential rule as
+            # ``update_sparse``; any q, like the reference's single SVD)
+            ps = [ops.gram(B, v[:, s0:s0 + step].contiguous()) for B, v in zip(self._panels(inv_root), vs)]
+            root, inv_root = self._apply(ps, inplace=s0 > 0, root=root, inv_root=inv_root)
+        return root, inv_root
 
     def _apply(self, ps, inplace, root=None, inv_root=None):
         root = self.root if root is None else root
@@ -260,9 +266,12 @@ class UpdatedRootLazyTensor(LazyTensor):
             root, inv_root = root.clone(), inv_root.clone()
             Ls, Bs = self._panels(root), self._panels(inv_root)
         for L, B, p in zip(Ls, Bs, ps):
+            # the row-local kernel takes q <= 32 columns per call; callers chunk wider updates and re-project each
+            # block on the inverse root as updated so far (``update_sparse``, ``collect_vector``)
+            if p.shape[1] > 32:
+                raise ValueError("rank-q panel update: q <= 32 per call (callers chunk the columns and re-project)")
             C, Cp = _sym_factors(p)
-            ops.panel_lowrank_update_(L, p, C @ p.t())
-            ops.panel_lowrank_update_(B, p, Cp @ p.t())
+            ops.panel_lowrank_update2_(L, B, p, C @ p.t(), Cp @ p.t())      # both panels in one launch
         return root, inv_root
 
     # ---- misc

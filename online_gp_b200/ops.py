@@ -349,12 +349,23 @@ def _fused_pair_grad(cols, sizes, pair, Z, P, acc, store, chunk_z=1, zout=None):
     return Zout
 
 
-def _fused_pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store):
+def _fused_pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store, chunk_z=1, zout=None):
+    """One directional backward pair pass (wiski_kron_fused_pair_grad_dir): out3 += [<g_2p, dirs_2p>, <g_2p+1, dirs_2p+1>,
+    <Z', K' P'>].  chunk_z = W > 1: Z is given column-chunked [W, m, c / W] (received from the column -> row
+    all-to-all); P and the returned Zout are plain [m, c]."""
     d, gmax = cols.shape
-    Zout = torch.empty_like(Z) if store else None
+    m, c = P.shape
+    Zout = (torch.empty_like(P) if zout is None else zout) if store else None
+    if Zout is not None and (Zout.shape != P.shape or not Zout.is_contiguous() or Zout.data_ptr() in (Z.data_ptr(), P.data_ptr())):
+        raise ValueError("_fused_pair_grad_dir: bad `zout`")
     h_g = (c_int64 * d)(*sizes)
+    if chunk_z > 1:
+        _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_fused_pair_grad_dir_lay_f32, _ptr(cols), _ptr(dirs), d,
+                 h_g, gmax, pair, _ptr(Z), _ptr(P), _ptr(Zout), c, _ptr(out3), _lay_array(c, (chunk_z, m), None, None),
+                 _stream())
+        return Zout
     _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_fused_pair_grad_dir_f32, _ptr(cols), _ptr(dirs), d, h_g,
-             gmax, pair, _ptr(Z), _ptr(P), _ptr(Zout), Z.shape[1], _ptr(out3), _stream())
+             gmax, pair, _ptr(Z), _ptr(P), _ptr(Zout), c, _ptr(out3), _stream())
     return Zout
 
 
@@ -617,6 +628,20 @@ def panel_lowrank_update_(P, U, Vt):
     q = U.shape[1]
     _call("wiski_panel_lowrank_update", P.dtype, _ptr(P), m, r, _ptr(U.contiguous()), _ptr(Vt.contiguous()), q, _stream())
     return P
+
+
+def panel_lowrank_update2_(P0, P1, U, Vt0, Vt1):
+    """In place, one launch: P0 <- P0 + (P0 @ U) @ Vt0 and P1 <- P1 + (P1 @ U) @ Vt1 (the root / inverse-root pair of the
+    rank-q update; U [r,q] shared, Vt [q,r]).  q > 32 is applied in column blocks of 32 — exact, because
+    I + U Vt is only ever used here with Vt = C U^T blocks that the callers already chunk; see ``_apply``."""
+    _require_cuda(P0, P1, U, Vt0, Vt1)
+    if not (P0.is_contiguous() and P1.is_contiguous()) or P0.shape != P1.shape:
+        raise ValueError("panel_lowrank_update2_: panels must be contiguous and of equal shape")
+    m, r = P0.shape
+    q = U.shape[1]
+    _call("wiski_panel_lowrank_update2", P0.dtype, _ptr(P0), _ptr(P1), m, r, _ptr(U.contiguous()), _ptr(Vt0.contiguous()),
+          _ptr(Vt1.contiguous()), q, _stream())
+    return P0, P1
 
 
 def q_matvec(L, KL, v):

@@ -529,8 +529,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
                 cw = self.Lc.shape[1]
                 t_full = self.comm.allgather(ops.panel_rmul(self.L_loc, p)).reshape(self.plan.m, p.shape[1])
                 self.Lc.addmm_(t_full, CpT[:, self.comm.rank * cw:(self.comm.rank + 1) * cw])
-            ops.panel_lowrank_update_(self.L_loc, p, CpT)
-            ops.panel_lowrank_update_(self.B_loc, p, Cp @ p.t())
+            ops.panel_lowrank_update2_(self.L_loc, self.B_loc, p, CpT, Cp @ p.t())
 
     # ---- pieces with grad (Kuu / sigma^2, K L, Q, K b, c)  — batched_fixed_noise_online_gp.py:334-366
     def _noise(self):

@@ -21,7 +21,8 @@ def install():
     from online_gp_b200 import ops
 
     saved = {k: getattr(ops, k) for k in ("_require_cuda", "_interp_fwd", "_gather", "_scatter_add", "_kron_mm",
-                                          "_kron_bwd_cols", "_rmul", "_gram", "panel_lowrank_update_", "q_matvec",
+                                          "_kron_bwd_cols", "_rmul", "_gram", "panel_lowrank_update_", "panel_lowrank_update2_",
+                                          "q_matvec",
                                           "cg_solve", "kron_axis_apply", "kron_axis_contract")}
     orig_init = ops.GridSpec.__init__
     orig_bwd = ops._InterpFn.backward
@@ -97,6 +98,7 @@ def install():
     ops._rmul = lambda P, M: P @ M
     ops._gram = lambda A, B: A.t() @ B
     ops.panel_lowrank_update_ = lowrank
+    ops.panel_lowrank_update2_ = lambda P0, P1, U, Vt0, Vt1: (lowrank(P0, U, Vt0), lowrank(P1, U, Vt1))
     ops.q_matvec = q_matvec
     ops.cg_solve = cg_solve
     try:
