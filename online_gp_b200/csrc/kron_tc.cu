@@ -25,6 +25,7 @@
 //   warp 2      TMEM allocator
 //   warps 4-11  workers: two groups of 4 warps (one TMEM lane quadrant each); group g owns MMA tiles g and g + 2
 // TMEM: 4 slots (group x tile) of 128 columns: A raw [0,32) | A remainder [32,64) | D [64,128).
+#include <stdlib.h>
 #include "tc_ptx.cuh"
 
 namespace wiski {
@@ -127,6 +128,8 @@ struct Bars {
 // ------------------------------------------------------------------------------------------ Y = (T_u x T_v) X
 struct ApplyParams {
     int cwx, cwy;            // block widths of X and Y (TMA coordinates)
+    float* Ydirect;          // non-NULL: results leave through per-thread global stores (layout ly) instead of TMA stores
+    Lay ly;
     Geom g;
     const float* col_u;      // 32 floats each
     const float* col_v;
@@ -227,7 +230,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
         const int wq = warp - 4, grp = wq >> 2, quad = wq & 3;
         const int rho = quad * 32 + lane, hi = rho >> 4, w = rho & 15;
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const bool store_thread = quad == 0 && lane == 0;      // one per group: issues the group's TMA stores
+        const bool direct = p.Ydirect != nullptr;
+        const bool store_thread = !direct && quad == 0 && lane == 0;      // one per group: issues the group's TMA stores
+        const long long ustride = (long long)G * g.sv * p.ly.ld;
         uint32_t use = 0;
         long long it = 0;
         long long pr[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tl = PROF ? clock64() : 0;
@@ -252,8 +257,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
                 KTC_TICK(1);
             }
             // ybuf doubles as the staging buffer of the previous tile's output stores: they must have been read out
-            if (store_thread) tma_store_wait_read<0>();
-            named_bar_sync(3, NWORK);
+            if (!direct) {
+                if (store_thread) tma_store_wait_read<0>();
+                named_bar_sync(3, NWORK);
+            }
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int j = grp + 2 * jj, slot = grp * 2 + jj;
@@ -296,14 +303,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
                 tc_fence_after();
                 uint32_t d[32];
                 tmem_ld32(tlane + slot * SLOT_COLS + 64, d);
-                float* og = ybuf + j * STAGE_F + hi * CB + w;
+                if (direct) {
+                    const int blkd = col0 / (int)p.ly.cw;
+                    float* yp = p.Ydirect + blkd * p.ly.cstride + (col0 - blkd * (int)p.ly.cw) + w +
+                                ((long long)ob * (G * G) * g.sv + oa + (long long)(8 * j + hi) * g.sv) * p.ly.ld;
 #pragma unroll
-                for (int u = 0; u < 32; ++u) og[u * (8 * CB)] = __uint_as_float(d[u]);
-                fence_proxy_async_smem();
-                named_bar_sync(4 + grp, 128);
-                if (store_thread) {
-                    tma_store_5d(&tmY, ybuf + j * STAGE_F, c0y, oa, 8 * j, 0, c4y);
-                    tma_store_commit();
+                    for (int u = 0; u < 32; ++u) {
+                        *yp = __uint_as_float(d[u]);
+                        yp += ustride;
+                    }
+                } else {
+                    float* og = ybuf + j * STAGE_F + hi * CB + w;
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) og[u * (8 * CB)] = __uint_as_float(d[u]);
+                    fence_proxy_async_smem();
+                    named_bar_sync(4 + grp, 128);
+                    if (store_thread) {
+                        tma_store_5d(&tmY, ybuf + j * STAGE_F, c0y, oa, 8 * j, 0, c4y);
+                        tma_store_commit();
+                    }
                 }
                 KTC_TICK(8);
             }
@@ -332,6 +350,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
 //   C  rows (u,w): [zuv | zd2] = [T_v | T'_v] zu      (zbuf); out3[1] += zd2 . P (P streamed again: L2 hits); Zout = zuv
 struct GradParams {
     int cwz, cwp, cwo;       // block widths of Z, P and Zout (TMA coordinates)
+    float* Odirect;          // non-NULL: Zout leaves through per-thread global stores (layout lo) instead of TMA stores
+    Lay lo;
     Geom g;
     const float* col_u;
     const float* col_v;
@@ -440,7 +460,9 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
         const int wq = warp - 4, grp = wq >> 2, quad = wq & 3;
         const int rho = quad * 32 + lane, hi = rho >> 4, w = rho & 15;
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
-        const bool store_thread = STORE && quad == 0 && lane == 0;
+        const bool direct = p.Odirect != nullptr;
+        const bool store_thread = STORE && !direct && quad == 0 && lane == 0;
+        const long long vstride = (long long)g.sv * p.lo.ld;
         uint32_t use = 0;
         long long it = 0;
         for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
@@ -461,7 +483,7 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
                 mbar_arrive(&B.a_ready[slot]);
                 mbar_arrive(&B.empty[s]);
             }
-            if (STORE) {        // sbuf doubles as the staging buffer of the previous tile's Zout stores
+            if (STORE && !direct) {        // sbuf doubles as the staging buffer of the previous tile's Zout stores
                 if (store_thread) tma_store_wait_read<0>();
                 named_bar_sync(3, NWORK);
             }
@@ -548,15 +570,26 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
 #pragma unroll
                 for (int v = 0; v < 32; ++v) acc_v = fmaf(__uint_as_float(d[v]), pv[v], acc_v);
                 if (STORE) {
-                    tmem_ld32(tlane + slot * SLOT_COLS + 64, d);                // zuv = T_v zu -> sbuf box [8 u][32 v][16 w]
-                    float* og = sbuf + j * STAGE_F + hi * (G * CB) + w;
+                    tmem_ld32(tlane + slot * SLOT_COLS + 64, d);                // zuv = T_v zu
+                    if (direct) {
+                        const int blkd = col0 / (int)p.lo.cw;
+                        float* yp = p.Odirect + blkd * p.lo.cstride + (col0 - blkd * (int)p.lo.cw) + w +
+                                    ((long long)ob * (G * G) * g.sv + oa + (long long)(8 * j + hi) * G * g.sv) * p.lo.ld;
 #pragma unroll
-                    for (int v = 0; v < 32; ++v) og[v * CB] = __uint_as_float(d[v]);
-                    fence_proxy_async_smem();
-                    named_bar_sync(4 + grp, 128);
-                    if (store_thread) {
-                        tma_store_5d(&tmO, sbuf + j * STAGE_F, c0o, oa, 0, 8 * j, c4o);
-                        tma_store_commit();
+                        for (int v = 0; v < 32; ++v) {
+                            *yp = __uint_as_float(d[v]);
+                            yp += vstride;
+                        }
+                    } else {                                                    // -> sbuf box [8 u][32 v][16 w] -> TMA store
+                        float* og = sbuf + j * STAGE_F + hi * (G * CB) + w;
+#pragma unroll
+                        for (int v = 0; v < 32; ++v) og[v * CB] = __uint_as_float(d[v]);
+                        fence_proxy_async_smem();
+                        named_bar_sync(4 + grp, 128);
+                        if (store_thread) {
+                            tma_store_5d(&tmO, sbuf + j * STAGE_F, c0o, oa, 0, 8 * j, c4o);
+                            tma_store_commit();
+                        }
                     }
                 }
             }
@@ -642,6 +675,21 @@ static Lay lay_of(const int64_t* h_lay, int i, int64_t c) {
 constexpr int kApplyStages = 8;
 constexpr int kGradStages = 4;
 
+// How results leave the SM: TMA stores (one bulk tensor store per 16 KB box) when the rows of a tile are close together
+// in memory, per-thread stores when every 64-byte row of the tile lands in a different 2 MB page (pair (0,1) of a
+// 32^4 grid in a plain row-major panel: 1024 rows 1.7 MB apart) — measured on B200 the TMA store engine then falls
+// behind the 256 storing threads.  WISKI_KTC_STORE=tma|stg overrides (A/B timings).
+static bool use_direct_store(const Geom& g, const Lay& l) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("WISKI_KTC_STORE");
+        mode = (e != nullptr && e[0] == 't') ? 1 : (e != nullptr && e[0] == 's') ? 2 : 0;
+    }
+    if (mode == 1) return false;
+    if (mode == 2) return true;
+    return (long long)g.sv * l.ld * 4 >= (1ll << 19);
+}
+
 }  // namespace ktc
 
 // Y = (T_{2 pair} x T_{2 pair + 1}) X on the tensor pipe.  Returns 3 when the shape / layout is not supported.
@@ -657,6 +705,8 @@ int tc_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, in
     ApplyParams p;
     p.cwx = (int)lx.cw;
     p.cwy = (int)ly.cw;
+    p.ly = ly;
+    p.Ydirect = use_direct_store(g, ly) ? Y : nullptr;
     p.g = g;
     p.col_u = cols + (int64_t)(2 * pair) * gmax;
     p.col_v = cols + (int64_t)(2 * pair + 1) * gmax;
@@ -686,6 +736,8 @@ int tc_pair_grad_dir(const float* cols, const float* dirs, int d, const int64_t*
     p.cwz = (int)lz.cw;
     p.cwp = (int)lp.cw;
     p.cwo = (int)lo.cw;
+    p.lo = lo;
+    p.Odirect = (Zout != nullptr && use_direct_store(g, lo)) ? Zout : nullptr;
     p.g = g;
     p.col_u = cols + (int64_t)(2 * pair) * gmax;
     p.col_v = cols + (int64_t)(2 * pair + 1) * gmax;

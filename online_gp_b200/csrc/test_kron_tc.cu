@@ -243,6 +243,20 @@ static void timeit(int64_t c) {
         snprintf(nm, 64, "simt grad_dir store pair %d", pair);
         report(nm, 3 * bytes, [&] { wiski::fused_pair_grad_jvp(dcols, ddirs, d, g, gmax, pair, dZ, dX, dY, c, dout, 0, nullptr); });
     }
+    // page / DRAM locality of the strided pair (0,1): the same pass with the input and / or the output panel stored as
+    // column blocks of 16 columns ([27][m][16]: a tile's 1024 rows are then 64 KB apart instead of 1.7 MB)
+    {
+        int64_t lay[6];
+        const int64_t cwv[2] = {c, 16};
+        for (int li = 0; li < 2; ++li)
+            for (int lo = 0; lo < 2; ++lo) {
+                lay[0] = cwv[li]; lay[1] = cwv[li]; lay[2] = li ? m * 16 : 0;
+                lay[3] = cwv[lo]; lay[4] = cwv[lo]; lay[5] = lo ? m * 16 : 0;
+                char nm[64];
+                snprintf(nm, 64, "tc pair_apply pair 0 in cw=%lld out cw=%lld", (long long)cwv[li], (long long)cwv[lo]);
+                report(nm, 2 * bytes, [&] { wiski::tc_pair_apply(dcols, d, g, gmax, 0, dX, dY, c, 0, lay, nullptr); });
+            }
+    }
     // role / phase cycle breakdown of the apply kernel (PROF instantiation), averaged per CTA and tile
     long long* dprof;
     cudaMalloc(&dprof, 16 * 8);

@@ -224,6 +224,7 @@ class FixedNoiseOnlineSKIGP(GP):
         likelihood=None,
         learn_additional_noise=False,
         num_data=None,
+        per_output_noise=False,
     ):
         super().__init__()
 
@@ -272,10 +273,14 @@ class FixedNoiseOnlineSKIGP(GP):
         if likelihood is None:
             if train_noise_term is None:
                 train_noise_term = torch.ones_like(train_targets)
+            # the learnable multiplicative noise is ONE scalar shared by all outputs, as in the reference (``:127-130``
+            # builds the likelihood without a batch shape, so ``raw_noise`` has shape [1] and a reference state_dict
+            # loads); ``per_output_noise=True`` (an addition) gives every output its own sigma^2 instead
+            noise_t = train_noise_term.transpose(-1, -2)
             self.likelihood = FNMGLikelihood(
-                noise=train_noise_term.transpose(-1, -2),
+                noise=noise_t,
                 learn_additional_noise=learn_additional_noise,
-                batch_shape=train_noise_term.transpose(-1, -2).shape[:-1],
+                batch_shape=noise_t.shape[:-1] if per_output_noise else torch.Size(),
             )
         else:
             self.likelihood = likelihood

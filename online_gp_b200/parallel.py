@@ -242,7 +242,7 @@ class _ShardedKronFn(torch.autograd.Function):
         cols = cols.contiguous()
         ctx.plan, ctx.comm = plan, comm
         ctx.fused = _fused_ok(plan, X)
-        ctx.dirs = None if (dirs is None or not ctx.fused or plan.world > 1) else dirs.detach().to(cols.dtype).contiguous()
+        ctx.dirs = None if (dirs is None or not ctx.fused) else dirs.detach().to(cols.dtype).contiguous()
         W = plan.world
         if ctx.fused:
             # slab [g0/W, 32, 32, 32, c]: pair (2,3) is slab-local; pair (0,1) runs in the column-sharded layout
@@ -275,10 +275,18 @@ class _ShardedKronFn(torch.autograd.Function):
             if xb is not None and gYb.untyped_storage().data_ptr() != xb.untyped_storage().data_ptr():
                 gYb = xb.view(W, plan.m_loc, cw).copy_(gYb)         # (the Gram backward normally writes it there itself)
             Zc = comm.all_to_all(gYb.contiguous()).view(W * plan.m_loc, cw)
-            if ctx.dirs is not None:            # world == 1 only
+            if ctx.dirs is not None:
+                # directional form: 3 numbers per pair pass instead of two 32-entry column gradients; the partial sums
+                # of the ranks (pair (0,1): my column block, pair (2,3): my row slab) meet in one 6-double all-reduce
                 out = torch.zeros(2, 3, dtype=torch.float64, device=X.device)
-                Z01 = ops._fused_pair_grad_dir(cols, ctx.dirs, plan.sizes, 0, Zc, X23c, out[0], store=True)
-                ops._fused_pair_grad_dir(cols, ctx.dirs, slab, 1, Z01, X, out[1], store=False)
+                Z01c = ops._fused_pair_grad_dir(cols, ctx.dirs, plan.sizes, 0, Zc, X23c, out[0], store=True,
+                                                zout=None if xb is None else xb.view(W * plan.m_loc, cw))
+                if W > 1:
+                    Z01b = comm.all_to_all(Z01c.view(W, plan.m_loc, cw))
+                    ops._fused_pair_grad_dir(cols, ctx.dirs, slab, 1, Z01b, X, out[1], store=False, chunk_z=W)
+                    comm.allreduce_(out)
+                else:
+                    ops._fused_pair_grad_dir(cols, ctx.dirs, slab, 1, Z01c, X, out[1], store=False)
                 gcols = ops._surrogate_col_grad(cols, ctx.dirs, out[:, :2].reshape(-1), out[-1, 2])
                 return gcols, None, None, None, None
             Z01c = ops._fused_pair_grad(cols, plan.sizes, 0, Zc, X23c, acc, store=True,
@@ -443,8 +451,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         base = covar_module if covar_module is not None else ScaleKernel(RBFKernel(ard_num_dims=d))
         self.covar_module = GridInterpolationKernel(base, grid_size=sizes, num_dims=d,
                                                     grid_bounds=torch.tensor([[-grid_bound, grid_bound]] * d)).to(init_x.device)
-        self.likelihood = FNMGLikelihood(noise=torch.ones_like(init_y).t(), learn_additional_noise=True,
-                                         batch_shape=torch.Size([1])).to(init_x.device)
+        self.likelihood = FNMGLikelihood(noise=torch.ones_like(init_y).t(), learn_additional_noise=True).to(init_x.device)
         self.plan = ShardPlan(sizes, self.comm.world, self.comm.rank)
         self.dtype = init_y.dtype
         self.gp_optimizer = torch.optim.Adam(self.parameters(), lr=lr)

@@ -163,8 +163,11 @@ class defer_interp_bounds_check(_feature_flag):
 
 
 class kron_directional_grad(_feature_flag):
-    """Use the directional (JVP) form of the fused Kronecker column-gradient pass (one 512-FMA direction apply + dot
-    per grid line instead of a 1024-FMA contraction; ``ops._surrogate_col_grad``).  Numerically equivalent for
-    lengthscale / scale parameters and parity-tested, but measured on B200 it is *not* faster than the full
-    contraction pass (the pass is limited by its strided 64-byte tile traffic, not by FMA count), so it is off."""
-    _state = False
+    """Directional (JVP) form of the fused Kronecker column-gradient pass: the loss depends on grid column i only through
+    <grad_i, d col_i / d lengthscale_i> and <grad_i, col_i> (every scale-type parameter), so the pass applies the
+    direction matrix T'_i and takes dot products instead of forming the 32-entry column gradient
+    (``ops._surrogate_col_grad``).  Exact for stationary product kernels with one lengthscale per dimension and scalar
+    scales (RBF / Matern + ScaleKernel + noise: every shipped config) and parity-tested against the full contraction.
+    On (default) it runs on the tensor pipe (``csrc/kron_tc.cu``); kernels without ``grid_column_dirs`` and
+    ``kron_directional_grad(False)`` use the full column-gradient pass."""
+    _state = True

@@ -95,6 +95,21 @@ def toeplitz_dense(col):
     return col[(ar.unsqueeze(0) - ar.unsqueeze(1)).abs()]
 
 
+def toeplitz_matmul_fft(col, X, axis):
+    """T(col) applied along ``axis`` of X by circulant embedding + FFT — GPyTorch ``ToeplitzLazyTensor._matmul`` ->
+    ``toeplitz_matmul`` / ``sym_toeplitz_matmul`` (embedding of length 2g - 1... implemented, as there,
+    with the circulant [c_0 .. c_{g-1}, c_{g-1} .. c_1] and real FFTs).  This is what the reference runs per grid axis."""
+    g = col.shape[0]
+    n = 2 * g - 1 if g > 1 else 1
+    circ = torch.cat([col, col[1:].flip(0)]) if g > 1 else col
+    fc = torch.fft.rfft(circ, n=n)
+    shape = [1] * X.dim()
+    fx = torch.fft.rfft(X, n=n, dim=axis)
+    shape[axis] = fc.shape[0]
+    out = torch.fft.irfft(fx * fc.reshape(shape), n=n, dim=axis)
+    return out.narrow(axis, 0, g)
+
+
 def kron_dense(cols):
     K = torch.ones(1, 1, dtype=cols[0].dtype)
     for c in cols:

@@ -20,17 +20,51 @@ import math
 import torch
 
 from .interp import interpolate, left_interp
-from .gridkernel import kuu_columns, toeplitz_dense
+from .gridkernel import kuu_columns, toeplitz_dense, toeplitz_matmul_fft
 from .wiski_ref import psd_safe_cholesky
+
+#: how K X is evaluated per grid axis: "dense" (Toeplitz matrix GEMM), "fft" (GPyTorch's ToeplitzLazyTensor product, A.4)
+#: or "auto" (bench.py: whichever is faster on this host for the axis size, decided once by ``pick_kron_mode``)
+KRON_MODE = {"mode": "dense", "per_size": {}}
+
+
+def pick_kron_mode(sizes, ncol, dtype, reps=2):
+    """Time the dense and the FFT form of one axis product on a slice of the workload's shape and remember the faster
+    one per axis size (so that the CPU baseline is the best the reference's algorithm does on this host)."""
+    import time
+    for g in sorted(set(int(s) for s in sizes)):
+        if g in KRON_MODE["per_size"]:
+            continue
+        inner = max(1, min(ncol * 64, (1 << 22) // g))
+        X = torch.randn(g, inner, dtype=dtype)
+        col = torch.exp(-0.01 * torch.arange(g, dtype=dtype) ** 2)
+        best = {}
+        for mode in ("dense", "fft"):
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                if mode == "dense":
+                    torch.tensordot(toeplitz_dense(col), X, dims=([1], [0]))
+                else:
+                    toeplitz_matmul_fft(col, X, 0)
+            best[mode] = time.perf_counter() - t0
+        KRON_MODE["per_size"][g] = min(best, key=best.get)
+    KRON_MODE["mode"] = "auto"
+    return dict(KRON_MODE["per_size"])
 
 
 def kron_mm(cols, X):
-    """K X via one dense Toeplitz GEMM per grid axis (A.4), X (m x c)."""
+    """K X, one product per grid axis (A.4), X (m x c): dense Toeplitz GEMM, or the reference's FFT form."""
     sizes = [c.shape[0] for c in cols]
     ncol = X.shape[-1]
     Y = X.reshape(*sizes, ncol)
     for i, c in enumerate(cols):
-        Y = torch.tensordot(toeplitz_dense(c), Y, dims=([1], [i])).movedim(0, i)
+        mode = KRON_MODE["mode"]
+        if mode == "auto":
+            mode = KRON_MODE["per_size"].get(int(c.shape[0]), "dense")
+        if mode == "fft":
+            Y = toeplitz_matmul_fft(c, Y, i)
+        else:
+            Y = torch.tensordot(toeplitz_dense(c), Y, dims=([1], [i])).movedim(0, i)
     return Y.reshape(-1, ncol)
 
 
@@ -43,7 +77,7 @@ def scatter_wt(idx, val, src, m):
 
 class WiskiMatFree:
     def __init__(self, grid, hyp, X, y, noise_diag, max_cholesky_size=2048, max_root=512, chunk=64,
-                 dtype=torch.float64, update_mode="svd"):
+                 dtype=torch.float64, update_mode="svd", fold="sequential"):
         self.grid, self.hyp, self.dtype = grid, hyp, dtype
         self.sizes = [len(g) for g in grid]
         self.m = 1
@@ -71,9 +105,25 @@ class WiskiMatFree:
             lam, U = lam[keep].flip(0), U[:, keep].flip(1)
             self.L = V1 @ U
             self.B = self.L / lam
-            for s in range(n1, n0, chunk):
-                e = min(s + chunk, n0)
-                self._root_update(idx[s:e], val[s:e] / noise_diag[s:e].clamp_min(1e-7).sqrt().unsqueeze(-1))
+            if fold == "batched" and n0 > n1:
+                # the projected updates telescope (L_k = L_0 G_k, p_k = G_k^-1 B_0^T v_k):  L_n L_n^T = L_0 (I + P P^T) L_0^T
+                # with P = B_0^T [v_{n1} .. v_{n0}] — one r x r factorisation and one panel GEMM per panel instead of
+                # (n0 - n1) / chunk passes.  Same L L^T / B B^T as the sequential rule below (tests compare the two);
+                # used by bench.py's CPU legs so that an initial set of 2e4 points does not take hours on host cores.
+                r = self.L.shape[1]
+                M = torch.eye(r, dtype=torch.float64)
+                for s in range(n1, n0, 4096):
+                    e = min(s + 4096, n0)
+                    Pc = left_interp(idx[s:e], val[s:e] / noise_diag[s:e].clamp_min(1e-7).sqrt().unsqueeze(-1), self.B).double()
+                    M = M + Pc.t() @ Pc
+                F = torch.linalg.cholesky(M)
+                Finv_t = torch.linalg.solve_triangular(F, torch.eye(r, dtype=torch.float64), upper=False).t()
+                self.L = self.L @ F.to(dtype)
+                self.B = self.B @ Finv_t.to(dtype)
+            else:
+                for s in range(n1, n0, chunk):
+                    e = min(s + chunk, n0)
+                    self._root_update(idx[s:e], val[s:e] / noise_diag[s:e].clamp_min(1e-7).sqrt().unsqueeze(-1))
 
     def _interp(self, X):
         idx, val = interpolate(self.grid, X)
