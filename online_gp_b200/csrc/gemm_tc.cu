@@ -127,6 +127,14 @@ struct Batching {
     //   result written to out + (n / o_cw) * o_cstride + row * ld_out + n % o_cw
     int64_t b_cw, b_crows;
     int64_t o_cw, o_cstride;
+    // terms = 3: 3xTF32 split products (fp32-grade result); 1: one kind::tf32 product of the raw operands (the hardware
+    //   truncates them to tf32: a uniform relative bias of ~-2^-11 plus ~2^-12 noise per product — used for gradient
+    //   quantities only, see settings.backward_gemm_tf32_passes)
+    int terms;
+    // n_list > 0: a slice's tiles are the listed (m-tile, n-tile) pairs only (symmetric result: tiles entirely below the
+    //   diagonal are skipped and mirrored by the reduction)
+    int n_list;
+    unsigned char list_m[24], list_n[24];
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -160,7 +168,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tiles_per_slice = (int64_t)n_tiles_n * n_tiles_m;
+    const int64_t tiles_per_slice = bt.n_list > 0 ? (int64_t)bt.n_list : (int64_t)n_tiles_n * n_tiles_m;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -188,7 +196,10 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     auto decode = [&](int64_t w, int64_t& m0, int64_t& n0, int64_t& kb0, int& nkb, int64_t& z) {
         z = w / tiles_per_slice;
         const int64_t t = w - z * tiles_per_slice;
-        if (bt.m_fastest) {
+        if (bt.n_list > 0) {
+            m0 = (int64_t)bt.list_m[t] * 128;
+            n0 = (int64_t)bt.list_n[t] * (int64_t)BN;
+        } else if (bt.m_fastest) {
             m0 = (t % n_tiles_m) * 128;
             n0 = (t / n_tiles_m) * (int64_t)BN;
         } else {
@@ -294,9 +305,13 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                       : make_desc(bB + ks * 1024, BK * 128, 512, 1);
                         const uint64_t dBs = B_KMAJOR ? make_desc(bS + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4)
                                                       : make_desc(bS + ks * 1024, BK * 128, 512, 1);
-                        umma_tf32(tmem_d, dAs, dBb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
-                        umma_tf32(tmem_d, dAb, dBs, idesc, 1u);
-                        umma_tf32(tmem_d, dAb, dBb, idesc, 1u);
+                        if (bt.terms == 1) {
+                            umma_tf32(tmem_d, dAb, dBb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+                        } else {
+                            umma_tf32(tmem_d, dAs, dBb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
+                            umma_tf32(tmem_d, dAb, dBs, idesc, 1u);
+                            umma_tf32(tmem_d, dAb, dBb, idesc, 1u);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);
                     if (kb == nkb - 1) umma_commit(&tmem_full_bar[acc]);
@@ -318,7 +333,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&full_bar[stage], phase);
                 uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
 #pragma unroll 4
-                for (int i = t; i < nvec; i += 128) {
+                for (int i = t; i < (bt.terms == 1 ? 0 : nvec); i += 128) {
                     // vectors [0, A_BYTES/16) belong to A (big at sA, small at sA + A_BYTES), the rest to B
                     const bool isA = i < A_BYTES / 16;
                     uint4* big = reinterpret_cast<uint4*>(isA ? sA : sA + 2 * A_BYTES) + (isA ? i : i - A_BYTES / 16);
@@ -450,14 +465,17 @@ template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, int64_t Mdim, int64_t Ndim, int64_t Kdim,
                   int bn, int ntiles, int64_t k_per_slice, int64_t nslices, int64_t ld_out, int64_t slice_stride,
                   cudaStream_t st, const char* name, const Batching* btp = nullptr) {
-    Batching bt = {k_per_slice, k_per_slice, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    Batching bt = {};
+    bt.a_kstride = bt.b_kstride = k_per_slice;
+    bt.terms = 3;
     if (btp != nullptr) bt = *btp;
+    if (bt.terms != 1) bt.terms = 3;
     size_t smem = (size_t)STAGES * 2 * ((size_t)128 * BK * 4 + (size_t)bn * BK * 4) + 4 * 32 * 36 * 4 +
                   (3 * STAGES + 5) * 8 + 1024;
     auto kfn = tc_gemm3x_kernel<A_KMAJOR, B_KMAJOR, BK, STAGES>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
     const int n_tiles_m = (int)ceil_div(Mdim, 128);
-    const int64_t n_work = (int64_t)n_tiles_m * ntiles * nslices;
+    const int64_t n_work = (bt.n_list > 0 ? (int64_t)bt.n_list : (int64_t)n_tiles_m * ntiles) * nslices;
     const int64_t grid = n_work < kNumSMs ? n_work : kNumSMs;
     kfn<<<(unsigned)grid, 384, smem, st>>>(tmA, tmB, out, Mdim, Ndim, Kdim, bn, ntiles, n_tiles_m, n_work, k_per_slice,
                                            ld_out, slice_stride, bt);
@@ -481,10 +499,26 @@ int64_t tc_gram_work_elems(int64_t m, int64_t r, int64_t r2) {
 }
 
 // nblk > 1: Bm is column-chunked, nblk blocks [m, r2 / nblk] stacked (block j = columns [j r2/nblk, (j+1) r2/nblk)).
+// symmetric: the caller guarantees A^T Bm is symmetric (Q - I = L^T (K L), K symmetric): tiles entirely below the
+// diagonal are not computed; the reduction mirrors them from the upper triangle.
+template <typename T>
+__global__ void reduce_slices_sym_kernel(const T* __restrict__ part, int64_t nparts, int64_t r, int bn, T* __restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= r * r) return;
+    int64_t i = e / r, j = e - i * r;
+    // tile (i / 128, j / bn) was skipped iff its first row is at or beyond its last column + 1
+    const bool skipped = (i / 128) * 128 >= (j / bn + 1) * (int64_t)bn;
+    const int64_t src = skipped ? j * r + i : e;
+    double s = 0.0;
+    for (int64_t p = 0; p < nparts; ++p) s += (double)part[p * r * r + src];
+    out[e] = (T)s;
+}
+
 int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
-                cudaStream_t st, int64_t nblk) {
+                cudaStream_t st, int64_t nblk, bool symmetric) {
     if (!tc_shape_ok(m, r, r2)) return 3;
     if (nblk > 1 && (r2 % nblk != 0 || (r2 / nblk) % 32 != 0 || nblk * m >= (int64_t)1 << 31)) return 3;
+    if (symmetric && (r != r2 || nblk > 1)) symmetric = false;
     CUtensorMap tmA, tmB;
     if (int rc = make_map(&tmA, A, m, r, kGramBK, true)) return rc;
     if (int rc = (nblk > 1 ? make_map(&tmB, Bm, nblk * m, r2 / nblk, kGramBK, true) : make_map(&tmB, Bm, m, r2, kGramBK, true)))
@@ -494,11 +528,27 @@ int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r
     int64_t nslices = ceil_div(m, kGramSliceRows);
     Batching bt = {kGramSliceRows, kGramSliceRows, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (nblk > 1) { bt.b_cw = r2 / nblk; bt.b_crows = m; }
+    if (symmetric) {
+        const int ntm = (int)ceil_div(r, 128);
+        int n_list = 0;
+        for (int mt = 0; mt < ntm && n_list < 24; ++mt)
+            for (int nt = 0; nt < ntiles && n_list < 24; ++nt)
+                if (!((int64_t)mt * 128 >= (int64_t)(nt + 1) * bn)) {
+                    bt.list_m[n_list] = (unsigned char)mt;
+                    bt.list_n[n_list] = (unsigned char)nt;
+                    ++n_list;
+                }
+        if (n_list >= 24 || n_list == ntm * ntiles) symmetric = false;      // nothing to skip (or too many tiles to list)
+        else bt.n_list = n_list;
+    }
     if (int rc = launch<false, false, kGramBK, kGramStages>(tmA, tmB, work, r, r2, m, bn, ntiles, kGramSliceRows, nslices, r2,
                                                      r * r2, st, "tc_gram", &bt))
         return rc;
     int64_t n = r * r2;
-    reduce_slices_kernel<float><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nslices, n, G);
+    if (symmetric)
+        reduce_slices_sym_kernel<float><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nslices, r, bn, G);
+    else
+        reduce_slices_kernel<float><<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(work, nslices, n, G);
     WISKI_CHECK_LAUNCH("tc_gram(reduce)");
     count_launches(1);
     return 0;
@@ -506,7 +556,7 @@ int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r
 
 // nblk > 1: Out is written column-chunked, nblk blocks [m, r2 / nblk] stacked.
 int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st,
-                      int64_t nblk) {
+                      int64_t nblk, int terms) {
     if (!tc_shape_ok(m, r, r2)) return 3;
     if (nblk > 1 && (r2 % nblk != 0 || (r2 / nblk) % 32 != 0)) return 3;
     CUtensorMap tmA, tmB;
@@ -515,6 +565,7 @@ int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int6
     int ntiles;
     int bn = pick_bn(r2, &ntiles);
     Batching bt = {r, r, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    bt.terms = terms == 1 ? 1 : 3;
     int64_t ld_out = r2;
     if (nblk > 1) { bt.o_cw = r2 / nblk; bt.o_cstride = m * (r2 / nblk); ld_out = r2 / nblk; }
     return launch<true, false, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, ld_out, 0, st, "tc_panel_rmul",

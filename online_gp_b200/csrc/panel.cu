@@ -10,9 +10,9 @@ namespace wiski {
 
 // gemm_tc.cu (fp32, tcgen05): return 0 if handled, 3 if the shape is not supported by the tensor-core path.
 int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
-                cudaStream_t st, int64_t nblk = 1);
+                cudaStream_t st, int64_t nblk = 1, bool symmetric = false);
 int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st,
-                      int64_t nblk = 1);
+                      int64_t nblk = 1, int terms = 3);
 int64_t tc_gram_work_elems(int64_t m, int64_t r, int64_t r2);
 
 // ------------------------------------------------------------------ Out[M x N] = P[M x K] @ Mm[K x N]
@@ -774,6 +774,21 @@ int wiski_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_
 int wiski_gram_f64(const double* A, const double* Bm, int64_t m, int64_t r, int64_t r2, double* G, double* work,
                    void* stream) {
     return wiski::gram<double>(A, Bm, m, r, r2, G, work, stream);
+}
+int wiski_gram_sym_f32(const float* A, const float* Bm, int64_t m, int64_t r, float* G, float* work, void* stream) {
+    int rc = wiski::tc_gram_f32(A, Bm, m, r, r, G, work, wiski::as_stream(stream), 1, true);
+    if (rc != 3) return rc;
+    return wiski::gram<float>(A, Bm, m, r, r, G, work, stream);
+}
+int wiski_panel_rmul_ex_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, int64_t nblk, int terms,
+                            float* Out, void* stream) {
+    WISKI_CHECK_ARG(nblk >= 1 && r2 % nblk == 0 && (terms == 1 || terms == 3), "panel_rmul_ex: bad nblk / terms");
+    int rc = wiski::tc_panel_rmul_f32(P, m, r, M, r2, Out, wiski::as_stream(stream), nblk, terms);
+    if (rc != 3) return rc;
+    if (nblk == 1) return wiski::panel_rmul<float>(P, m, r, M, r2, Out, stream);
+    wiski::set_error("panel_rmul_ex: shape m=%lld r=%lld r2=%lld nblk=%lld not supported by the tensor-core path",
+                     (long long)m, (long long)r, (long long)r2, (long long)nblk);
+    return 3;
 }
 /* Column-chunked variants for the row-sharded path (K L and its gradient live as the all-to-all's receive / send
  * buffer: nblk blocks [m, r2 / nblk], block j = columns [j r2/nblk, (j+1) r2/nblk)).  One tensor-core launch when the

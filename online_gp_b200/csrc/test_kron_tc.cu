@@ -279,6 +279,31 @@ static void timeit(int64_t c) {
 
 int main(int argc, char** argv) {
     int bad = 0;
+    if (argc > 1 && !strcmp(argv[1], "once")) {
+        // one launch of each production kernel at the bench shape (for ncu --set full)
+        const int d = 4;
+        const int64_t g[4] = {32, 32, 32, 32}, gmax = 32, m = 1 << 20, c = argc > 2 ? atoll(argv[2]) : 432;
+        std::vector<float> cols(d * gmax), dirs(d * gmax);
+        for (int i = 0; i < d; ++i)
+            for (int k = 0; k < 32; ++k) {
+                cols[i * gmax + k] = expf(-0.004f * (1 + i) * k * k);
+                dirs[i * gmax + k] = cols[i * gmax + k] * 0.01f * k * k;
+            }
+        float *dcols, *ddirs, *dX, *dZ, *dY;
+        double* dout;
+        cudaMalloc(&dcols, cols.size() * 4); cudaMalloc(&ddirs, dirs.size() * 4);
+        cudaMalloc(&dX, (size_t)m * c * 4); cudaMalloc(&dZ, (size_t)m * c * 4); cudaMalloc(&dY, (size_t)m * c * 4);
+        cudaMalloc(&dout, 24);
+        cudaMemcpy(dcols, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(ddirs, dirs.data(), dirs.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemset(dX, 0, (size_t)m * c * 4); cudaMemset(dZ, 0, (size_t)m * c * 4); cudaMemset(dout, 0, 24);
+        wiski::tc_pair_apply(dcols, d, g, gmax, 1, dX, dY, c, 0, nullptr, nullptr);
+        wiski::tc_pair_apply(dcols, d, g, gmax, 0, dX, dY, c, 0, nullptr, nullptr);
+        wiski::tc_pair_grad_dir(dcols, ddirs, d, g, gmax, 0, dZ, dX, dY, c, dout, 0, nullptr);
+        wiski::tc_pair_grad_dir(dcols, ddirs, d, g, gmax, 1, dZ, dX, nullptr, c, dout, 0, nullptr);
+        printf("once: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+        return 0;
+    }
     if (argc > 1 && !strcmp(argv[1], "time")) {
         timeit(argc > 2 ? atoll(argv[2]) : 432);
         return 0;

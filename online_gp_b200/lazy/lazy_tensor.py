@@ -535,7 +535,7 @@ class PanelGramLazyTensor(LazyTensor):
 
     def evaluate(self):
         if self._eval is None:
-            G = ops.gram(self.L, self.KL)
+            G = ops.gram(self.L, self.KL, symmetric=True)       # L^T (K L) with K symmetric
             self._eval = G + self.jitter * torch.eye(G.shape[-1], dtype=G.dtype, device=G.device)
         return self._eval
 

@@ -48,22 +48,29 @@ def _stencils(lazy_kernel):
     return idx, val
 
 
+def _wt_scatter(idx, val, src, m):
+    """W^T src (m x c).  When the interpolation values carry a graph (features of a trainable stem inside ``fit()``, the
+    reference differentiates its dense W^T unless ``detach_interp_coeff`` is on, ``:22-28``) the scatter is the
+    autograd-capable one; otherwise the CUDA scatter kernel."""
+    if torch.is_grad_enabled() and val.requires_grad:
+        return _scatter_dense(idx, val, src, m)
+    return ops.left_t_interp(idx, val, src, m)
+
+
 def _lowrank_initial_roots(idx, vval, m, max_rank):
     """Deterministic initial (root, inv_root) beyond the Cholesky regime — see the module docstring."""
     n0 = idx.shape[0]
     n1 = min(n0, max_rank)
     dtype, device = vval.dtype, vval.device
-    V1 = ops.left_t_interp(idx[:n1], vval[:n1], torch.eye(n1, dtype=dtype, device=device), m)
+    V1 = _wt_scatter(idx[:n1], vval[:n1], torch.eye(n1, dtype=dtype, device=device), m)
     lam, U = torch.linalg.eigh(ops.gram(V1, V1))
     tol = 1e-10 if dtype == torch.float64 else 1e-5
-    keep = lam > tol * lam.max()
+    keep = lam.detach() > tol * lam.detach().max()
     lam, U = lam[keep].flip(0), U[:, keep].flip(1)
     r_eff = lam.numel()
     r = ((r_eff + 15) // 16) * 16                      # zero columns stay zero under every update
-    Upad = torch.zeros(n1, r, dtype=dtype, device=device)
-    Upad[:, :r_eff] = U
-    scale = torch.zeros(r, dtype=dtype, device=device)
-    scale[:r_eff] = 1.0 / lam
+    Upad = torch.nn.functional.pad(U, (0, r - r_eff))
+    scale = torch.nn.functional.pad(1.0 / lam, (0, r - r_eff))
     L = ops.panel_rmul(V1, Upad)
     B = (L * scale).contiguous()
     return L, B, n1
@@ -82,7 +89,7 @@ def _initialize_caches(targets, noise_diagonal, stencils, m, create_w_cache=True
     dinv_y = y / noise_diagonal                         # :42
     cache = {
         "response_cache": (y * dinv_y).sum(-1).reshape(-1, 1, 1),                                        # :45
-        "interpolation_cache": ops.left_t_interp(idx, val, dinv_y.t().contiguous(), m).t().unsqueeze(-1).contiguous(),  # :46
+        "interpolation_cache": _wt_scatter(idx, val, dinv_y.t().contiguous(), m).t().unsqueeze(-1).contiguous(),  # :46
     }
     if create_w_cache:                                  # :49-53
         t, n = y.shape
@@ -90,7 +97,7 @@ def _initialize_caches(targets, noise_diagonal, stencils, m, create_w_cache=True
         if m <= settings.max_cholesky_size.value():
             tens = []
             for o in range(t):
-                Vt = ops.left_t_interp(idx, vvals[o].contiguous(), torch.eye(n, dtype=val.dtype, device=val.device), m)
+                Vt = _wt_scatter(idx, vvals[o].contiguous(), torch.eye(n, dtype=val.dtype, device=val.device), m)
                 tens.append(Vt @ Vt.t())
             cache["WtW"] = UpdatedRootLazyTensor(torch.stack(tens), initial_is_root=False)
         else:

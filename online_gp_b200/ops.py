@@ -509,17 +509,24 @@ def kron_axis_contract(Z, P, g, outer, inner, acc64):
 
 
 # ---------------------------------------------------------------------------------------------- panels
-def _rmul(P, M):
+def _rmul(P, M, terms=3):
+    """terms: tcgen05 passes of the fp32 tensor-core path (3 = 3xTF32 split, fp32-grade; 1 = single tf32 pass,
+    gradient quantities only — settings.backward_gemm_tf32_passes)."""
     _require_cuda(P, M)
     P, M = P.contiguous(), M.contiguous()
     m, r = P.shape
     r2 = M.shape[1]
     out = torch.empty(m, r2, dtype=P.dtype, device=P.device)
+    if terms == 1 and P.dtype == torch.float32:
+        _call_fn("wiski_panel_rmul", _lib.load().wiski_panel_rmul_ex_f32, _ptr(P), m, r, _ptr(M), r2, 1, 1, _ptr(out), _stream())
+        return out
     _call("wiski_panel_rmul", P.dtype, _ptr(P), m, r, _ptr(M), r2, _ptr(out), _stream())
     return out
 
 
-def _gram(A, B):
+def _gram(A, B, symmetric=False):
+    """symmetric: the caller knows A^T B is symmetric (Q - I = L^T (K L)): the fp32 tensor-core path then skips the
+    result tiles below the diagonal and mirrors them."""
     _require_cuda(A, B)
     A, B = A.contiguous(), B.contiguous()
     m, r = A.shape
@@ -527,6 +534,9 @@ def _gram(A, B):
     n = _lib.load().wiski_gram_work_elems(m, r, r2)
     work = torch.empty(max(int(n), 1), dtype=A.dtype, device=A.device)
     G = torch.empty(r, r2, dtype=A.dtype, device=A.device)
+    if symmetric and r == r2 and A.dtype == torch.float32:
+        _call_fn("wiski_gram", _lib.load().wiski_gram_sym_f32, _ptr(A), _ptr(B), m, r, _ptr(G), _ptr(work), _stream())
+        return G
     _call("wiski_gram", A.dtype, _ptr(A), _ptr(B), m, r, r2, _ptr(G), _ptr(work), _stream())
     return G
 
@@ -551,24 +561,28 @@ def gram_blocks(A, Bb):
     return torch.cat([_gram(A, Bb[j]) for j in range(nb)], dim=1)
 
 
-def rmul_blocks(P, M, nb, out=None):
+def rmul_blocks(P, M, nb, out=None, terms=3):
     """[Out_0 | Out_1 | ...] = P M returned as column blocks [nb, m, r2 / nb] (no autograd)."""
     _require_cuda(P, M)
     m, r = P.shape
     r2 = M.shape[1]
     cwb = r2 // nb
     if nb == 1:
-        return _rmul(P, M).unsqueeze(0)
+        return _rmul(P, M, terms).unsqueeze(0)
     if P.dtype == torch.float32 and cwb % 32 == 0:
         P, M = P.contiguous(), M.contiguous()
         Out = torch.empty(nb, m, cwb, dtype=P.dtype, device=P.device) if out is None else out
-        rc = _lib.load().wiski_panel_rmul_chunked_f32(_ptr(P), m, r, _ptr(M), r2, nb, _ptr(Out), _stream())
+        rc = _lib.load().wiski_panel_rmul_ex_f32(_ptr(P), m, r, _ptr(M), r2, nb, int(terms), _ptr(Out), _stream())
         if rc == 0:
             return Out
         if rc != 3:
             _lib.check(rc, "wiski_panel_rmul_chunked")
-    res = torch.stack([_rmul(P, M[:, j * cwb:(j + 1) * cwb].contiguous()) for j in range(nb)])
+    res = torch.stack([_rmul(P, M[:, j * cwb:(j + 1) * cwb].contiguous(), terms) for j in range(nb)])
     return res if out is None else out.copy_(res)
+
+
+def _bwd_terms():
+    return int(settings.backward_gemm_tf32_passes.value())
 
 
 class _RmulFn(torch.autograd.Function):
@@ -582,7 +596,7 @@ class _RmulFn(torch.autograd.Function):
         P, M = ctx.saved_tensors
         gP = gM = None
         if ctx.needs_input_grad[0]:
-            gP = _rmul(gO, M.t().contiguous())
+            gP = _rmul(gO, M.t().contiguous(), _bwd_terms())
         if ctx.needs_input_grad[1]:
             gM = _gram(P, gO)
         return gP, gM
@@ -590,19 +604,19 @@ class _RmulFn(torch.autograd.Function):
 
 class _GramFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, A, B):
+    def forward(ctx, A, B, symmetric=False):
         ctx.save_for_backward(A, B)
-        return _gram(A, B)
+        return _gram(A, B, symmetric)
 
     @staticmethod
     def backward(ctx, gG):
         A, B = ctx.saved_tensors
         gA = gB = None
         if ctx.needs_input_grad[0]:
-            gA = _rmul(B, gG.t().contiguous())
+            gA = _rmul(B, gG.t().contiguous(), _bwd_terms())
         if ctx.needs_input_grad[1]:
-            gB = _rmul(A, gG.contiguous())
-        return gA, gB
+            gB = _rmul(A, gG.contiguous(), _bwd_terms())
+        return gA, gB, None
 
 
 def panel_rmul(P, M):
@@ -612,11 +626,11 @@ def panel_rmul(P, M):
     return _rmul(P.detach(), M.detach())
 
 
-def gram(A, B):
-    """A^T @ B for panels A [m,r], B [m,r2] -> [r,r2]."""
+def gram(A, B, symmetric=False):
+    """A^T @ B for panels A [m,r], B [m,r2] -> [r,r2].  ``symmetric``: the caller knows the result is symmetric."""
     if torch.is_grad_enabled() and (A.requires_grad or B.requires_grad):
-        return _GramFn.apply(A, B)
-    return _gram(A.detach(), B.detach())
+        return _GramFn.apply(A, B, symmetric)
+    return _gram(A.detach(), B.detach(), symmetric)
 
 
 def panel_lowrank_update_(P, U, Vt):

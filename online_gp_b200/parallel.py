@@ -336,7 +336,7 @@ class _ShardedGramBlocksFn(torch.autograd.Function):
         (A,) = ctx.saved_tensors
         xb = ctx.comm.send_buffer(A.shape[0] * gG.shape[1], A) if ctx.nb > 1 else None
         out = None if xb is None else xb.view(ctx.nb, A.shape[0], ctx.cwb)
-        return None, ops.rmul_blocks(A, gG.contiguous(), ctx.nb, out=out), None
+        return None, ops.rmul_blocks(A, gG.contiguous(), ctx.nb, out=out, terms=ops._bwd_terms()), None
 
 
 class _AllReduceGradFn(torch.autograd.Function):
@@ -378,7 +378,7 @@ class _ShardedGramFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gG):
         (A,) = ctx.saved_tensors
-        return None, ops.panel_rmul(A, gG.contiguous()), None
+        return None, ops._rmul(A, gG.contiguous(), ops._bwd_terms()), None
 
 
 class _ShardSliceFn(torch.autograd.Function):

@@ -171,3 +171,12 @@ class kron_directional_grad(_feature_flag):
     On (default) it runs on the tensor pipe (``csrc/kron_tc.cu``); kernels without ``grid_column_dirs`` and
     ``kron_directional_grad(False)`` use the full column-gradient pass."""
     _state = True
+
+
+class backward_gemm_tf32_passes(_value_context):
+    """tcgen05 passes of the fp32 panel GEMMs that produce *gradient* quantities (``Z = L grad_Q`` in the backward of
+    ``Q = I + L^T K L``, ``online_gp/models/online_ski_regression.py:141``): 1 = one kind::tf32 product of the raw fp32
+    operands (the tensor core truncates them: ~1e-3 relative, mostly a uniform scale of the gradient, which Adam
+    normalises away), 3 = the 3xTF32 split every *value* GEMM uses.  fp32 hyper-gradients stay within the 1e-2 bar
+    either way (asserted in tests/model_cases.py); fp64 is unaffected (SIMT kernels)."""
+    _global_value = 1

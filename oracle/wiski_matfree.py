@@ -35,11 +35,12 @@ def pick_kron_mode(sizes, ncol, dtype, reps=2):
     for g in sorted(set(int(s) for s in sizes)):
         if g in KRON_MODE["per_size"]:
             continue
-        inner = max(1, min(ncol * 64, (1 << 22) // g))
+        inner = max(ncol, (1 << 25) // g)                # ~128 MB in fp32: far beyond the caches, like the real panels
         X = torch.randn(g, inner, dtype=dtype)
         col = torch.exp(-0.01 * torch.arange(g, dtype=dtype) ** 2)
         best = {}
         for mode in ("dense", "fft"):
+            (torch.tensordot(toeplitz_dense(col), X, dims=([1], [0])) if mode == "dense" else toeplitz_matmul_fft(col, X, 0))
             t0 = time.perf_counter()
             for _ in range(reps):
                 if mode == "dense":
@@ -185,12 +186,18 @@ class WiskiMatFree:
             cov = cov * self.hyp.noise.to(self.dtype)
         return mean, cov
 
-    def mll(self, pieces=None):
+    def mll(self, pieces=None, skip_logdet_forward=False):
+        """``skip_logdet_forward``: GPyTorch's setting of the same name, which the reference switches on around the
+        streaming hyper-parameter step (online_ski_regression.py:137): the *value* of log|Q| is dropped from the loss,
+        its gradient is kept."""
         cols, KL, Q, Kb, c = self.pieces() if pieces is None else pieces
         Lq = torch.linalg.cholesky(Q)
         inner_qform = c @ torch.cholesky_solve(c.unsqueeze(-1), Lq).squeeze(-1)
         inv_quad = self.response_cache - self.interpolation_cache @ Kb + inner_qform
-        logdet = 2 * Lq.diagonal().log().sum() + self.D_logdet
+        logdet_q = 2 * Lq.diagonal().log().sum()
+        if skip_logdet_forward:
+            logdet_q = logdet_q - logdet_q.detach()
+        logdet = logdet_q + self.D_logdet
         n = self.num_data
         final = n * math.log(2 * math.pi)
         if self.hyp.learn_noise:

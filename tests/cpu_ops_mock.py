@@ -95,8 +95,8 @@ def install():
     ops._scatter_add = scatter_add
     ops._kron_mm = kron_mm
     ops._kron_bwd_cols = kron_bwd_cols
-    ops._rmul = lambda P, M: P @ M
-    ops._gram = lambda A, B: A.t() @ B
+    ops._rmul = lambda P, M, terms=3: P @ M
+    ops._gram = lambda A, B, symmetric=False: A.t() @ B
     ops.panel_lowrank_update_ = lowrank
     ops.panel_lowrank_update2_ = lambda P0, P1, U, Vt0, Vt1: (lowrank(P0, U, Vt0), lowrank(P1, U, Vt1))
     ops.q_matvec = q_matvec

@@ -239,9 +239,13 @@ def test_posterior_mll_grads_vs_matfree_oracle(d, g, n0, mcs, kind, mode, dt):
             vo_ = orc.mll()
             vo_.backward()
             assert np.allclose(val.item(), vo_.item(), rtol=rt), (val.item(), vo_.item())
+            go = np.concatenate([p.grad.numpy().reshape(-1) for p in hyp.params()])
             if dt == torch.float64:
-                go = np.concatenate([p.grad.numpy().reshape(-1) for p in hyp.params()])
                 assert np.allclose(_grads(model)[0], go, rtol=1e-4, atol=1e-7 + 1e-4 * np.abs(go).max())
+            else:
+                # fp32 (the bench dtype): hyper-parameter gradients within the north-star 1e-2 bar, relative to the
+                # largest gradient entry (3xTF32 value GEMMs, single-pass tf32 gradient GEMM, directional passes)
+                assert np.allclose(_grads(model)[0], go, rtol=1e-2, atol=1e-2 * np.abs(go).max()), (_grads(model)[0], go)
             # condition on a few new points (q = 1, 3, 8)
             q = [1, 3, 8][step]
             s0 = n0 + sum([1, 3, 8][:step])
@@ -286,6 +290,65 @@ def test_regression_wrapper_stream_matches_oracle_loop():
             assert abs(float(reg.noise.mean()) - float(hyp.noise)) <= 1e-6
         ls = reg.gp.covar_module.base_kernel.base_kernel.lengthscale.detach().cpu().reshape(-1)
         assert torch.allclose(ls, hyp.lengthscale.detach(), rtol=1e-6)
+
+
+@pytest.mark.parametrize("d,g,n0,steps", [(2, 48, 128, 500), (2, 32, 128, 300)])
+def test_long_fp32_stream_does_not_drift_from_fp64_oracle(d, g, n0, steps):
+    """Hundreds of in-place fp32 root updates + Adam steps (BASELINE config 2 runs 8 182 of them): the streamed
+    (rmse, nll), the learned noise and B^T L = I stay within the fp32 bar of the fp64 oracle run on the same stream.
+    (2, 48): tcgen05 Gram / panel GEMMs (m = 2304, r = 128); (2, 32): the tcgen05 Kronecker pair kernels."""
+    if _dev() == "cpu":
+        pytest.skip("long stream: GPU only")
+    M = _mods()
+    from online_gp_b200 import ops
+    prev = torch.get_default_dtype()
+    gen = torch.Generator().manual_seed(21)
+    X = torch.rand(n0 + steps, d, generator=gen, dtype=torch.float64) * 2 - 1
+    y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen, dtype=torch.float64)).unsqueeze(-1)
+    torch.set_default_dtype(torch.float32)
+    try:
+        with warnings.catch_warnings(), M["S"].max_cholesky_size(0), M["S"].max_root_decomposition_size(128):
+            warnings.simplefilter("ignore")
+            reg = M["OnlineSKIRegression"](M["Identity"](d), X[:n0].float().to(_dev()), y[:n0].float().to(_dev()), lr=5e-3,
+                                           grid_size=g, grid_bound=1.0)
+            reg.set_lr(5e-3)
+            hyp = Hypers(d, learn_noise=True)
+            orc = WiskiMatFree(create_grid([g] * d, [(-1.1, 1.1)] * d), hyp, X[:n0], y[:n0, 0],
+                               torch.ones(n0, dtype=torch.float64), max_cholesky_size=0, max_root=128, update_mode="svd")
+        assert reg.gp._kernel_cache["WtW"].root.shape[-1] >= 112
+        opt = torch.optim.Adam(hyp.params(), lr=5e-3)
+        worst = [0.0, 0.0]
+        with warnings.catch_warnings(), M["S"].max_cholesky_size(2048), M["S"].max_root_decomposition_size(128):
+            warnings.simplefilter("ignore")
+            for t in range(steps):
+                xt, yt = X[n0 + t:n0 + t + 1], y[n0 + t:n0 + t + 1]
+                with M["S"].detach_interp_coeff(True):
+                    rmse, nll = reg.evaluate(xt.float().to(_dev()), yt.float().to(_dev()))
+                reg.update(xt.float().to(_dev()), yt.float().to(_dev()))
+                pieces = orc.pieces()
+                with torch.no_grad():
+                    mo, co = orc.predict(xt, pieces=pieces)
+                    var_o = co.diagonal() + hyp.noise
+                    rmse_o = float((mo - yt[:, 0]).pow(2).mean().sqrt())
+                    nll_o = float(-torch.distributions.Normal(mo, var_o.sqrt()).log_prob(yt[:, 0]).mean())
+                opt.zero_grad()
+                (-orc.mll(pieces=pieces)).backward()
+                opt.step()
+                with torch.no_grad():
+                    orc.condition_on_observations(xt, yt[:, 0], torch.ones(1, dtype=torch.float64))
+                worst[0] = max(worst[0], abs(rmse - rmse_o) / max(1.0, abs(rmse_o)))
+                worst[1] = max(worst[1], abs(nll - nll_o) / max(1.0, abs(nll_o)))
+            assert worst[0] <= 1e-2 and worst[1] <= 1e-2, worst
+            assert abs(float(reg.noise.mean()) - float(hyp.noise)) <= 1e-2 * float(hyp.noise)
+            ls = reg.gp.covar_module.base_kernel.base_kernel.lengthscale.detach().cpu().reshape(-1).double()
+            assert torch.allclose(ls, hyp.lengthscale.detach(), rtol=1e-2)
+            wtw = reg.gp._kernel_cache["WtW"]
+            Lp, Bp = wtw._panels(wtw.root)[0], wtw._panels(wtw.inv_root)[0]
+            live = (torch.linalg.vector_norm(Lp, dim=0) > 0).to(Lp.dtype)
+            btl = float((ops.gram(Bp, Lp) - torch.diag(live)).abs().max())
+            assert btl <= 1e-2, btl
+    finally:
+        torch.set_default_dtype(prev)
 
 
 def test_cg_path_matches_cholesky_path():

@@ -167,14 +167,33 @@ def _install_fused_emulation(ops, parallel, axis):
         Zo = torch.einsum("cd,oadwk->oacwk", Tv, TuZ).reshape(P.shape)
         return Zo if zout is None else zout.copy_(Zo)
 
-    saved = (ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok)
-    ops._fused_pair_apply, ops._fused_pair_grad = pair_apply, pair_grad
+    def pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store, chunk_z=1, zout=None):
+        if chunk_z > 1:
+            Z = unchunk(Z)
+        Zv, u, v = pair_views(sizes, pair, Z)
+        Pv, _, _ = pair_views(sizes, pair, P)
+        Tu, Tv = _toeplitz(cols[2 * pair], u), _toeplitz(cols[2 * pair + 1], v)
+        Du, Dv = _toeplitz(dirs[2 * pair], u), _toeplitz(dirs[2 * pair + 1], v)
+        S = torch.einsum("cd,obdwk->obcwk", Tv, Pv).double()
+        zu = torch.einsum("ab,obdwk->oadwk", Tu, Zv)
+        zd = torch.einsum("ab,obdwk->oadwk", Du, Zv).double()
+        zd2 = torch.einsum("cd,oadwk->oacwk", Dv, zu).double()
+        out3[0] += (zd * S).sum()
+        out3[1] += (zd2 * Pv.double()).sum()
+        out3[2] += (zu.double() * S).sum()
+        if not store:
+            return None
+        Zo = torch.einsum("cd,oadwk->oacwk", Tv, zu).reshape(P.shape)
+        return Zo if zout is None else zout.copy_(Zo)
+
+    saved = (ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok, ops._fused_pair_grad_dir)
+    ops._fused_pair_apply, ops._fused_pair_grad, ops._fused_pair_grad_dir = pair_apply, pair_grad, pair_grad_dir
     parallel._fused_ok = lambda plan, X: plan.d == 4 and all(s == axis for s in plan.sizes) and \
         X.shape[1] % (16 * plan.world) == 0
     return saved
 
 
-def _fused_worker(rank, world, port, ret):
+def _fused_worker(rank, world, port, ret, directional=True):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -190,7 +209,8 @@ def _fused_worker(rank, world, port, ret):
     X = torch.rand(n0 + steps, d, generator=gen) * 2 - 1
     y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen)).unsqueeze(-1)
     out = []
-    with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64), S.eval_cg_tolerance(1e-13):
+    with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64), S.eval_cg_tolerance(1e-13), \
+            S.kron_directional_grad(directional):
         saved = _install_fused_emulation(ops, parallel, g)
         try:
             model = parallel.ShardedOnlineSKIRegression(X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0,
@@ -204,20 +224,22 @@ def _fused_worker(rank, world, port, ret):
                 _, loss = model.update(xt, yt)
                 out.append((rmse, nll, loss, float(model._noise())))
         finally:
-            ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok = saved
+            ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok, ops._fused_pair_grad_dir = saved
     ret[rank] = out
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_fused_sharded_orchestration_matches_unsharded_oracle():
+@pytest.mark.parametrize("directional", [True, False])
+def test_fused_sharded_orchestration_matches_unsharded_oracle(directional):
     """The default multi-GPU path (slab-local pair, exchange, column-sharded pair, column blocks through Gram / rmul /
-    gathers, chunked operands in the backward) with the pair kernels emulated on a 4^4 grid."""
+    gathers, chunked operands in the backward) with the pair kernels emulated on a 4^4 grid; hyper-gradient through
+    the directional passes (default) and through the full column-gradient passes."""
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (os.getpid() % 2000) + 13
-    mp.spawn(_fused_worker, args=(world, port, ret), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + 13 + int(directional)
+    mp.spawn(_fused_worker, args=(world, port, ret, directional), nprocs=world, join=True)
     from oracle.gridkernel import Hypers
     from oracle.interp import create_grid
     from oracle.wiski_matfree import WiskiMatFree
