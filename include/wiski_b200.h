@@ -204,6 +204,9 @@ int wiski_gram_chunked_f32(const float* A, const float* Bb, int64_t m, int64_t r
                            float* work, void* stream);
 int wiski_panel_rmul_chunked_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, int64_t nblk,
                                  float* Outb, void* stream);
+/* wiski_gram_chunked_f32 for a product the caller knows to be symmetric (see wiski_gram_sym_f32). */
+int wiski_gram_chunked_sym_f32(const float* A, const float* Bb, int64_t m, int64_t r, int64_t nblk, float* G, float* work,
+                               void* stream);
 
 /* ---- k11 (CG path): fused Q-MVM  w = v + L^T (KL v),  v,w [r,c]  — one pass over both panels
  * (the matmul closure GPyTorch's linear_cg calls when r > max_cholesky_size, App. A.5).

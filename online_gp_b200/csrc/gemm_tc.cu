@@ -518,7 +518,7 @@ int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r
                 cudaStream_t st, int64_t nblk, bool symmetric) {
     if (!tc_shape_ok(m, r, r2)) return 3;
     if (nblk > 1 && (r2 % nblk != 0 || (r2 / nblk) % 32 != 0 || nblk * m >= (int64_t)1 << 31)) return 3;
-    if (symmetric && (r != r2 || nblk > 1)) symmetric = false;
+    if (symmetric && r != r2) symmetric = false;
     CUtensorMap tmA, tmB;
     if (int rc = make_map(&tmA, A, m, r, kGramBK, true)) return rc;
     if (int rc = (nblk > 1 ? make_map(&tmB, Bm, nblk * m, r2 / nblk, kGramBK, true) : make_map(&tmB, Bm, m, r2, kGramBK, true)))

@@ -803,6 +803,16 @@ int wiski_gram_chunked_f32(const float* A, const float* Bb, int64_t m, int64_t r
                      (long long)m, (long long)r, (long long)r2, (long long)nblk);
     return 3;
 }
+int wiski_gram_chunked_sym_f32(const float* A, const float* Bb, int64_t m, int64_t r, int64_t nblk, float* G, float* work,
+                               void* stream) {
+    WISKI_CHECK_ARG(nblk >= 1 && r % nblk == 0, "gram_chunked_sym: r=%lld not divisible into %lld blocks", (long long)r,
+                    (long long)nblk);
+    int rc = wiski::tc_gram_f32(A, Bb, m, r, r, G, work, wiski::as_stream(stream), nblk, true);
+    if (rc != 3) return rc;
+    wiski::set_error("gram_chunked_sym: shape m=%lld r=%lld nblk=%lld not supported by the tensor-core path", (long long)m,
+                     (long long)r, (long long)nblk);
+    return 3;
+}
 int wiski_panel_rmul_chunked_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, int64_t nblk,
                                  float* Outb, void* stream) {
     WISKI_CHECK_ARG(nblk >= 1 && r2 % nblk == 0, "panel_rmul_chunked: r2=%lld not divisible into %lld blocks",

@@ -243,6 +243,22 @@ static void timeit(int64_t c) {
         snprintf(nm, 64, "simt grad_dir store pair %d", pair);
         report(nm, 3 * bytes, [&] { wiski::fused_pair_grad_jvp(dcols, ddirs, d, g, gmax, pair, dZ, dX, dY, c, dout, 0, nullptr); });
     }
+    // access pattern of a pairing (1,2) of the same 32^4 grid (rows 55 KB / 1.7 MB apart, 32 pages per tile), emulated as
+    // pair 1 of the 5-D grid [32, 1, 32, 32, 32] (n_before = 32, sv = 32)
+    {
+        const int64_t g5[5] = {32, 1, 32, 32, 32};
+        std::vector<float> c5(5 * gmax), d5(5 * gmax);
+        for (int i = 0; i < 5; ++i)
+            for (int k = 0; k < 32; ++k) { c5[i * gmax + k] = expf(-0.004f * (1 + i) * k * k); d5[i * gmax + k] = c5[i * gmax + k] * 0.01f * k * k; }
+        float *dc5, *dd5;
+        cudaMalloc(&dc5, c5.size() * 4); cudaMalloc(&dd5, d5.size() * 4);
+        cudaMemcpy(dc5, c5.data(), c5.size() * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(dd5, d5.data(), d5.size() * 4, cudaMemcpyHostToDevice);
+        report("tc pair_apply axes (1,2) emulated", 2 * bytes, [&] { wiski::tc_pair_apply(dc5, 5, g5, gmax, 1, dX, dY, c, 0, nullptr, nullptr); });
+        report("tc grad_dir store axes (1,2) emul", 3 * bytes, [&] { wiski::tc_pair_grad_dir(dc5, dd5, 5, g5, gmax, 1, dZ, dX, dY, c, dout, 0, nullptr); });
+        report("tc grad_dir nostore axes (1,2) emul", 2 * bytes, [&] { wiski::tc_pair_grad_dir(dc5, dd5, 5, g5, gmax, 1, dZ, dX, nullptr, c, dout, 0, nullptr); });
+        cudaFree(dc5); cudaFree(dd5);
+    }
     // page / DRAM locality of the strided pair (0,1): the same pass with the input and / or the output panel stored as
     // column blocks of 16 columns ([27][m][16]: a tile's 1024 rows are then 64 KB apart instead of 1.7 MB)
     {

@@ -541,19 +541,22 @@ def _gram(A, B, symmetric=False):
     return G
 
 
-def gram_blocks(A, Bb):
+def gram_blocks(A, Bb, symmetric=False):
     """A^T [B_0 | B_1 | ...] for column blocks Bb [nb, m, cwb] -> [r, nb cwb] (no autograd)."""
     _require_cuda(A, Bb)
     nb, m, cwb = Bb.shape
     r, r2 = A.shape[1], nb * cwb
     if nb == 1:
-        return _gram(A, Bb[0])
+        return _gram(A, Bb[0], symmetric)
     if A.dtype == torch.float32 and cwb % 32 == 0:
         A, Bb = A.contiguous(), Bb.contiguous()
         lib = _lib.load()
         work = torch.empty(max(int(lib.wiski_gram_work_elems(m, r, r2)), 1), dtype=A.dtype, device=A.device)
         G = torch.empty(r, r2, dtype=A.dtype, device=A.device)
-        rc = lib.wiski_gram_chunked_f32(_ptr(A), _ptr(Bb), m, r, r2, nb, _ptr(G), _ptr(work), _stream())
+        if symmetric and r == r2:
+            rc = lib.wiski_gram_chunked_sym_f32(_ptr(A), _ptr(Bb), m, r, nb, _ptr(G), _ptr(work), _stream())
+        else:
+            rc = lib.wiski_gram_chunked_f32(_ptr(A), _ptr(Bb), m, r, r2, nb, _ptr(G), _ptr(work), _stream())
         if rc == 0:
             return G
         if rc != 3:

@@ -329,7 +329,8 @@ class _ShardedGramBlocksFn(torch.autograd.Function):
         ctx.save_for_backward(A)
         ctx.comm = comm
         ctx.nb, ctx.cwb = Bb.shape[0], Bb.shape[2]
-        return comm.allreduce_(ops.gram_blocks(A, Bb))
+        return comm.allreduce_(ops.gram_blocks(A, Bb, symmetric=True))      # L^T (K L): symmetric after the sum over ranks
+
 
     @staticmethod
     def backward(ctx, gG):
@@ -555,7 +556,9 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             # autograd; one exchange brings it to row-sharded column blocks, the backward sends the gradient back
             cw = self.Lc.shape[1]
             xb = comm.send_buffer(plan.m * cw, self.Lc)
-            KLc = ops.kron_toeplitz_matmul(_AllReduceGradFn.apply(cols, comm), plan.sizes, self.Lc, dirs=None,
+            # (the surrogate column gradient of the directional backward is linear in the per-rank partial sums, so
+            #  summing it over the ranks in _AllReduceGradFn gives the surrogate of the complete sums)
+            KLc = ops.kron_toeplitz_matmul(_AllReduceGradFn.apply(cols, comm), plan.sizes, self.Lc, dirs=dirs,
                                            out=None if xb is None else xb.view(plan.m, cw))
             KL = _ColsToRowBlocksFn.apply(KLc, plan, comm)
         else:

@@ -78,7 +78,7 @@ def scatter_wt(idx, val, src, m):
 
 class WiskiMatFree:
     def __init__(self, grid, hyp, X, y, noise_diag, max_cholesky_size=2048, max_root=512, chunk=64,
-                 dtype=torch.float64, update_mode="svd", fold="sequential"):
+                 dtype=torch.float64, update_mode="svd", fold="sequential", root_tol=None):
         self.grid, self.hyp, self.dtype = grid, hyp, dtype
         self.sizes = [len(g) for g in grid]
         self.m = 1
@@ -101,7 +101,7 @@ class WiskiMatFree:
             n1 = min(n0, max_root)
             V1 = scatter_wt(idx[:n1], val[:n1] / noise_diag[:n1].sqrt().unsqueeze(-1), torch.eye(n1, dtype=dtype), self.m)
             lam, U = torch.linalg.eigh(V1.t() @ V1)
-            tol = 1e-10 if dtype == torch.float64 else 1e-5
+            tol = root_tol if root_tol is not None else (1e-10 if dtype == torch.float64 else 1e-5)
             keep = lam > tol * lam.max()
             lam, U = lam[keep].flip(0), U[:, keep].flip(1)
             self.L = V1 @ U

@@ -15,7 +15,11 @@ TOLX = 1.0
 
 
 def _close(a, b, rtol, atol=0.0):
-    return torch.allclose(a, b, rtol=min(rtol * TOLX, 1e-4), atol=min(atol * TOLX, 1e-6) if atol else 0.0)
+    ok = torch.allclose(a, b, rtol=min(rtol * TOLX, 1e-4), atol=min(atol * TOLX, 1e-6) if atol else 0.0)
+    if not ok:          # shown by pytest on failure
+        print("mismatch: max abs diff %.3e, max |b| %.3e, dtypes %s %s" % (float((a - b).abs().max()), float(b.abs().max()),
+                                                                         a.dtype, b.dtype))
+    return ok
 
 
 def _rand(*size, generator=None):

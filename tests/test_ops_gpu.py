@@ -155,13 +155,14 @@ def test_panel_rmul_and_gram(dt, m, r, r2):
     Bp = torch.randn(m, r2, generator=gen, dtype=dt)
     out = ops.panel_rmul(P.to(DEV), M.to(DEV))
     ref = P.double() @ M.double()
-    # fp32: error relative to the scale of the accumulated terms (sqrt(K) for unit-variance data): 3xTF32 / SIMT fp32
-    # both stay below 2e-6 of it; fp64 to rounding
-    tol = dict(rtol=1e-10, atol=1e-9) if dt == torch.float64 else dict(rtol=0.0, atol=4e-6 * r ** 0.5 * 4)
+    # fp32: error relative to the scale of the accumulated terms (sqrt(K) for unit-variance data).  The operands are exact
+    # to ~2^-22 (3xTF32); what remains is the tensor core's fp32 accumulation over a K slice (2048 rows for the Gram),
+    # measured at ~2e-5 of that scale (csrc/test_gemm_tc.cu); fp64 to rounding
+    tol = dict(rtol=1e-10, atol=1e-9) if dt == torch.float64 else dict(rtol=0.0, atol=2e-5 * r ** 0.5)
     assert torch.allclose(out.cpu().double(), ref, **tol)
     G = ops.gram(P.to(DEV), Bp.to(DEV))
     refg = P.double().t() @ Bp.double()
-    tolg = dict(rtol=1e-10, atol=1e-8) if dt == torch.float64 else dict(rtol=0.0, atol=4e-6 * m ** 0.5 * 4)
+    tolg = dict(rtol=1e-10, atol=1e-8) if dt == torch.float64 else dict(rtol=0.0, atol=5e-5 * m ** 0.5)
     assert torch.allclose(G.cpu().double(), refg, **tolg)
 
 
@@ -251,19 +252,20 @@ def test_gram_symmetric_and_single_pass_rmul(m, r):
     G = ops._gram(L.to(DEV), KL.to(DEV), symmetric=True)
     G0 = ops._gram(L.to(DEV), KL.to(DEV), symmetric=False)
     scale = float(ref.abs().max())
-    assert torch.allclose(G.cpu().double(), ref, rtol=0.0, atol=2e-5 * scale)
-    assert torch.allclose(G.cpu(), G.cpu().t(), rtol=0.0, atol=2e-5 * scale)
-    assert torch.allclose(G.cpu(), G0.cpu(), rtol=0.0, atol=2e-5 * scale)
+    assert torch.allclose(G.cpu().double(), ref, rtol=0.0, atol=1e-4 * scale), float((G.cpu().double() - ref).abs().max()) / scale
+    assert torch.allclose(G.cpu(), G.cpu().t(), rtol=0.0, atol=1e-4 * scale)
+    assert torch.allclose(G.cpu(), G0.cpu(), rtol=0.0, atol=1e-4 * scale)
     M = torch.randn(r, r, generator=gen)
     refz = L.double() @ M.double()
     Z3 = ops._rmul(L.to(DEV), M.to(DEV), terms=3).cpu().double()
     Z1 = ops._rmul(L.to(DEV), M.to(DEV), terms=1).cpu().double()
     zs = float(refz.abs().max())
-    assert float((Z3 - refz).abs().max()) <= 5e-6 * zs
-    assert 1e-5 * zs <= float((Z1 - refz).abs().max()) <= 4e-3 * zs       # one tf32 pass: coarser, and really taken
+    assert float((Z3 - refz).abs().max()) <= 2e-5 * zs, float((Z3 - refz).abs().max()) / zs
+    e1 = float((Z1 - refz).abs().max())
+    assert 3e-5 * zs <= e1 <= 4e-3 * zs, e1 / zs                          # one tf32 pass: coarser, and really taken
     # the error of the single pass is dominated by a uniform scale (operands truncated toward zero)
     alpha = float((Z1 * refz).sum() / (refz * refz).sum())
-    assert 0.998 < alpha < 1.0
+    assert 0.998 < alpha < 1.0, alpha
 
 
 def test_tensor_core_pair_kernels_match_simt():
