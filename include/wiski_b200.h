@@ -151,7 +151,20 @@ int wiski_kron_fused_pair_grad_dir_lay_f32(const float* cols, const float* dirs,
  * 5-D tensor maps) and fall back to the SIMT kernels only for shapes / layouts the tensor maps cannot describe.
  * wiski_kron_tc_enable(0 / 1) switches the tensor-core form off / on (returns the previous setting; the environment
  * variable WISKI_KRON_TC=0 sets the initial state) — used by the A/B timings of bench.py and the parity tests. */
-int wiski_kron_tc_enable(int on);
+int wiski_kron_tc_enable(int on);      /* on < 0: query only */
+
+/* The two pair passes for ANY two 32-point grid axes axis_u < axis_v (the remaining axes are batch indices; at most two
+ * of the three index groups before / between / after the pair may be non-trivial — always true for d <= 4).
+ * For a 32^4 grid the host layer pairs the axes as (1,2) + (0,3) instead of (0,1) + (2,3): a tile of the pair (0,1) is
+ * 1024 rows 1024 rows apart (one 64-byte piece per 2 MB page), which the memory system serves at half the rate of the
+ * 32-consecutive-row / 32-rows-apart tiles of (0,3) / (1,2) (profiles/r02_pair_kernels.md).  Adjacent even pairs fall back
+ * to the SIMT kernels when the tensor-core form is off; other axes need it (status 3 otherwise).
+ * h_lay may be NULL (plain row-major operands); out3 as in wiski_kron_fused_pair_grad_dir_f32 (axis_u, axis_v, scale). */
+int wiski_kron_pair_apply_axes_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int axis_u, int axis_v,
+                                   const float* X, float* Y, int64_t c, const int64_t* h_lay, void* stream);
+int wiski_kron_pair_grad_dir_axes_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,
+                                      int axis_u, int axis_v, const float* Z, const float* P, float* Zout, int64_t c,
+                                      double* out3, const int64_t* h_lay, void* stream);
 
 /* ---- k7: panel right-multiply  Out = P @ M,  P,Out [m,r], M [r,r2], Out [m,r2]  (Out must not alias P)
  * (replaces current_root.matmul(inner_root) / current_inv_root^T.matmul(inner_inv_root),

@@ -25,6 +25,11 @@ int tc_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, in
                   int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof);
 int tc_pair_grad_dir(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,
                      const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st, const int64_t* h_lay);
+int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gmax, int au, int av, const float* X, float* Y,
+                       int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof);
+int tc_pair_grad_dir_axes(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int au, int av,
+                          const float* Z, const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st,
+                          const int64_t* h_lay);
 
 // tensor-core pair kernels on (default) / off (SIMT kernels of this file): env WISKI_KRON_TC=0 or wiski_kron_tc_enable(0)
 static int g_use_tc = -1;
@@ -515,6 +520,13 @@ int fused_kron_mm(const float* cols, int d, const int64_t* h_g, int64_t gmax, co
                   float* work, cudaStream_t st) {
     const int npairs = d / 2;
     const float* src = X;
+    if (d == 4 && use_tc()) {
+        // pairing (1,2) + (0,3): every tile then touches rows that are close in memory (32 consecutive rows per outer
+        // index, or rows 32 apart), instead of the 1024 rows 1024 apart of the pair (0,1) — see DESIGN.md
+        int rc = tc_pair_apply_axes(cols, d, h_g, gmax, 1, 2, X, work, c, st, nullptr, nullptr);
+        if (rc == 0) rc = tc_pair_apply_axes(cols, d, h_g, gmax, 0, 3, work, Y, c, st, nullptr, nullptr);
+        if (rc != 3) return rc;
+    }
     size_t smem = 2 * TILE_FLOATS * sizeof(float);
     auto kfn = pair_apply_kernel<256, false>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_fused(attr)");
@@ -621,8 +633,44 @@ int fused_pair_grad_jvp(const float* cols, const float* dirs, int d, const int64
 extern "C" {
 int wiski_kron_tc_enable(int on) {
     const int prev = wiski::use_tc() ? 1 : 0;
-    wiski::g_use_tc = on ? 1 : 0;
+    if (on >= 0) wiski::g_use_tc = on ? 1 : 0;          // on < 0: query only
     return prev;
+}
+
+int wiski_kron_pair_apply_axes_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int axis_u, int axis_v,
+                                   const float* X, float* Y, int64_t c, const int64_t* h_lay, void* stream) {
+    if (d < 2 || d > WISKI_MAX_DIMS || axis_u < 0 || axis_v <= axis_u || axis_v >= d || X == Y) {
+        wiski::set_error("kron_pair_apply_axes: bad axes / operands");
+        return 1;
+    }
+    if (wiski::use_tc()) {
+        const int rc = wiski::tc_pair_apply_axes(cols, d, h_g, gmax, axis_u, axis_v, X, Y, c, wiski::as_stream(stream), h_lay,
+                                                 nullptr);
+        if (rc != 3) return rc;
+    }
+    if (axis_v == axis_u + 1 && axis_u % 2 == 0)          // the SIMT kernels know the pairs (2p, 2p + 1) only
+        return wiski::fused_pair_apply(cols, d, h_g, gmax, axis_u / 2, X, Y, c, wiski::as_stream(stream), h_lay);
+    wiski::set_error("kron_pair_apply_axes: axes (%d, %d) need the tensor-core path", axis_u, axis_v);
+    return 3;
+}
+
+int wiski_kron_pair_grad_dir_axes_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,
+                                      int axis_u, int axis_v, const float* Z, const float* P, float* Zout, int64_t c,
+                                      double* out3, const int64_t* h_lay, void* stream) {
+    if (d < 2 || d > WISKI_MAX_DIMS || axis_u < 0 || axis_v <= axis_u || axis_v >= d || dirs == nullptr) {
+        wiski::set_error("kron_pair_grad_dir_axes: bad axes / operands");
+        return 1;
+    }
+    if (wiski::use_tc()) {
+        const int rc = wiski::tc_pair_grad_dir_axes(cols, dirs, d, h_g, gmax, axis_u, axis_v, Z, P, Zout, c, out3,
+                                                    wiski::as_stream(stream), h_lay);
+        if (rc != 3) return rc;
+    }
+    if (axis_v == axis_u + 1 && axis_u % 2 == 0)
+        return wiski::fused_pair_grad_jvp(cols, dirs, d, h_g, gmax, axis_u / 2, Z, P, Zout, c, out3, wiski::as_stream(stream),
+                                          h_lay);
+    wiski::set_error("kron_pair_grad_dir_axes: axes (%d, %d) need the tensor-core path", axis_u, axis_v);
+    return 3;
 }
 
 int wiski_kron_fused_pair_grad_dir_lay_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,

@@ -42,11 +42,18 @@ constexpr int NTHREADS = 128 + NWORK;
 constexpr int SLOT_COLS = 128;
 constexpr int TIMG_B = 4096;              // one 32 x 32 fp32 Toeplitz image (K-major, SWIZZLE_128B)
 
+// Geometry of one axis pair (a, b), a < b, both of 32 points, on a grid [.., g_a, .., g_b, ..]:
+//   row(u, v, f0, f1) = u * su + v * sv + f0 * sf0 + f1 * sf1      (row strides; sv < su)
+// f0, f1 = the (at most two) non-trivial free index groups among {axes after b, axes between a and b, axes before a},
+// f0 the faster one in memory.  The 5-D tensor map of an operand lists (column, then the row groups in memory order);
+// pos_* are the positions of u, v, f0, f1 in it; the column-block index of a chunked operand folds into dimension
+// pos_blk (the slowest real one, extent size_blk).  Tile id -> (column chunk, f0, f1), chunk fastest.
 struct Geom {
-    int sv;              // row stride of axis v (product of the grid sizes after the pair)
-    int n_before;        // product of the grid sizes before the pair
+    int nf0, nf1;        // extents of the free groups
     int n_chunks;        // c / CB
-    long long n_tiles;   // n_before * sv * n_chunks
+    long long n_tiles;   // nf0 * nf1 * n_chunks
+    int pos_u, pos_v, pos_f0, pos_f1, pos_blk, size_blk;
+    long long su, sv, sf0, sf1;
 };
 // where element (row, col) of a panel lives: ptr + (col / cw) * cstride + row * ld + col % cw
 struct Lay {
@@ -107,11 +114,37 @@ __device__ __forceinline__ void issue_mma_tile(uint32_t tslot, const BDesc& b, u
     }
 }
 
-__device__ __forceinline__ void decode_tile(const Geom& g, long long tile, int& cc, int& oa, int& ob) {
+__device__ __forceinline__ void decode_tile(const Geom& g, long long tile, int& cc, int& f0, int& f1) {
     cc = (int)(tile % g.n_chunks);
     const long long o = tile / g.n_chunks;
-    oa = (int)(o % g.sv);
-    ob = (int)(o / g.sv);
+    f0 = (int)(o % g.nf0);
+    f1 = (int)(o / g.nf0);
+}
+
+// TMA coordinates of the box of tile (f0, f1) that starts at (u0, v0) and column c0 of column block blk
+struct Coords {
+    int c[5];
+};
+__device__ __forceinline__ Coords tile_coords(const Geom& g, int c0, int blk, int f0, int f1, int u0, int v0) {
+    Coords r;
+    r.c[0] = c0;
+#pragma unroll
+    for (int i = 1; i < 5; ++i) {
+        int x = 0;
+        if (i == g.pos_u) x = u0;
+        if (i == g.pos_v) x = v0;
+        if (i == g.pos_f0) x = f0;
+        if (i == g.pos_f1) x = f1;
+        if (i == g.pos_blk) x += blk * g.size_blk;
+        r.c[i] = x;
+    }
+    return r;
+}
+__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* tm, uint64_t* bar, const Coords& k) {
+    tma_load_5d(dst, tm, bar, k.c[0], k.c[1], k.c[2], k.c[3], k.c[4]);
+}
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* tm, const void* src, const Coords& k) {
+    tma_store_5d(tm, src, k.c[0], k.c[1], k.c[2], k.c[3], k.c[4]);
 }
 
 // XOR-swizzled [u][v][w] buffer: two consecutive u (two lanes groups of a warp in the (u,w)-row steps) hit different
@@ -180,17 +213,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
             long long seq = 0;
             long long pr[2] = {0, 0}, tl = PROF ? clock64() : 0;
             for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-                int cc, oa, ob;
-                decode_tile(g, tile, cc, oa, ob);
+                int cc, f0, f1;
+                decode_tile(g, tile, cc, f0, f1);
                 const int col0 = cc * CB, blk = col0 / p.cwx;
-                const int c0 = col0 - blk * p.cwx, c4 = ob + blk * g.n_before;
+                const int c0 = col0 - blk * p.cwx;
                 for (int j = 0; j < 4; ++j, ++seq) {
                     const int s = (int)(seq % NST);
                     KTC_TICK(1);
                     mbar_wait(&B.empty[s], (uint32_t)(((seq / NST) & 1) ^ 1));
                     KTC_TICK(0);
                     mbar_arrive_expect_tx(&B.full[s], STAGE_B);
-                    tma_load_5d(ring + s * STAGE_F, &tmX, &B.full[s], c0, oa, 0, 8 * j, c4);
+                    tma_load_box(ring + s * STAGE_F, &tmX, &B.full[s], tile_coords(g, c0, blk, f0, f1, 8 * j, 0));
                 }
             }
             if (PROF) atomicAdd(reinterpret_cast<unsigned long long*>(p.prof + 12), (unsigned long long)pr[0]);
@@ -232,13 +265,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const bool direct = p.Ydirect != nullptr;
         const bool store_thread = !direct && quad == 0 && lane == 0;      // one per group: issues the group's TMA stores
-        const long long ustride = (long long)G * g.sv * p.ly.ld;
+        const long long ustride = g.su * p.ly.ld;
         uint32_t use = 0;
         long long it = 0;
         long long pr[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tl = PROF ? clock64() : 0;
         for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
-            int cc, oa, ob;
-            decode_tile(g, tile, cc, oa, ob);
+            int cc, f0, f1;
+            decode_tile(g, tile, cc, f0, f1);
             // ---- axis v: rows (u, w), K = v'
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
@@ -294,7 +327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
             KTC_TICK(6);
             // results -> ybuf as four [32 u][8 v][16 w] boxes (conflict free) -> one TMA store per MMA tile
             const int col0 = cc * CB, blk = col0 / p.cwy;
-            const int c0y = col0 - blk * p.cwy, c4y = ob + blk * g.n_before;
+            const int c0y = col0 - blk * p.cwy;
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int j = grp + 2 * jj, slot = grp * 2 + jj;
@@ -306,7 +339,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
                 if (direct) {
                     const int blkd = col0 / (int)p.ly.cw;
                     float* yp = p.Ydirect + blkd * p.ly.cstride + (col0 - blkd * (int)p.ly.cw) + w +
-                                ((long long)ob * (G * G) * g.sv + oa + (long long)(8 * j + hi) * g.sv) * p.ly.ld;
+                                (f0 * g.sf0 + f1 * g.sf1 + (long long)(8 * j + hi) * g.sv) * p.ly.ld;
 #pragma unroll
                     for (int u = 0; u < 32; ++u) {
                         *yp = __uint_as_float(d[u]);
@@ -319,7 +352,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
                     fence_proxy_async_smem();
                     named_bar_sync(4 + grp, 128);
                     if (store_thread) {
-                        tma_store_5d(&tmY, ybuf + j * STAGE_F, c0y, oa, 8 * j, 0, c4y);
+                        tma_store_box(&tmY, ybuf + j * STAGE_F, tile_coords(g, c0y, blk, f0, f1, 0, 8 * j));
                         tma_store_commit();
                     }
                 }
@@ -410,21 +443,20 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
         if (lane == 0) {
             long long seq = 0;
             for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-                int cc, oa, ob;
-                decode_tile(g, tile, cc, oa, ob);
+                int cc, f0, f1;
+                decode_tile(g, tile, cc, f0, f1);
                 const int col0 = cc * CB;
                 const int blkp = col0 / p.cwp, blkz = col0 / p.cwz;
-                const int p0 = col0 - blkp * p.cwp, p4 = ob + blkp * g.n_before;
-                const int z0 = col0 - blkz * p.cwz, z4 = ob + blkz * g.n_before;
+                const int p0 = col0 - blkp * p.cwp, z0 = col0 - blkz * p.cwz;
                 for (int k = 0; k < 12; ++k, ++seq) {
                     const int s = (int)(seq % NST);
                     mbar_wait(&B.empty[s], (uint32_t)(((seq / NST) & 1) ^ 1));
                     mbar_arrive_expect_tx(&B.full[s], STAGE_B);
                     const int j = k & 3;
                     if (k >= 4 && k < 8)
-                        tma_load_5d(ring + s * STAGE_F, &tmZv, &B.full[s], z0, oa, 8 * j, 0, z4);     // [32 u][8 v][16 w]
+                        tma_load_box(ring + s * STAGE_F, &tmZv, &B.full[s], tile_coords(g, z0, blkz, f0, f1, 0, 8 * j));     // [32 u][8 v][16 w]
                     else
-                        tma_load_5d(ring + s * STAGE_F, &tmPu, &B.full[s], p0, oa, 0, 8 * j, p4);     // [8 u][32 v][16 w]
+                        tma_load_box(ring + s * STAGE_F, &tmPu, &B.full[s], tile_coords(g, p0, blkp, f0, f1, 8 * j, 0));     // [8 u][32 v][16 w]
                 }
             }
         }
@@ -462,12 +494,12 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
         const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16);
         const bool direct = p.Odirect != nullptr;
         const bool store_thread = STORE && !direct && quad == 0 && lane == 0;
-        const long long vstride = (long long)g.sv * p.lo.ld;
+        const long long vstride = g.sv * p.lo.ld;
         uint32_t use = 0;
         long long it = 0;
         for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
-            int cc, oa, ob;
-            decode_tile(g, tile, cc, oa, ob);
+            int cc, f0, f1;
+            decode_tile(g, tile, cc, f0, f1);
             // ---- step A: S = T_v P, rows (u, w)
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
@@ -551,7 +583,7 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
                 mbar_arrive(&B.a_ready[slot]);
             }
             const int col0 = cc * CB, blko = col0 / p.cwo;
-            const int c0o = col0 - blko * p.cwo, c4o = ob + blko * g.n_before;
+            const int c0o = col0 - blko * p.cwo;
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int j = grp + 2 * jj, slot = grp * 2 + jj;
@@ -574,7 +606,7 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
                     if (direct) {
                         const int blkd = col0 / (int)p.lo.cw;
                         float* yp = p.Odirect + blkd * p.lo.cstride + (col0 - blkd * (int)p.lo.cw) + w +
-                                    ((long long)ob * (G * G) * g.sv + oa + (long long)(8 * j + hi) * G * g.sv) * p.lo.ld;
+                                    (f0 * g.sf0 + f1 * g.sf1 + (long long)(8 * j + hi) * g.su) * p.lo.ld;
 #pragma unroll
                         for (int v = 0; v < 32; ++v) {
                             *yp = __uint_as_float(d[v]);
@@ -587,7 +619,7 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
                         fence_proxy_async_smem();
                         named_bar_sync(4 + grp, 128);
                         if (store_thread) {
-                            tma_store_5d(&tmO, sbuf + j * STAGE_F, c0o, oa, 0, 8 * j, c4o);
+                            tma_store_box(&tmO, sbuf + j * STAGE_F, tile_coords(g, c0o, blko, f0, f1, 8 * j, 0));
                             tma_store_commit();
                         }
                     }
@@ -621,46 +653,82 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------ host side
-static bool make_geom(Geom& g, int d, const int64_t* h_g, int pair, int64_t c) {
-    const int u = 2 * pair, v = u + 1;
-    if (v >= d || h_g[u] != G || h_g[v] != G || c % CB != 0 || c < CB) return false;
-    int64_t sv = 1, nb = 1;
-    for (int j = v + 1; j < d; ++j) sv *= h_g[j];
-    for (int j = 0; j < u; ++j) nb *= h_g[j];
-    if (sv >= (1 << 30) || nb >= (1 << 30) || c / CB >= (1 << 30)) return false;
-    g.sv = (int)sv;
-    g.n_before = (int)nb;
+// Geometry of the pair (au, av), au < av.  dims[] receives (extent, row stride) of the four row groups of the tensor
+// map in memory order (positions 1..4 of the 5-D map; padded with extent-1 groups).
+struct MapDims {
+    long long ext[4], stride[4];
+    int n;               // real groups
+};
+static bool make_geom(Geom& g, MapDims& md, int d, const int64_t* h_g, int au, int av, int64_t c) {
+    if (au < 0 || av <= au || av >= d || h_g[au] != G || h_g[av] != G || c % CB != 0 || c < CB) return false;
+    long long after = 1, mid = 1, before = 1;
+    for (int j = av + 1; j < d; ++j) after *= h_g[j];
+    for (int j = au + 1; j < av; ++j) mid *= h_g[j];
+    for (int j = 0; j < au; ++j) before *= h_g[j];
+    if ((after > 1) + (mid > 1) + (before > 1) > 2) return false;          // needs a 6-D map: not supported
+    if (after >= (1 << 30) || mid >= (1 << 30) || before >= (1 << 30) || c / CB >= (1 << 30)) return false;
+    const long long s_after = 1, s_v = after, s_mid = G * after, s_u = mid * G * after, s_before = G * mid * G * after;
+    g.su = s_u;
+    g.sv = s_v;
+    g.nf0 = g.nf1 = 1;
+    g.sf0 = g.sf1 = 0;
+    g.pos_f0 = g.pos_f1 = 0;                                               // 0 = unused (never matches a row position)
+    md.n = 0;
+    int nfree = 0;
+    auto add = [&](long long ext, long long stride) { md.ext[md.n] = ext; md.stride[md.n] = stride; return ++md.n; };
+    auto add_free = [&](long long ext, long long stride) {
+        const int pos = add(ext, stride);
+        if (nfree == 0) { g.nf0 = (int)ext; g.sf0 = stride; g.pos_f0 = pos; }
+        else { g.nf1 = (int)ext; g.sf1 = stride; g.pos_f1 = pos; }
+        ++nfree;
+    };
+    if (after > 1) add_free(after, s_after);
+    g.pos_v = add(G, s_v);
+    if (mid > 1) add_free(mid, s_mid);
+    g.pos_u = add(G, s_u);
+    if (before > 1) add_free(before, s_before);
+    g.pos_blk = md.n;                                                      // slowest real group
+    g.size_blk = (int)md.ext[md.n - 1];
+    const long long rows = before * G * mid * G * after;
+    while (md.n < 4) { md.ext[md.n] = 1; md.stride[md.n] = rows; ++md.n; }
     g.n_chunks = (int)(c / CB);
-    g.n_tiles = (long long)nb * sv * g.n_chunks;
+    g.n_tiles = (long long)g.nf0 * g.nf1 * g.n_chunks;
     return true;
 }
 
-// 5-D map over a panel operand: (column within block, inner offset oa, axis v, axis u, outer offset ob [+ block]).
+// 5-D map over a panel operand: (column within block, then the row groups of MapDims).
 // Column-chunked operands (cw < c) must be stacked blocks [nblk][rows][cw] (ld = cw, cstride = rows * cw): the block
-// index then folds into the outermost coordinate.
-static int make_map5(CUtensorMap* map, const float* base, const Geom& g, const Lay& l, int64_t c, int box_v, int box_u) {
+// index then folds into the slowest real row group.
+static int make_map5(CUtensorMap* map, const float* base, const Geom& g, const MapDims& md, const Lay& l, int64_t c,
+                     int box_v, int box_u) {
     TcEncodeTiledFn enc = tc_encode_fn();
     if (enc == nullptr) {
         set_error("kron_tc: cuTensorMapEncodeTiled unavailable");
         return 2;
     }
-    const int64_t rows = (int64_t)g.n_before * G * G * g.sv;
+    const int64_t rows = g.su * G * (g.pos_blk == g.pos_u ? 1 : (int64_t)g.size_blk);   // su * 32 * (extent of the groups before u)
     int64_t nblk = 1;
     if (l.cw < c) {
         if (l.ld != l.cw || l.cstride != rows * l.cw || c % l.cw != 0) return 3;
         nblk = c / l.cw;
     }
     if (l.cw % CB != 0 || l.ld % 4 != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return 3;
-    cuuint64_t gdim[5] = {(cuuint64_t)l.cw, (cuuint64_t)g.sv, (cuuint64_t)G, (cuuint64_t)G, (cuuint64_t)(g.n_before * nblk)};
-    cuuint64_t gstr[4] = {(cuuint64_t)l.ld * 4, (cuuint64_t)g.sv * l.ld * 4, (cuuint64_t)G * g.sv * l.ld * 4,
-                          (cuuint64_t)G * G * g.sv * l.ld * 4};
-    cuuint32_t box[5] = {(cuuint32_t)CB, 1u, (cuuint32_t)box_v, (cuuint32_t)box_u, 1u};
-    cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t box[5], estr[5] = {1u, 1u, 1u, 1u, 1u};
+    gdim[0] = (cuuint64_t)l.cw;
+    box[0] = (cuuint32_t)CB;
+    for (int i = 0; i < 4; ++i) {
+        const int pos = i + 1;
+        gdim[pos] = (cuuint64_t)md.ext[i] * (pos == g.pos_blk ? (cuuint64_t)nblk : 1u);
+        gstr[i] = (cuuint64_t)md.stride[i] * l.ld * 4;
+        box[pos] = pos == g.pos_u ? (cuuint32_t)box_u : pos == g.pos_v ? (cuuint32_t)box_v : 1u;
+    }
     CUresult rc = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), gdim, gstr, box, estr,
                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
-        set_error("kron_tc: cuTensorMapEncodeTiled failed (%d) sv=%d nb=%d ld=%lld cw=%lld", (int)rc, g.sv, g.n_before,
+        set_error("kron_tc: cuTensorMapEncodeTiled failed (%d) su=%lld sv=%lld ld=%lld cw=%lld", (int)rc, g.su, g.sv,
                   (long long)l.ld, (long long)l.cw);
         return 2;
     }
@@ -687,29 +755,31 @@ static bool use_direct_store(const Geom& g, const Lay& l) {
     }
     if (mode == 1) return false;
     if (mode == 2) return true;
-    return (long long)g.sv * l.ld * 4 >= (1ll << 19);
+    return g.sv * l.ld * 4 >= (1ll << 19);
 }
 
 }  // namespace ktc
 
-// Y = (T_{2 pair} x T_{2 pair + 1}) X on the tensor pipe.  Returns 3 when the shape / layout is not supported.
-int tc_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X, float* Y,
-                  int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof) {
+// Y = (T_au x T_av) X on the tensor pipe for any two 32-point grid axes au < av (the other axes act as batch indices).
+// Returns 3 when the shape / layout is not supported.
+int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gmax, int au, int av, const float* X, float* Y,
+                       int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof) {
     using namespace ktc;
     Geom g;
-    if (!make_geom(g, d, h_g, pair, c)) return 3;
+    MapDims md;
+    if (!make_geom(g, md, d, h_g, au, av, c)) return 3;
     const Lay lx = lay_of(h_lay, 0, c), ly = lay_of(h_lay, 1, c);
     CUtensorMap tmX, tmY;
-    if (int rc = make_map5(&tmX, X, g, lx, c, G, 8)) return rc;
-    if (int rc = make_map5(&tmY, Y, g, ly, c, 8, G)) return rc;
+    if (int rc = make_map5(&tmX, X, g, md, lx, c, G, 8)) return rc;
+    if (int rc = make_map5(&tmY, Y, g, md, ly, c, 8, G)) return rc;
     ApplyParams p;
     p.cwx = (int)lx.cw;
     p.cwy = (int)ly.cw;
     p.ly = ly;
     p.Ydirect = use_direct_store(g, ly) ? Y : nullptr;
     p.g = g;
-    p.col_u = cols + (int64_t)(2 * pair) * gmax;
-    p.col_v = cols + (int64_t)(2 * pair + 1) * gmax;
+    p.col_u = cols + (int64_t)au * gmax;
+    p.col_v = cols + (int64_t)av * gmax;
     p.prof = prof;
     const size_t smem = 1024 + 4 * TIMG_B + (size_t)kApplyStages * STAGE_B + TILE_B + (2 * kApplyStages + 8) * 8 + 16;
     auto kfn = prof != nullptr ? pair_apply_tc_kernel<kApplyStages, true> : pair_apply_tc_kernel<kApplyStages, false>;
@@ -721,17 +791,25 @@ int tc_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, in
     return 0;
 }
 
-// Directional backward pair pass on the tensor pipe; out3: 3 doubles, accumulated.  Zout may be NULL.
-int tc_pair_grad_dir(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,
-                     const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st, const int64_t* h_lay) {
+int tc_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X, float* Y,
+                  int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof) {
+    return tc_pair_apply_axes(cols, d, h_g, gmax, 2 * pair, 2 * pair + 1, X, Y, c, st, h_lay, prof);
+}
+
+// Directional backward pair pass on the tensor pipe for the axes au < av; out3 (3 doubles, accumulated):
+// <grad_au, dirs_au>, <grad_av, dirs_av>, <Z', K' P'>.  Zout may be NULL.
+int tc_pair_grad_dir_axes(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int au, int av,
+                          const float* Z, const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st,
+                          const int64_t* h_lay) {
     using namespace ktc;
     Geom g;
-    if (!make_geom(g, d, h_g, pair, c)) return 3;
+    MapDims md;
+    if (!make_geom(g, md, d, h_g, au, av, c)) return 3;
     const Lay lz = lay_of(h_lay, 0, c), lp = lay_of(h_lay, 1, c), lo = lay_of(h_lay, 2, c);
     CUtensorMap tmPu, tmZv, tmO;
-    if (int rc = make_map5(&tmPu, P, g, lp, c, G, 8)) return rc;
-    if (int rc = make_map5(&tmZv, Z, g, lz, c, 8, G)) return rc;
-    if (int rc = make_map5(&tmO, Zout != nullptr ? Zout : P, g, Zout != nullptr ? lo : lp, c, G, 8)) return rc;
+    if (int rc = make_map5(&tmPu, P, g, md, lp, c, G, 8)) return rc;
+    if (int rc = make_map5(&tmZv, Z, g, md, lz, c, 8, G)) return rc;
+    if (int rc = make_map5(&tmO, Zout != nullptr ? Zout : P, g, md, Zout != nullptr ? lo : lp, c, G, 8)) return rc;
     GradParams p;
     p.cwz = (int)lz.cw;
     p.cwp = (int)lp.cw;
@@ -739,10 +817,10 @@ int tc_pair_grad_dir(const float* cols, const float* dirs, int d, const int64_t*
     p.lo = lo;
     p.Odirect = (Zout != nullptr && use_direct_store(g, lo)) ? Zout : nullptr;
     p.g = g;
-    p.col_u = cols + (int64_t)(2 * pair) * gmax;
-    p.col_v = cols + (int64_t)(2 * pair + 1) * gmax;
-    p.dir_u = dirs + (int64_t)(2 * pair) * gmax;
-    p.dir_v = dirs + (int64_t)(2 * pair + 1) * gmax;
+    p.col_u = cols + (int64_t)au * gmax;
+    p.col_v = cols + (int64_t)av * gmax;
+    p.dir_u = dirs + (int64_t)au * gmax;
+    p.dir_v = dirs + (int64_t)av * gmax;
     p.out3 = out3;
     const size_t smem = 1024 + 8 * TIMG_B + (size_t)kGradStages * STAGE_B + 2 * TILE_B + (2 * kGradStages + 9) * 8 + 3 * 8 * 4 + 16;
     const long long grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
@@ -758,6 +836,11 @@ int tc_pair_grad_dir(const float* cols, const float* dirs, int d, const int64_t*
     WISKI_CHECK_LAUNCH("kron_tc(pair_grad_dir)");
     count_launches(1);
     return 0;
+}
+
+int tc_pair_grad_dir(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,
+                     const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st, const int64_t* h_lay) {
+    return tc_pair_grad_dir_axes(cols, dirs, d, h_g, gmax, 2 * pair, 2 * pair + 1, Z, P, Zout, c, out3, st, h_lay);
 }
 
 }  // namespace wiski

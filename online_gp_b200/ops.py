@@ -294,6 +294,21 @@ def _fused_supported(sizes, X):
     return bool(_lib.load().wiski_kron_fused_supported(len(sizes), h_g, X.shape[1]))
 
 
+def _pair_axes(pair):
+    """pair index p -> grid axes (2p, 2p + 1); an explicit (axis_u, axis_v) tuple passes through."""
+    return (2 * pair, 2 * pair + 1) if isinstance(pair, int) else (int(pair[0]), int(pair[1]))
+
+
+def kron_pairs(sizes, directional=True):
+    """How the grid axes are paired for the fused two-axes passes (applied last to first).  4-D grids on the tensor-core
+    path use (0,3) + (1,2) — see settings.kron_outer_inner_pairing; the SIMT full-gradient pass only knows adjacent pairs."""
+    d = len(sizes)
+    if (d == 4 and directional and settings.kron_outer_inner_pairing.on() and settings.kron_directional_grad.on()
+            and _lib.load().wiski_kron_tc_enable(-1)):
+        return [(0, 3), (1, 2)]
+    return [(2 * p, 2 * p + 1) for p in range(d // 2)]
+
+
 def _lay_array(c, *chunked):
     """(ld, cw, cstride) per operand for the *_lay entry points; `chunked` item = None (plain [m, c]) or (W, m):
     column-chunked [W, m, c / W] (block j = columns [j c/W, (j+1) c/W), row-major with pitch c / W)."""
@@ -308,25 +323,27 @@ def _lay_array(c, *chunked):
 
 
 def _fused_pair_apply(cols, sizes, pair, X, chunk_out=1, out=None):
-    """Y = (T_2p x T_2p+1) X for X [m, c].  chunk_out = W > 1: Y is written column-chunked, [W, m, c / W] (the send
-    buffer of the row -> column all-to-all of the sharded path: no transposing copy)."""
+    """Y = (T_u x T_v) X for X [m, c]; pair = index p (axes 2p, 2p+1) or an (axis_u, axis_v) tuple.  chunk_out = W > 1: Y is
+    written column-chunked, [W, m, c / W] (the send buffer of the row -> column all-to-all of the sharded path: no
+    transposing copy)."""
     d, gmax = cols.shape
     m, c = X.shape
     h_g = (c_int64 * d)(*sizes)
+    au, av = _pair_axes(pair)
+    fn = _lib.load().wiski_kron_pair_apply_axes_f32
     if chunk_out > 1:
         if c % (16 * chunk_out) != 0:
             raise ValueError("column-chunked output needs c % (16 * chunks) == 0")
         Y = torch.empty(chunk_out, m, c // chunk_out, dtype=X.dtype, device=X.device) if out is None else out
         if Y.shape != (chunk_out, m, c // chunk_out) or not Y.is_contiguous() or Y.dtype != X.dtype:
             raise ValueError("_fused_pair_apply: bad `out`")
-        _call_fn("wiski_kron_fused_pair_apply", _lib.load().wiski_kron_fused_pair_apply_lay_f32, _ptr(cols), d, h_g, gmax,
-                 pair, _ptr(X), _ptr(Y), c, _lay_array(c, None, (chunk_out, m)), _stream())
+        _call_fn("wiski_kron_fused_pair_apply", fn, _ptr(cols), d, h_g, gmax, au, av, _ptr(X), _ptr(Y), c,
+                 _lay_array(c, None, (chunk_out, m)), _stream())
         return Y
     Y = torch.empty_like(X) if out is None else out
     if Y.shape != X.shape or not Y.is_contiguous() or Y.dtype != X.dtype or Y.data_ptr() == X.data_ptr():
         raise ValueError("_fused_pair_apply: bad `out`")
-    _call_fn("wiski_kron_fused_pair_apply", _lib.load().wiski_kron_fused_pair_apply_f32, _ptr(cols), d, h_g, gmax, pair,
-             _ptr(X), _ptr(Y), c, _stream())
+    _call_fn("wiski_kron_fused_pair_apply", fn, _ptr(cols), d, h_g, gmax, au, av, _ptr(X), _ptr(Y), c, None, _stream())
     return Y
 
 
@@ -350,8 +367,8 @@ def _fused_pair_grad(cols, sizes, pair, Z, P, acc, store, chunk_z=1, zout=None):
 
 
 def _fused_pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store, chunk_z=1, zout=None):
-    """One directional backward pair pass (wiski_kron_fused_pair_grad_dir): out3 += [<g_2p, dirs_2p>, <g_2p+1, dirs_2p+1>,
-    <Z', K' P'>].  chunk_z = W > 1: Z is given column-chunked [W, m, c / W] (received from the column -> row
+    """One directional backward pair pass: out3 += [<g_u, dirs_u>, <g_v, dirs_v>, <Z', K' P'>] for the axes of `pair` (index p
+    or (axis_u, axis_v)).  chunk_z = W > 1: Z is given column-chunked [W, m, c / W] (received from the column -> row
     all-to-all); P and the returned Zout are plain [m, c]."""
     d, gmax = cols.shape
     m, c = P.shape
@@ -359,14 +376,20 @@ def _fused_pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store, chunk_z=1, 
     if Zout is not None and (Zout.shape != P.shape or not Zout.is_contiguous() or Zout.data_ptr() in (Z.data_ptr(), P.data_ptr())):
         raise ValueError("_fused_pair_grad_dir: bad `zout`")
     h_g = (c_int64 * d)(*sizes)
-    if chunk_z > 1:
-        _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_fused_pair_grad_dir_lay_f32, _ptr(cols), _ptr(dirs), d,
-                 h_g, gmax, pair, _ptr(Z), _ptr(P), _ptr(Zout), c, _ptr(out3), _lay_array(c, (chunk_z, m), None, None),
-                 _stream())
-        return Zout
-    _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_fused_pair_grad_dir_f32, _ptr(cols), _ptr(dirs), d, h_g,
-             gmax, pair, _ptr(Z), _ptr(P), _ptr(Zout), c, _ptr(out3), _stream())
+    au, av = _pair_axes(pair)
+    lay = _lay_array(c, (chunk_z, m), None, None) if chunk_z > 1 else None
+    _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_pair_grad_dir_axes_f32, _ptr(cols), _ptr(dirs), d, h_g, gmax,
+             au, av, _ptr(Z), _ptr(P), _ptr(Zout), c, _ptr(out3), lay, _stream())
     return Zout
+
+
+def _by_axis(out, pairs, d):
+    """out [npairs, 3] (per pair: axis_u, axis_v, scale) -> the d directional sums ordered by grid axis."""
+    order = [0] * d
+    for p, (au, av) in enumerate(pairs):
+        order[au], order[av] = 2 * p, 2 * p + 1
+    flat = out[:, :2].reshape(-1)
+    return flat[torch.tensor(order, device=out.device)]
 
 
 def _surrogate_col_grad(cols, dirs, s_dir, s_scale):
@@ -402,14 +425,16 @@ class _KronFn(torch.autograd.Function):
             return Y if out is None else out.copy_(Y)
         if _fused_supported(sizes, X):
             # pairs applied last to first; M[p] = (pairs > p) applied to X is what the backward pair pass p needs
-            npairs = len(sizes) // 2
+            pairs = kron_pairs(sizes, directional=dirs is not None)
+            npairs = len(pairs)
             M = [None] * npairs
             M[-1] = X.contiguous()
             for p in range(npairs - 1, 0, -1):
-                M[p - 1] = _fused_pair_apply(cols, sizes, p, M[p])
-            Y = _fused_pair_apply(cols, sizes, 0, M[0], out=out)       # `out`: e.g. the send buffer of an exchange
+                M[p - 1] = _fused_pair_apply(cols, sizes, pairs[p], M[p])
+            Y = _fused_pair_apply(cols, sizes, pairs[0], M[0], out=out)       # `out`: e.g. the send buffer of an exchange
             ctx.save_for_backward(cols, *M)
             ctx.suffix = "fused"
+            ctx.pairs = pairs
             ctx.dirs = None if dirs is None else dirs.detach().to(cols.dtype).contiguous()
             return Y
         geo = _axis_geometry(sizes, X.shape[1])
@@ -436,14 +461,15 @@ class _KronFn(torch.autograd.Function):
         acc = torch.zeros(d, gmax, dtype=torch.float64, device=gY.device)
         if ctx.suffix == "fused":
             Zc = gY
-            npairs = d // 2
+            pairs = ctx.pairs
+            npairs = len(pairs)
             if ctx.dirs is not None:
-                # directional form: one 512-FMA direction apply + dot per grid line instead of a 1024-FMA contraction
+                # directional form: direction-matrix applies + dot products instead of the 32-entry column gradients
                 out = torch.zeros(npairs, 3, dtype=torch.float64, device=gY.device)
                 for p in range(npairs):
-                    Zc = _fused_pair_grad_dir(cols, ctx.dirs, sizes, p, Zc, S[p], out[p],
+                    Zc = _fused_pair_grad_dir(cols, ctx.dirs, sizes, pairs[p], Zc, S[p], out[p],
                                               store=(p < npairs - 1 or ctx.needs_input_grad[1]))
-                gcols = _surrogate_col_grad(cols[:, :sizes[0]], ctx.dirs[:, :sizes[0]], out[:, :2].reshape(-1), out[-1, 2])
+                gcols = _surrogate_col_grad(cols[:, :sizes[0]], ctx.dirs[:, :sizes[0]], _by_axis(out, pairs, d), out[-1, 2])
                 if gcols.shape[1] < gmax:
                     gcols = torch.nn.functional.pad(gcols, (0, gmax - gcols.shape[1]))
                 return gcols, (Zc if ctx.needs_input_grad[1] else None), None, None

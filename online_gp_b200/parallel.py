@@ -245,14 +245,17 @@ class _ShardedKronFn(torch.autograd.Function):
         ctx.dirs = None if (dirs is None or not ctx.fused) else dirs.detach().to(cols.dtype).contiguous()
         W = plan.world
         if ctx.fused:
-            # slab [g0/W, 32, 32, 32, c]: pair (2,3) is slab-local; pair (0,1) runs in the column-sharded layout
+            # slab [g0/W, 32, 32, 32, c]: one pair of the axes 1..3 is slab-local, the pair containing axis 0 runs in the
+            # column-sharded layout: (1,2) + (0,3) with the directional tensor-core passes, (2,3) + (0,1) otherwise
+            ctx.col_pair, ctx.loc_pair = ops.kron_pairs(plan.sizes, directional=ctx.dirs is not None)
             slab = [plan.g0_loc] + plan.sizes[1:]
             cw = X.shape[1] // W
             xb = comm.send_buffer(W * plan.m_loc * cw, X)            # symmetric (peer-mapped) send buffer or None
-            X23s = ops._fused_pair_apply(cols, slab, 1, X.contiguous(), chunk_out=W,
+            X23s = ops._fused_pair_apply(cols, slab, ctx.loc_pair, X.contiguous(), chunk_out=W,
                                          out=None if xb is None else xb.view(W, plan.m_loc, cw))   # send layout
             X23c = comm.all_to_all(X23s.view(W, plan.m_loc, cw)).view(W * plan.m_loc, cw)     # all rows of my columns
-            Yc = ops._fused_pair_apply(cols, plan.sizes, 0, X23c, out=None if xb is None else xb.view(W * plan.m_loc, cw))
+            Yc = ops._fused_pair_apply(cols, plan.sizes, ctx.col_pair, X23c,
+                                       out=None if xb is None else xb.view(W * plan.m_loc, cw))
             ctx.save_for_backward(cols, X, X23c)
             return comm.all_to_all(Yc.view(W, plan.m_loc, cw))                                # [W, m_loc, cw] blocks
         ctx.save_for_backward(cols, X)
@@ -279,17 +282,17 @@ class _ShardedKronFn(torch.autograd.Function):
                 # directional form: 3 numbers per pair pass instead of two 32-entry column gradients; the partial sums
                 # of the ranks (pair (0,1): my column block, pair (2,3): my row slab) meet in one 6-double all-reduce
                 out = torch.zeros(2, 3, dtype=torch.float64, device=X.device)
-                Z01c = ops._fused_pair_grad_dir(cols, ctx.dirs, plan.sizes, 0, Zc, X23c, out[0], store=True,
+                Z01c = ops._fused_pair_grad_dir(cols, ctx.dirs, plan.sizes, ctx.col_pair, Zc, X23c, out[0], store=True,
                                                 zout=None if xb is None else xb.view(W * plan.m_loc, cw))
                 if W > 1:
                     Z01b = comm.all_to_all(Z01c.view(W, plan.m_loc, cw))
-                    ops._fused_pair_grad_dir(cols, ctx.dirs, slab, 1, Z01b, X, out[1], store=False, chunk_z=W)
+                    ops._fused_pair_grad_dir(cols, ctx.dirs, slab, ctx.loc_pair, Z01b, X, out[1], store=False, chunk_z=W)
                     comm.allreduce_(out)
                 else:
-                    ops._fused_pair_grad_dir(cols, ctx.dirs, slab, 1, Z01c, X, out[1], store=False)
-                gcols = ops._surrogate_col_grad(cols, ctx.dirs, out[:, :2].reshape(-1), out[-1, 2])
+                    ops._fused_pair_grad_dir(cols, ctx.dirs, slab, ctx.loc_pair, Z01c, X, out[1], store=False)
+                gcols = ops._surrogate_col_grad(cols, ctx.dirs, ops._by_axis(out, [ctx.col_pair, ctx.loc_pair], plan.d), out[-1, 2])
                 return gcols, None, None, None, None
-            Z01c = ops._fused_pair_grad(cols, plan.sizes, 0, Zc, X23c, acc, store=True,
+            Z01c = ops._fused_pair_grad(cols, plan.sizes, 0, Zc, X23c, acc, store=True,      # (full-gradient form: pairs (0,1), (2,3))
                                         zout=None if xb is None else xb.view(W * plan.m_loc, cw))   # axes 0, 1 (+ Z01)
             Z01b = comm.all_to_all(Z01c.view(W, plan.m_loc, cw))                               # chunked row layout
             ops._fused_pair_grad(cols, slab, 1, Z01b, X, acc, store=False, chunk_z=W)          # axes 2, 3

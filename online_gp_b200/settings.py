@@ -180,3 +180,11 @@ class backward_gemm_tf32_passes(_value_context):
     normalises away), 3 = the 3xTF32 split every *value* GEMM uses.  fp32 hyper-gradients stay within the 1e-2 bar
     either way (asserted in tests/model_cases.py); fp64 is unaffected (SIMT kernels)."""
     _global_value = 1
+
+
+class kron_outer_inner_pairing(_feature_flag):
+    """32^4 grids, tensor-core pair kernels: pair the grid axes as (1,2) + (0,3) instead of (0,1) + (2,3).  Every tile of the
+    pair (0,1) is 1024 rows that lie 1024 rows apart (one 64-byte piece per 2 MB page); the tiles of (0,3) are 32 runs of 32
+    consecutive rows and those of (1,2) rows 32 apart inside 32 pages, which the memory system streams about twice as
+    fast (measured on B200, profiles/r02_pair_kernels.md).  The Kronecker factors commute, so the result is the same."""
+    _state = True

@@ -127,22 +127,26 @@ def _toeplitz(col, g):
 
 def _install_fused_emulation(ops, parallel, axis):
     def pair_views(sizes, pair, X):
+        """X [m, c] viewed as [before, u, mid, v, after, c] for the axes of `pair` (index p or (axis_u, axis_v))."""
+        au, av = ops._pair_axes(pair)
         c = X.shape[1]
-        u, v = sizes[2 * pair], sizes[2 * pair + 1]
-        before = 1
-        for s in sizes[:2 * pair]:
-            before *= s
-        after = X.shape[0] // (before * u * v)
-        return X.reshape(before, u, v, after, c), u, v
+        u, v = sizes[au], sizes[av]
+        before = mid = 1
+        for s_ in sizes[:au]:
+            before *= s_
+        for s_ in sizes[au + 1:av]:
+            mid *= s_
+        after = X.shape[0] // (before * u * mid * v)
+        return X.reshape(before, u, mid, v, after, c), u, v, au, av
 
     def unchunk(Zb):                        # [W, m, cw] -> [m, W cw]
         W, m, cw = Zb.shape
         return Zb.permute(1, 0, 2).reshape(m, W * cw)
 
     def pair_apply(cols, sizes, pair, X, chunk_out=1, out=None):
-        V, u, v = pair_views(sizes, pair, X)
-        Tu, Tv = _toeplitz(cols[2 * pair], u), _toeplitz(cols[2 * pair + 1], v)
-        Y = torch.einsum("ab,cd,obdwk->oacwk", Tu, Tv, V).reshape(X.shape)
+        V, u, v, au, av = pair_views(sizes, pair, X)
+        Tu, Tv = _toeplitz(cols[au], u), _toeplitz(cols[av], v)
+        Y = torch.einsum("ab,cd,obmdwk->oamcwk", Tu, Tv, V).reshape(X.shape)
         if chunk_out > 1:
             m, c = X.shape
             Y = Y.view(m, chunk_out, c // chunk_out).permute(1, 0, 2).contiguous()
@@ -151,39 +155,39 @@ def _install_fused_emulation(ops, parallel, axis):
     def pair_grad(cols, sizes, pair, Z, P, acc, store, chunk_z=1, zout=None):
         if chunk_z > 1:
             Z = unchunk(Z)
-        Zv, u, v = pair_views(sizes, pair, Z)
-        Pv, _, _ = pair_views(sizes, pair, P)
-        Tu, Tv = _toeplitz(cols[2 * pair], u), _toeplitz(cols[2 * pair + 1], v)
-        TvP = torch.einsum("cd,obdwk->obcwk", Tv, Pv)
-        TuZ = torch.einsum("ab,obdwk->oadwk", Tu, Zv)
-        Su = torch.einsum("oadwk,obdwk->ab", Zv.double(), TvP.double())
-        Sv = torch.einsum("oadwk,oaewk->de", TuZ.double(), Pv.double())
-        for S, g, slot in ((Su, u, 2 * pair), (Sv, v, 2 * pair + 1)):
+        Zv, u, v, au, av = pair_views(sizes, pair, Z)
+        Pv = pair_views(sizes, pair, P)[0]
+        Tu, Tv = _toeplitz(cols[au], u), _toeplitz(cols[av], v)
+        TvP = torch.einsum("cd,obmdwk->obmcwk", Tv, Pv)
+        TuZ = torch.einsum("ab,obmdwk->oamdwk", Tu, Zv)
+        Su = torch.einsum("oamdwk,obmdwk->ab", Zv.double(), TvP.double())
+        Sv = torch.einsum("oamdwk,oamewk->de", TuZ.double(), Pv.double())
+        for S, g, slot in ((Su, u, au), (Sv, v, av)):
             ar = torch.arange(g)
             off = (ar.unsqueeze(0) - ar.unsqueeze(1)).abs().reshape(-1)
             acc[slot][:g] += torch.zeros(g, dtype=torch.float64).index_add_(0, off, S.reshape(-1))
         if not store:
             return None
-        Zo = torch.einsum("cd,oadwk->oacwk", Tv, TuZ).reshape(P.shape)
+        Zo = torch.einsum("cd,oamdwk->oamcwk", Tv, TuZ).reshape(P.shape)
         return Zo if zout is None else zout.copy_(Zo)
 
     def pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store, chunk_z=1, zout=None):
         if chunk_z > 1:
             Z = unchunk(Z)
-        Zv, u, v = pair_views(sizes, pair, Z)
-        Pv, _, _ = pair_views(sizes, pair, P)
-        Tu, Tv = _toeplitz(cols[2 * pair], u), _toeplitz(cols[2 * pair + 1], v)
-        Du, Dv = _toeplitz(dirs[2 * pair], u), _toeplitz(dirs[2 * pair + 1], v)
-        S = torch.einsum("cd,obdwk->obcwk", Tv, Pv).double()
-        zu = torch.einsum("ab,obdwk->oadwk", Tu, Zv)
-        zd = torch.einsum("ab,obdwk->oadwk", Du, Zv).double()
-        zd2 = torch.einsum("cd,oadwk->oacwk", Dv, zu).double()
+        Zv, u, v, au, av = pair_views(sizes, pair, Z)
+        Pv = pair_views(sizes, pair, P)[0]
+        Tu, Tv = _toeplitz(cols[au], u), _toeplitz(cols[av], v)
+        Du, Dv = _toeplitz(dirs[au], u), _toeplitz(dirs[av], v)
+        S = torch.einsum("cd,obmdwk->obmcwk", Tv, Pv).double()
+        zu = torch.einsum("ab,obmdwk->oamdwk", Tu, Zv)
+        zd = torch.einsum("ab,obmdwk->oamdwk", Du, Zv).double()
+        zd2 = torch.einsum("cd,oamdwk->oamcwk", Dv, zu).double()
         out3[0] += (zd * S).sum()
         out3[1] += (zd2 * Pv.double()).sum()
         out3[2] += (zu.double() * S).sum()
         if not store:
             return None
-        Zo = torch.einsum("cd,oadwk->oacwk", Tv, zu).reshape(P.shape)
+        Zo = torch.einsum("cd,oamdwk->oamcwk", Tv, zu).reshape(P.shape)
         return Zo if zout is None else zout.copy_(Zo)
 
     saved = (ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok, ops._fused_pair_grad_dir)
