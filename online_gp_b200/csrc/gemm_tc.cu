@@ -147,7 +147,10 @@ struct Batching {
 // out: slice z writes out + z * slice_stride, row-major with leading dimension ld_out.
 // Warp roles (384 threads): 0 TMA producer | 1 MMA issuer | 2 TMEM allocator | 4-7 epilogue | 8-11 operand split.
 // Two TMEM accumulators (2 x BN <= 512 columns) let the MMAs of tile i+1 overlap the epilogue of tile i.
-template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
+// SPLIT = true: a stage holds each operand tile twice (raw | fp32 remainder) for the 3xTF32 products; false: raw tiles
+// only (single tf32 pass, bt.terms == 1) — half the shared memory per stage, which pays for BK = 32 (128-byte rows per
+// TMA request instead of 64-byte ones: the A panel of the panel GEMM is fetched as row pieces 1.7 KB apart).
+template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES, bool SPLIT = true>
 __global__ void __launch_bounds__(384, 1)
 tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, float* __restrict__ out,
                  int64_t Mdim, int64_t Ndim, int64_t Kdim, int BN, int n_tiles_n, int n_tiles_m, int64_t n_work,
@@ -156,7 +159,8 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int A_BYTES = 128 * BK * 4;
     const int B_BYTES = BN * BK * 4;
-    const int STAGE_BYTES = 2 * (A_BYTES + B_BYTES);
+    constexpr int NCOPY = SPLIT ? 2 : 1;
+    const int STAGE_BYTES = NCOPY * (A_BYTES + B_BYTES);
     constexpr int STG_PITCH = 36;                               // words per staged row (32 + 4: conflict-free 16 B rows)
     float* staging = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);        // [4 warps][32][36]
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + 4 * 32 * STG_PITCH * 4);
@@ -230,7 +234,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
-                    uint8_t* sB = sA + 2 * A_BYTES;
+                    uint8_t* sB = sA + NCOPY * A_BYTES;
                     mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)(A_BYTES + B_BYTES));
                     int kA, kB, mA = (int)m0, nB = (int)n0;
                     if (bt.nb > 0) {
@@ -287,7 +291,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t aB = smem_u32(smem + (size_t)stage * STAGE_BYTES);   // A big
                     const uint32_t aS = aB + A_BYTES;                                     // A small
-                    const uint32_t bB = aB + 2 * A_BYTES;                                 // B big
+                    const uint32_t bB = aB + NCOPY * A_BYTES;                             // B big
                     const uint32_t bS = bB + B_BYTES;                                     // B small
 #pragma unroll
                     for (int ks = 0; ks < BK / 8; ++ks) {
@@ -305,7 +309,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                                       : make_desc(bB + ks * 1024, BK * 128, 512, 1);
                         const uint64_t dBs = B_KMAJOR ? make_desc(bS + ks * 32, 0, BK * 32, BK == 32 ? 2 : 4)
                                                       : make_desc(bS + ks * 1024, BK * 128, 512, 1);
-                        if (bt.terms == 1) {
+                        if (!SPLIT || bt.terms == 1) {
                             umma_tf32(tmem_d, dAb, dBb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
                         } else {
                             umma_tf32(tmem_d, dAs, dBb, idesc, (kb > 0 || ks > 0) ? 1u : 0u);   // small terms first
@@ -333,10 +337,10 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&full_bar[stage], phase);
                 uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
 #pragma unroll 4
-                for (int i = t; i < (bt.terms == 1 ? 0 : nvec); i += 128) {
+                for (int i = t; i < ((!SPLIT || bt.terms == 1) ? 0 : nvec); i += 128) {
                     // vectors [0, A_BYTES/16) belong to A (big at sA, small at sA + A_BYTES), the rest to B
                     const bool isA = i < A_BYTES / 16;
-                    uint4* big = reinterpret_cast<uint4*>(isA ? sA : sA + 2 * A_BYTES) + (isA ? i : i - A_BYTES / 16);
+                    uint4* big = reinterpret_cast<uint4*>(isA ? sA : sA + NCOPY * A_BYTES) + (isA ? i : i - A_BYTES / 16);
                     uint4* sml = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(big) + (isA ? A_BYTES : B_BYTES));
                     uint4 v = *big;
                     uint4 s;
@@ -461,7 +465,7 @@ static inline bool tc_shape_ok(int64_t m, int64_t r, int64_t r2) {
     return m >= 2048 && r >= 64 && r2 >= 64 && (r % 4) == 0 && (r2 % 4) == 0 && r <= 65536 && r2 <= 65536;
 }
 
-template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES>
+template <bool A_KMAJOR, bool B_KMAJOR, int BK, int STAGES, bool SPLIT = true>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, int64_t Mdim, int64_t Ndim, int64_t Kdim,
                   int bn, int ntiles, int64_t k_per_slice, int64_t nslices, int64_t ld_out, int64_t slice_stride,
                   cudaStream_t st, const char* name, const Batching* btp = nullptr) {
@@ -470,9 +474,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, float* out, in
     bt.terms = 3;
     if (btp != nullptr) bt = *btp;
     if (bt.terms != 1) bt.terms = 3;
-    size_t smem = (size_t)STAGES * 2 * ((size_t)128 * BK * 4 + (size_t)bn * BK * 4) + 4 * 32 * 36 * 4 +
+    size_t smem = (size_t)STAGES * (SPLIT ? 2 : 1) * ((size_t)128 * BK * 4 + (size_t)bn * BK * 4) + 4 * 32 * 36 * 4 +
                   (3 * STAGES + 5) * 8 + 1024;
-    auto kfn = tc_gemm3x_kernel<A_KMAJOR, B_KMAJOR, BK, STAGES>;
+    auto kfn = tc_gemm3x_kernel<A_KMAJOR, B_KMAJOR, BK, STAGES, SPLIT>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), name);
     const int n_tiles_m = (int)ceil_div(Mdim, 128);
     const int64_t n_work = (bt.n_list > 0 ? (int64_t)bt.n_list : (int64_t)n_tiles_m * ntiles) * nslices;
@@ -560,14 +564,21 @@ int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int6
     if (!tc_shape_ok(m, r, r2)) return 3;
     if (nblk > 1 && (r2 % nblk != 0 || (r2 / nblk) % 32 != 0)) return 3;
     CUtensorMap tmA, tmB;
-    if (int rc = make_map(&tmA, P, m, r, 128, false, kRmulBK)) return rc;   // K-major A: box {BK k, 128 rows}
-    if (int rc = make_map(&tmB, M, r, r2, kRmulBK, true)) return rc;   // MN-major B: box {32 cols, BK rows}
     int ntiles;
     int bn = pick_bn(r2, &ntiles);
     Batching bt = {r, r, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     bt.terms = terms == 1 ? 1 : 3;
     int64_t ld_out = r2;
     if (nblk > 1) { bt.o_cw = r2 / nblk; bt.o_cstride = m * (r2 / nblk); ld_out = r2 / nblk; }
+    if (bt.terms == 1) {
+        constexpr int BK1 = 32, ST1 = 4;                                    // 4 x (16 KB + bn * 128 B) <= 176 KB
+        if (int rc = make_map(&tmA, P, m, r, 128, false, BK1)) return rc;
+        if (int rc = make_map(&tmB, M, r, r2, BK1, true)) return rc;
+        return launch<true, false, BK1, ST1, false>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, ld_out, 0, st,
+                                                    "tc_panel_rmul(tf32x1)", &bt);
+    }
+    if (int rc = make_map(&tmA, P, m, r, 128, false, kRmulBK)) return rc;   // K-major A: box {BK k, 128 rows}
+    if (int rc = make_map(&tmB, M, r, r2, kRmulBK, true)) return rc;   // MN-major B: box {32 cols, BK rows}
     return launch<true, false, kRmulBK, kRmulStages>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, ld_out, 0, st, "tc_panel_rmul",
                                                      &bt);
 }

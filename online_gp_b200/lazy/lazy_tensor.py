@@ -51,6 +51,24 @@ def psd_safe_cholesky(A, jitter=None, max_tries=3):
     raise NotPSDError(f"Matrix not positive definite after repeatedly adding jitter up to {jn:.1e}.")
 
 
+class _InvQuadFn(torch.autograd.Function):
+    """b^T A^-1 b per column of b, given a solve x = A^-1 b computed elsewhere (CG): the forward value uses x, the
+    backward is  dA = -x g x^T,  db = 2 x g  (GPyTorch ``InvQuadLogDet.backward`` without the probe vectors)."""
+
+    @staticmethod
+    def forward(ctx, A, b, x):
+        ctx.save_for_backward(x)
+        return (x * b).sum(-2)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        xg = x * g.unsqueeze(-2)
+        gA = -(xg @ x.transpose(-1, -2)) if ctx.needs_input_grad[0] else None
+        gb = 2.0 * xg if ctx.needs_input_grad[1] else None
+        return gA, gb, None
+
+
 class LazyTensor:
     # ---- protocol (override)
     def _size(self):
@@ -188,17 +206,27 @@ class LazyTensor:
         return inv_quad_term, logdet_term
 
     def _inv_quad_logdet_iterative(self, inv_quad_rhs, logdet, reduce_inv_quad):
+        """Beyond ``max_cholesky_size`` (GPyTorch: mBCG solves + stochastic Lanczos quadrature, App. A.5).  The solve is
+        the operator's CG driver, differentiable through  d(b^T A^-1 b) = -x^T dA x + 2 x^T db  with x = A^-1 b
+        (``_InvQuadFn``).  log|A|: GPyTorch estimates it with ``num_trace_samples`` random probes (non-deterministic, a
+        few per cent off); the operators of this path are at most max_root_decomposition_size wide, so it is taken
+        exactly from one dense factorisation instead — deterministic, and differentiable the ordinary way."""
         inv_quad_term = logdet_term = None
+        dense = self.evaluate() if (logdet or (inv_quad_rhs is not None and torch.is_grad_enabled())) else None
         if inv_quad_rhs is not None:
             rhs = inv_quad_rhs.unsqueeze(-1) if inv_quad_rhs.dim() == 1 else inv_quad_rhs
-            sol = self._solve(rhs)
-            inv_quad_term = (sol * rhs).sum(-2)
+            sol = self._solve(rhs.detach())
+            if dense is not None and (dense.requires_grad or rhs.requires_grad):
+                inv_quad_term = _InvQuadFn.apply(dense, rhs, sol.detach())
+            else:
+                inv_quad_term = (sol * rhs).sum(-2)
             if reduce_inv_quad:
                 inv_quad_term = inv_quad_term.sum(-1)
         if logdet:
-            raise NotImplementedError(
-                "logdet beyond max_cholesky_size needs stochastic Lanczos quadrature, which the WISKI path never "
-                "reaches (r <= max_root_decomposition_size <= max_cholesky_size in every shipped config, SURVEY F5)")
+            Lc = psd_safe_cholesky(dense)
+            logdet_term = 2.0 * Lc.diagonal(dim1=-2, dim2=-1).log().sum(-1)
+            if settings.skip_logdet_forward.on():
+                logdet_term = logdet_term - logdet_term.detach()
         return inv_quad_term, logdet_term
 
     def root_decomposition(self, method=None):

@@ -42,10 +42,13 @@ def _sym_factors(p):
     return C, Cp
 
 
-def _sym_factors_iterative(p, iters=10):
+def _sym_factors_iterative(p, iters=18):
     """Same factors without an eigendecomposition (no host read, so it can be captured in a CUDA graph): the
     Denman-Beavers iteration  Y <- (Y + Z^-1) / 2,  Z <- (Z + Y^-1) / 2  on A / ||A||_F, A = I + p^T p, gives
-    Y -> A^(1/2), Z -> A^(-1/2) quadratically (Higham, Functions of Matrices, §6.3)."""
+    Y -> A^(1/2), Z -> A^(-1/2) (Higham, Functions of Matrices, §6.3).  Convergence is quadratic only once every
+    eigenvalue of the iterate is near its limit; before that the small eigenvalues (1 / ||A||_F after the scaling) halve
+    their log-distance per step, so the count must cover ~0.5 log2 ||A||_F + 5 steps: 18 handles ||p||^2 up to ~6e7 (a
+    leverage no stream of unit-noise observations reaches), and the count cannot depend on device data under capture."""
     q = p.shape[1]
     eye = torch.eye(q, dtype=p.dtype, device=p.device)
     A = eye + p.t() @ p

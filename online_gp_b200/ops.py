@@ -389,7 +389,7 @@ def _by_axis(out, pairs, d):
     for p, (au, av) in enumerate(pairs):
         order[au], order[av] = 2 * p, 2 * p + 1
     flat = out[:, :2].reshape(-1)
-    return flat[torch.tensor(order, device=out.device)]
+    return torch.stack([flat[i] for i in order])        # (no index tensor: nothing may be copied from the host under capture)
 
 
 def _surrogate_col_grad(cols, dirs, s_dir, s_scale):

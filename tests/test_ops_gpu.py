@@ -157,12 +157,12 @@ def test_panel_rmul_and_gram(dt, m, r, r2):
     ref = P.double() @ M.double()
     # fp32: error relative to the scale of the accumulated terms (sqrt(K) for unit-variance data).  The operands are exact
     # to ~2^-22 (3xTF32); what remains is the tensor core's fp32 accumulation over a K slice (2048 rows for the Gram),
-    # measured at ~2e-5 of that scale (csrc/test_gemm_tc.cu); fp64 to rounding
-    tol = dict(rtol=1e-10, atol=1e-9) if dt == torch.float64 else dict(rtol=0.0, atol=2e-5 * r ** 0.5)
+    # which truncates: a relative bias of ~2e-5 of the value per 2048-row slice (csrc/test_gemm_tc.cu); fp64 to rounding
+    tol = dict(rtol=1e-10, atol=1e-9) if dt == torch.float64 else dict(rtol=5e-5, atol=1e-5 * r ** 0.5)
     assert torch.allclose(out.cpu().double(), ref, **tol)
     G = ops.gram(P.to(DEV), Bp.to(DEV))
     refg = P.double().t() @ Bp.double()
-    tolg = dict(rtol=1e-10, atol=1e-8) if dt == torch.float64 else dict(rtol=0.0, atol=5e-5 * m ** 0.5)
+    tolg = dict(rtol=1e-10, atol=1e-8) if dt == torch.float64 else dict(rtol=5e-5, atol=2e-5 * m ** 0.5)
     assert torch.allclose(G.cpu().double(), refg, **tolg)
 
 
