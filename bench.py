@@ -448,7 +448,9 @@ def run_gpu_sharded(args, rank, world, device):
     import torch.distributed as dist
     from online_gp_b200 import _lib, ops
     from online_gp_b200 import settings as S
-    from online_gp_b200.parallel import Comm, ShardedOnlineSKIRegression
+    from online_gp_b200.models import OnlineSKIRegression
+    from online_gp_b200.models.stems import Identity
+    from online_gp_b200.parallel import Comm
 
     d, g, q, n_init, lr, desc = WORKLOADS[args.workload]
     dtype = torch.float32 if args.dtype == "f32" else torch.float64
@@ -462,8 +464,11 @@ def run_gpu_sharded(args, rank, world, device):
            S.sharded_dual_layout(bool(args.dual_layout)))
     for c in ctx:
         c.__enter__()
-    model = ShardedOnlineSKIRegression(x[:n_init].to(device), y[:n_init].to(device), lr=lr, grid_size=g,
-                                       grid_bound=1.0, comm=Comm())
+    # the same class as N = 1, with the communicator: it drives the row-sharded engine (online_gp_b200/parallel.py)
+    wrapper = OnlineSKIRegression(Identity(d), x[:n_init].to(device), y[:n_init].to(device), lr=lr, grid_size=g,
+                                  grid_bound=1.0, comm=Comm())
+    wrapper.set_lr(lr)
+    model = wrapper.engine
     torch.set_default_dtype(prev)
     xs, ys = x[n_init:], y[n_init:]
     xd, yd = xs.to(device), ys.to(device)
@@ -473,8 +478,8 @@ def run_gpu_sharded(args, rank, world, device):
     trace = []
 
     def step(xb, yb):
-        rmse, nll = model.evaluate(xb, yb)
-        _, loss = model.update(xb, yb)
+        rmse, nll = wrapper.evaluate(xb, yb)
+        _, loss = wrapper.update(xb, yb)
         trace.append((rmse, nll, loss))
 
     t = 0
@@ -492,7 +497,7 @@ def run_gpu_sharded(args, rank, world, device):
     prof, ops.PROFILE = ops.PROFILE, None
     use_graphs = not args.no_graphs
     if use_graphs:
-        model.enable_cuda_graphs(True, warmup_calls=1)
+        wrapper.enable_cuda_graphs(True, warmup_calls=1)
         for _ in range(3):                       # 1 eager, 1 capture + first replay, 1 replay: all untimed
             step(xd[t * q:(t + 1) * q], yd[t * q:(t + 1) * q])
             t += 1
@@ -548,6 +553,7 @@ def run_gpu_sharded(args, rank, world, device):
             "config": {"workload": args.workload, "description": desc, "d": d, "grid": g, "m": m, "q": q,
                        "n_init": n_init, "root_rank": r, "stencil": 4 ** d, "lr": lr,
                        "parallelism": f"inducing-grid rows sharded over {world} GPUs (grid axis 0), r x r algebra replicated",
+                       "model_class": type(wrapper).__name__ + "(comm=Comm())",
                        "rows_per_gpu": m // world,
                        "l2": "per-GPU panel slab (%.2f GB) larger than L2" % (m // world * r * b / 1e9),
                        "step": "evaluate + update (Adam step on Woodbury MLL + condition_on_observations)",

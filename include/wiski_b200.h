@@ -201,12 +201,17 @@ int wiski_gram_f64(const double* A, const double* Bm, int64_t m, int64_t r, int6
  * work at r = 432).  Same scratch as wiski_gram_f32. */
 int wiski_gram_sym_f32(const float* A, const float* Bm, int64_t m, int64_t r, float* G, float* work, void* stream);
 /* Panel right-multiply with explicit options: nblk > 1 writes Out column-chunked (as wiski_panel_rmul_chunked_f32);
- * terms = 3: 3xTF32 split products (fp32-grade, what wiski_panel_rmul_f32 does); terms = 1: ONE kind::tf32 product of the
- * raw operands (the tensor core truncates them to tf32: relative error ~1e-3, a uniform ~-2^-11 scale bias plus noise).
- * The host layer uses terms = 1 only for gradient quantities (L grad_Q feeding the hyper-parameter gradient,
- * online_gp/models/online_ski_regression.py:141), never for values (settings.backward_gemm_tf32_passes). */
+ * terms = 3: 3xTF32 split products of both operands (fp32-grade, what wiski_panel_rmul_f32 does);
+ * terms = 2: the small operand M exact (M and its fp32 remainder after tf32 truncation stacked along K in `work`), the
+ *            panel truncated to tf32 by the tensor core — its error is independent from row to row and averages out of
+ *            sums over grid rows, while an error in M would be shared by every row;
+ * terms = 1: ONE kind::tf32 product of the raw operands (relative error ~1e-3).
+ * The host layer uses terms < 3 only for gradient quantities (L grad_Q feeding the hyper-parameter gradient,
+ * online_gp/models/online_ski_regression.py:141), never for values (settings.backward_gemm_tf32_passes).
+ * work: wiski_panel_rmul_ex_work_elems(r, r2) floats, needed for terms = 2 (may be NULL otherwise). */
+int64_t wiski_panel_rmul_ex_work_elems(int64_t r, int64_t r2);
 int wiski_panel_rmul_ex_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, int64_t nblk, int terms,
-                            float* Out, void* stream);
+                            float* Out, float* work, void* stream);
 
 /* Column-chunked forms of k10 / k7 for the row-sharded multi-GPU path, where K L and its gradient are kept as nblk
  * column blocks [m, r2 / nblk] (block j = columns [j r2/nblk, (j+1) r2/nblk)) — the receive / send buffers of the

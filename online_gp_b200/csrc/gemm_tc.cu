@@ -135,6 +135,9 @@ struct Batching {
     //   diagonal are skipped and mirrored by the reduction)
     int n_list;
     unsigned char list_m[24], list_n[24];
+    // a_kwrap > 0: the K coordinate of A wraps after a_kwrap k-blocks while B keeps advancing:  A [B_0 ; B_1] = A B_0 + A B_1
+    //   (panel GEMM with only the small operand split: B_0 = M, B_1 = M - tf32(M), see tc_panel_rmul_f32 terms = 2)
+    int a_kwrap;
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -244,7 +247,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         mA += (int)(o * bt.a_mstride);
                         nB += (int)(o * bt.b_nstride);
                     } else {
-                        kA = (int)(kb0 + (int64_t)kb * BK);
+                        kA = (int)(kb0 + (int64_t)(bt.a_kwrap > 0 ? kb % bt.a_kwrap : kb) * BK);
                         kB = (int)(z * bt.b_kstride + (int64_t)kb * BK);
                     }
                     if (A_KMAJOR) {
@@ -558,24 +561,56 @@ int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r
     return 0;
 }
 
+// [M ; 0 ; M - tf32(M) ; 0]: the small operand of the panel GEMM and its fp32 remainder stacked along K, each padded to
+// a multiple of 32 rows (work: 2 * ceil32(r) * r2 floats)
+__global__ void stack_split_kernel(const float* __restrict__ M, int64_t r, int64_t r2, int64_t rpad, float* __restrict__ out) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= 2 * rpad * r2) return;
+    const int64_t row = e / r2, col = e - row * r2;
+    const int64_t k = row >= rpad ? row - rpad : row;
+    float v = 0.f;
+    if (k < r) {
+        const uint32_t x = __float_as_uint(M[k * r2 + col]);
+        v = row >= rpad ? __uint_as_float(x) - __uint_as_float(x & 0xffffe000u) : __uint_as_float(x);
+    }
+    out[e] = v;
+}
+int64_t tc_rmul_work_elems(int64_t r, int64_t r2) { return 2 * ceil_div(r, 32) * 32 * r2; }
+
 // nblk > 1: Out is written column-chunked, nblk blocks [m, r2 / nblk] stacked.
+// terms: 3 = 3xTF32 (both operands split in shared memory); 1 = one tf32 pass of the raw operands; 2 = the small operand
+// M exact (M and its remainder stacked along K, built in `work`), the panel truncated to tf32 by the tensor core: the
+// panel's truncation error is independent from row to row, so it averages out of every sum over grid rows taken
+// downstream (the hyper-parameter gradient), while an error in M would be shared by all rows.
 int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st,
-                      int64_t nblk, int terms) {
+                      int64_t nblk, int terms, float* work) {
     if (!tc_shape_ok(m, r, r2)) return 3;
+    if (terms == 2 && work == nullptr) terms = 3;
     if (nblk > 1 && (r2 % nblk != 0 || (r2 / nblk) % 32 != 0)) return 3;
     CUtensorMap tmA, tmB;
     int ntiles;
     int bn = pick_bn(r2, &ntiles);
     Batching bt = {r, r, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    bt.terms = terms == 1 ? 1 : 3;
+    bt.terms = terms == 3 ? 3 : 1;
     int64_t ld_out = r2;
     if (nblk > 1) { bt.o_cw = r2 / nblk; bt.o_cstride = m * (r2 / nblk); ld_out = r2 / nblk; }
-    if (bt.terms == 1) {
+    if (terms == 1 || terms == 2) {
         constexpr int BK1 = 32, ST1 = 4;                                    // 4 x (16 KB + bn * 128 B) <= 176 KB
         if (int rc = make_map(&tmA, P, m, r, 128, false, BK1)) return rc;
-        if (int rc = make_map(&tmB, M, r, r2, BK1, true)) return rc;
-        return launch<true, false, BK1, ST1, false>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, ld_out, 0, st,
-                                                    "tc_panel_rmul(tf32x1)", &bt);
+        if (terms == 1) {
+            if (int rc = make_map(&tmB, M, r, r2, BK1, true)) return rc;
+            return launch<true, false, BK1, ST1, false>(tmA, tmB, Out, m, r2, r, bn, ntiles, r, 1, ld_out, 0, st,
+                                                        "tc_panel_rmul(tf32x1)", &bt);
+        }
+        const int64_t rpad = ceil_div(r, 32) * 32;
+        stack_split_kernel<<<(unsigned)ceil_div(2 * rpad * r2, 256), 256, 0, st>>>(M, r, r2, rpad, work);
+        WISKI_CHECK_LAUNCH("tc_panel_rmul(stack)");
+        count_launches(1);
+        if (int rc = make_map(&tmB, work, 2 * rpad, r2, BK1, true)) return rc;
+        bt.a_kstride = bt.b_kstride = 2 * rpad;
+        bt.a_kwrap = (int)(rpad / BK1);
+        return launch<true, false, BK1, ST1, false>(tmA, tmB, Out, m, r2, 2 * rpad, bn, ntiles, 2 * rpad, 1, ld_out, 0, st,
+                                                    "tc_panel_rmul(tf32, M split)", &bt);
     }
     if (int rc = make_map(&tmA, P, m, r, 128, false, kRmulBK)) return rc;   // K-major A: box {BK k, 128 rows}
     if (int rc = make_map(&tmB, M, r, r2, kRmulBK, true)) return rc;   // MN-major B: box {32 cols, BK rows}

@@ -12,7 +12,8 @@ namespace wiski {
 int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
                 cudaStream_t st, int64_t nblk = 1, bool symmetric = false);
 int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st,
-                      int64_t nblk = 1, int terms = 3);
+                      int64_t nblk = 1, int terms = 3, float* work = nullptr);
+int64_t tc_rmul_work_elems(int64_t r, int64_t r2);
 int64_t tc_gram_work_elems(int64_t m, int64_t r, int64_t r2);
 
 // ------------------------------------------------------------------ Out[M x N] = P[M x K] @ Mm[K x N]
@@ -780,10 +781,12 @@ int wiski_gram_sym_f32(const float* A, const float* Bm, int64_t m, int64_t r, fl
     if (rc != 3) return rc;
     return wiski::gram<float>(A, Bm, m, r, r, G, work, stream);
 }
+int64_t wiski_panel_rmul_ex_work_elems(int64_t r, int64_t r2) { return wiski::tc_rmul_work_elems(r, r2); }
 int wiski_panel_rmul_ex_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, int64_t nblk, int terms,
-                            float* Out, void* stream) {
-    WISKI_CHECK_ARG(nblk >= 1 && r2 % nblk == 0 && (terms == 1 || terms == 3), "panel_rmul_ex: bad nblk / terms");
-    int rc = wiski::tc_panel_rmul_f32(P, m, r, M, r2, Out, wiski::as_stream(stream), nblk, terms);
+                            float* Out, float* work, void* stream) {
+    WISKI_CHECK_ARG(nblk >= 1 && r2 % nblk == 0 && terms >= 1 && terms <= 3, "panel_rmul_ex: bad nblk / terms");
+    WISKI_CHECK_ARG(terms != 2 || work != nullptr, "panel_rmul_ex: terms = 2 needs the scratch buffer");
+    int rc = wiski::tc_panel_rmul_f32(P, m, r, M, r2, Out, wiski::as_stream(stream), nblk, terms, work);
     if (rc != 3) return rc;
     if (nblk == 1) return wiski::panel_rmul<float>(P, m, r, M, r2, Out, stream);
     wiski::set_error("panel_rmul_ex: shape m=%lld r=%lld r2=%lld nblk=%lld not supported by the tensor-core path",

@@ -23,9 +23,17 @@ class OnlineSKIRegression(torch.nn.Module):
 
     REPLAY_BATCH = 1024        # replay minibatch for BatchNorm statistics; also the chunk size of evaluate()
 
-    def __init__(self, stem, init_x, init_y, lr, grid_size, grid_bound, covar_module=None, **kwargs):
+    def __init__(self, stem, init_x, init_y, lr, grid_size, grid_bound, covar_module=None, comm=None, **kwargs):
+        """``comm`` (an ``online_gp_b200.parallel.Comm`` over a torch.distributed group, an addition to the reference
+        signature): with more than one rank the inducing-grid rows are sharded across the ranks' GPUs and this object
+        drives the row-sharded engine (``parallel.ShardedOnlineSKIRegression``: Identity stem, one output) through the
+        same ``evaluate / update / predict / set_lr / noise`` calls — one class for N = 1 and N > 1."""
         super().__init__()
         assert init_y.ndim == 2, "targets must have explicit output dimension"
+        self._engine = None
+        if comm is not None and getattr(comm, "world", 1) > 1:
+            self._init_sharded(stem, init_x, init_y, lr, grid_size, grid_bound, covar_module, comm)
+            return
         n_out = init_y.size(-1)
         self.stem = stem.to(init_x.device)
         half_width = grid_bound + 1e-1                     # the grid reaches a little beyond the stated feature range
@@ -43,6 +51,22 @@ class OnlineSKIRegression(torch.nn.Module):
         self._target_batch_shape = [] if n_out == 1 else torch.Size([n_out])
         self._raw_inputs = [init_x]
         self._graphs = None          # opt-in CUDA-graph replay of evaluate() / update(): enable_cuda_graphs()
+
+    # ------------------------------------------------------------------ row-sharded engine (N > 1)
+    def _init_sharded(self, stem, init_x, init_y, lr, grid_size, grid_bound, covar_module, comm):
+        from ..parallel import ShardedOnlineSKIRegression
+        if any(p.requires_grad for p in stem.parameters() if isinstance(p, torch.nn.Parameter)) or init_y.size(-1) != 1:
+            raise NotImplementedError("the row-sharded engine serves an Identity stem and one output (SURVEY §8e)")
+        self.stem = stem
+        self.target_dim = 1
+        self._graphs = None
+        self._engine = ShardedOnlineSKIRegression(init_x, init_y, lr, grid_size, grid_bound, comm=comm, covar_module=covar_module)
+        self.gp = self._engine            # covar_module, likelihood, num_data, panels (L_loc / B_loc) live on the engine
+
+    @property
+    def engine(self):
+        """The row-sharded engine when this model was built with ``comm=`` over more than one rank, else None."""
+        return self._engine
 
     def _new_optimizers(self, gp_lr, stem_lr):
         self.gp_optimizer = torch.optim.Adam(self.gp.parameters(), lr=gp_lr)
@@ -62,6 +86,8 @@ class OnlineSKIRegression(torch.nn.Module):
 
     def predict(self, inputs):
         """(mean, variance incl. the learned noise), each [q, target_dim]."""
+        if self._engine is not None:
+            return self._engine.predict(inputs.view(-1, self.stem.input_dim))
         self.eval()
         dist = self(inputs)
         var = self._columns(dist.variance)
@@ -79,6 +105,8 @@ class OnlineSKIRegression(torch.nn.Module):
         ``update`` differentiates (``online_ski_regression.py:64-78``)."""
         inputs = inputs.view(-1, self.stem.input_dim)
         targets = targets.view(-1, self.target_dim)
+        if self._engine is not None:
+            return self._engine.evaluate(inputs, targets)
         if self._graph_usable(inputs):
             return self._evaluate_graphed(inputs, targets)
         self._graph_phase(None)
@@ -96,6 +124,8 @@ class OnlineSKIRegression(torch.nn.Module):
     def fit(self, inputs, targets, num_epochs, test_dataset=None):
         """``num_epochs`` joint Adam steps on stem + GP hyper-parameters with cosine-annealed rates; the WISKI caches
         are rebuilt from the current features after every step (``:80-111``).  Returns one record per epoch."""
+        if self._engine is not None:
+            raise NotImplementedError("fit() is not available on the row-sharded engine")
         self._graph_phase(None)
         optimizers = (self.stem_optimizer, self.gp_optimizer)
         schedules = [CosineAnnealingLR(opt, num_epochs, 1e-4) for opt in optimizers]
@@ -125,6 +155,8 @@ class OnlineSKIRegression(torch.nn.Module):
         the Woodbury MLL, then the new batch is conditioned on in place.  Returns (stem_loss, gp_loss)."""
         inputs = inputs.view(-1, self.stem.input_dim)
         targets = targets.view(-1, self.target_dim)
+        if self._engine is not None:
+            return self._engine.update(inputs, targets)
         if update_gp and self._graph_usable(inputs) and self._graphs.phase == "evaluated":
             return self._update_graphed(inputs, targets)
         self._graph_phase(None)
@@ -193,6 +225,11 @@ class OnlineSKIRegression(torch.nn.Module):
         self.gp.set_train_data(inputs, targets, torch.ones_like(targets))
 
     def set_lr(self, gp_lr, stem_lr=None, bn_mom=None):
+        if self._engine is not None:
+            if self._engine._graphs is not None:
+                self._engine.enable_cuda_graphs(True, warmup_calls=self._engine._graphs.warm0)
+            self._engine.gp_optimizer = torch.optim.Adam(self._engine.parameters(), lr=gp_lr)
+            return
         if self._graphs is not None:
             self.enable_cuda_graphs(True, warmup_calls=self._graphs.warm0)     # captured graphs hold the old optimiser
         self._new_optimizers(gp_lr, gp_lr if stem_lr is None else stem_lr)
@@ -203,6 +240,8 @@ class OnlineSKIRegression(torch.nn.Module):
 
     @property
     def noise(self):
+        if self._engine is not None:
+            return self._engine._noise().reshape(1)
         return self.gp.likelihood.noise
 
     # ------------------------------------------------------------------ CUDA-graph replay (online_gp_b200/graphs.py)
@@ -211,6 +250,9 @@ class OnlineSKIRegression(torch.nn.Module):
         evaluate/update pairs still run eagerly (library handles, lazy module loading), the next pair is captured,
         later pairs replay.  Calls that do not fit the captured form (different batch size, trainable stem,
         ``update()`` without a preceding ``evaluate()``) run eagerly on the same state."""
+        if self._engine is not None:
+            self._engine.enable_cuda_graphs(enabled, warmup_calls)
+            return self
         self._graphs = StepGraphs(warmup_calls) if enabled else None
         return self
 
@@ -291,4 +333,6 @@ class OnlineSKIRegression(torch.nn.Module):
     @property
     def graph_launches(self):
         """Kernels of this library executed through graph replays so far (bench.py adds them to gpu_launches)."""
+        if self._engine is not None:
+            return self._engine.graph_launches
         return 0 if self._graphs is None else self._graphs.launches

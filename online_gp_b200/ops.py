@@ -535,6 +535,12 @@ def kron_axis_contract(Z, P, g, outer, inner, acc64):
 
 
 # ---------------------------------------------------------------------------------------------- panels
+def _rmul_work(r, r2, terms, device):
+    if terms != 2:
+        return None
+    return torch.empty(int(_lib.load().wiski_panel_rmul_ex_work_elems(r, r2)), dtype=torch.float32, device=device)
+
+
 def _rmul(P, M, terms=3):
     """terms: tcgen05 passes of the fp32 tensor-core path (3 = 3xTF32 split, fp32-grade; 1 = single tf32 pass,
     gradient quantities only — settings.backward_gemm_tf32_passes)."""
@@ -543,8 +549,9 @@ def _rmul(P, M, terms=3):
     m, r = P.shape
     r2 = M.shape[1]
     out = torch.empty(m, r2, dtype=P.dtype, device=P.device)
-    if terms == 1 and P.dtype == torch.float32:
-        _call_fn("wiski_panel_rmul", _lib.load().wiski_panel_rmul_ex_f32, _ptr(P), m, r, _ptr(M), r2, 1, 1, _ptr(out), _stream())
+    if terms in (1, 2) and P.dtype == torch.float32:
+        _call_fn("wiski_panel_rmul", _lib.load().wiski_panel_rmul_ex_f32, _ptr(P), m, r, _ptr(M), r2, 1, int(terms), _ptr(out),
+                 _ptr(_rmul_work(r, r2, terms, P.device)), _stream())
         return out
     _call("wiski_panel_rmul", P.dtype, _ptr(P), m, r, _ptr(M), r2, _ptr(out), _stream())
     return out
@@ -601,7 +608,8 @@ def rmul_blocks(P, M, nb, out=None, terms=3):
     if P.dtype == torch.float32 and cwb % 32 == 0:
         P, M = P.contiguous(), M.contiguous()
         Out = torch.empty(nb, m, cwb, dtype=P.dtype, device=P.device) if out is None else out
-        rc = _lib.load().wiski_panel_rmul_ex_f32(_ptr(P), m, r, _ptr(M), r2, nb, int(terms), _ptr(Out), _stream())
+        rc = _lib.load().wiski_panel_rmul_ex_f32(_ptr(P), m, r, _ptr(M), r2, nb, int(terms), _ptr(Out),
+                                                 _ptr(_rmul_work(r, r2, terms, P.device)), _stream())
         if rc == 0:
             return Out
         if rc != 3:

@@ -174,12 +174,14 @@ class kron_directional_grad(_feature_flag):
 
 
 class backward_gemm_tf32_passes(_value_context):
-    """tcgen05 passes of the fp32 panel GEMMs that produce *gradient* quantities (``Z = L grad_Q`` in the backward of
-    ``Q = I + L^T K L``, ``online_gp/models/online_ski_regression.py:141``): 1 = one kind::tf32 product of the raw fp32
-    operands (the tensor core truncates them: ~1e-3 relative, mostly a uniform scale of the gradient, which Adam
-    normalises away), 3 = the 3xTF32 split every *value* GEMM uses.  fp32 hyper-gradients stay within the 1e-2 bar
-    either way (asserted in tests/model_cases.py); fp64 is unaffected (SIMT kernels)."""
-    _global_value = 1
+    """tcgen05 passes of the fp32 panel GEMM that produces the *gradient* panel ``Z = L grad_Q`` in the backward of
+    ``Q = I + L^T K L`` (``online_gp/models/online_ski_regression.py:141``).  3 = the 3xTF32 split every value GEMM uses.
+    2 (default) = grad_Q exact (big + remainder stacked along K), the panel L truncated to tf32 by the tensor core: L's
+    truncation error is independent from grid row to grid row and averages out of the sums over ~1e6 rows the
+    hyper-gradient consists of (a 500-step stream follows the fp64 oracle like the 3-pass form), whereas an error in
+    grad_Q would be shared by every row.  1 = one raw tf32 pass: 0.1 % gradient error that lets the Adam trajectory
+    drift by ~0.5 % over 200 steps (measured, tools/diag_drift.py) — opt-in only.  fp64 is unaffected (SIMT)."""
+    _global_value = 2
 
 
 class kron_outer_inner_pairing(_feature_flag):

@@ -292,11 +292,18 @@ def test_regression_wrapper_stream_matches_oracle_loop():
         assert torch.allclose(ls, hyp.lengthscale.detach(), rtol=1e-6)
 
 
-@pytest.mark.parametrize("d,g,n0,steps", [(2, 48, 128, 500), (2, 32, 128, 300)])
-def test_long_fp32_stream_does_not_drift_from_fp64_oracle(d, g, n0, steps):
+@pytest.mark.parametrize("d,g,n0,steps,stream", [(2, 48, 128, 500, "sites"), (2, 32, 128, 300, "fresh")])
+def test_long_fp32_stream_does_not_drift_from_fp64_oracle(d, g, n0, steps, stream):
     """Hundreds of in-place fp32 root updates + Adam steps (BASELINE config 2 runs 8 182 of them): the streamed
     (rmse, nll), the learned noise and B^T L = I stay within the fp32 bar of the fp64 oracle run on the same stream.
-    (2, 48): tcgen05 Gram / panel GEMMs (m = 2304, r = 128); (2, 32): the tcgen05 Kronecker pair kernels."""
+    (2, 48): tcgen05 Gram / panel GEMMs (m = 2304, r = 128); (2, 32): the tcgen05 Kronecker pair kernels.
+
+    stream "sites": the streamed inputs revisit the initial sites (repeated noisy measurements), so every new stencil
+    vector lies in span(L) and the frozen-rank root update (updated_root_lazy_tensor.py:76-100) loses nothing: the model
+    keeps learning for all 500 steps and fp32 rounding is the only difference from the oracle.  stream "fresh": new
+    uniformly random inputs; their out-of-span part is dropped from the root but kept in W^T y, which makes the
+    reference's own algorithm ill-conditioned as the learned noise shrinks (the fp64 oracle's rmse reaches the
+    hundreds after ~250 steps at this size), so that stream is compared for the 300 steps before that regime."""
     if _dev() == "cpu":
         pytest.skip("long stream: GPU only")
     M = _mods()
@@ -310,6 +317,8 @@ def test_long_fp32_stream_does_not_drift_from_fp64_oracle(d, g, n0, steps):
     side = int(round(n0 ** 0.5)) + 1
     lat = torch.stack(torch.meshgrid(*[torch.linspace(-0.9, 0.9, side, dtype=torch.float64)] * d, indexing="ij"), -1).reshape(-1, d)
     X[:n0] = lat[:n0] + 0.01 * (torch.rand(n0, d, generator=gen, dtype=torch.float64) - 0.5)
+    if stream == "sites":
+        X[n0:] = X[torch.randint(0, n0, (steps,), generator=gen)]
     y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen, dtype=torch.float64)).unsqueeze(-1)
     torch.set_default_dtype(torch.float32)
     try:
@@ -340,7 +349,7 @@ def test_long_fp32_stream_does_not_drift_from_fp64_oracle(d, g, n0, steps):
                     rmse_o = float((mo - yt[:, 0]).pow(2).mean().sqrt())
                     nll_o = float(-torch.distributions.Normal(mo, var_o.sqrt()).log_prob(yt[:, 0]).mean())
                 opt.zero_grad()
-                (-orc.mll(pieces=pieces)).backward()
+                (-orc.mll(pieces=pieces, skip_logdet_forward=True)).backward()
                 opt.step()
                 with torch.no_grad():
                     orc.condition_on_observations(xt, yt[:, 0], torch.ones(1, dtype=torch.float64))

@@ -217,15 +217,24 @@ def _fused_worker(rank, world, port, ret, directional=True):
             S.kron_directional_grad(directional):
         saved = _install_fused_emulation(ops, parallel, g)
         try:
-            model = parallel.ShardedOnlineSKIRegression(X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0,
-                                                        comm=parallel.Comm())
+            if directional:
+                # through the public class: OnlineSKIRegression(..., comm=) drives the row-sharded engine
+                from online_gp_b200.models import OnlineSKIRegression
+                from online_gp_b200.models.stems import Identity
+                front = OnlineSKIRegression(Identity(d), X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0,
+                                            comm=parallel.Comm())
+                model = front.engine
+                assert isinstance(model, parallel.ShardedOnlineSKIRegression) and front.gp is model
+            else:
+                front = model = parallel.ShardedOnlineSKIRegression(X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0,
+                                                                    comm=parallel.Comm())
             assert parallel._fused_ok(model.plan, model.L_loc)
             for t in range(steps):
                 xt, yt = X[n0 + t:n0 + t + 1], y[n0 + t:n0 + t + 1]
-                rmse, nll = model.evaluate(xt, yt)
+                rmse, nll = front.evaluate(xt, yt)
                 P = model.pieces()
                 assert P["KL"].shape == (world, model.plan.m_loc, model.L_loc.shape[1] // world)     # column blocks
-                _, loss = model.update(xt, yt)
+                _, loss = front.update(xt, yt)
                 out.append((rmse, nll, loss, float(model._noise())))
         finally:
             ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok, ops._fused_pair_grad_dir = saved

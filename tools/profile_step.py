@@ -6,10 +6,10 @@ from torch.profiler import profile, ProfilerActivity
 import bench
 
 args = type("A", (), {})()
-d, g, q, n_init, _ = bench.WORKLOADS["powerplant_4d_g32"]
+d, g, q, n_init, _lr, _ = bench.WORKLOADS["powerplant_4d_g32"]
 dev = torch.device("cuda:0")
 from online_gp_b200 import settings as S
-model, xs, ys = bench.build_model(d, g, n_init, torch.float32, dev)
+model, xs, ys = bench.build_model(d, g, n_init, _lr, torch.float32, dev)
 xd, yd = xs.to(dev), ys.to(dev)
 with S.max_root_decomposition_size(512), S.max_cholesky_size(2048), S.cg_tolerance(1e-2):
     for t in range(4):
