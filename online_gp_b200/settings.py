@@ -175,13 +175,14 @@ class kron_directional_grad(_feature_flag):
 
 class backward_gemm_tf32_passes(_value_context):
     """tcgen05 passes of the fp32 panel GEMM that produces the *gradient* panel ``Z = L grad_Q`` in the backward of
-    ``Q = I + L^T K L`` (``online_gp/models/online_ski_regression.py:141``).  3 = the 3xTF32 split every value GEMM uses.
-    2 (default) = grad_Q exact (big + remainder stacked along K), the panel L truncated to tf32 by the tensor core: L's
-    truncation error is independent from grid row to grid row and averages out of the sums over ~1e6 rows the
-    hyper-gradient consists of (a 500-step stream follows the fp64 oracle like the 3-pass form), whereas an error in
-    grad_Q would be shared by every row.  1 = one raw tf32 pass: 0.1 % gradient error that lets the Adam trajectory
-    drift by ~0.5 % over 200 steps (measured, tools/diag_drift.py) — opt-in only.  fp64 is unaffected (SIMT)."""
-    _global_value = 2
+    ``Q = I + L^T K L`` (``online_gp/models/online_ski_regression.py:141``).  3 (default) = the 3xTF32 split every value
+    GEMM uses; a 500-step stream then follows the fp64 oracle within 1e-2 (tests/model_cases.py).  2 = grad_Q exact (big
+    + remainder stacked along K), the panel L cut to tf32 by the tensor core; 1 = one raw tf32 pass.  Both cheaper forms
+    are opt-in only: the tensor core TRUNCATES its fp32 inputs, so the gradient carries a one-sided ~5e-4 bias and the
+    Adam trajectory walks away from the oracle (noise 8 % off after 500 steps with 2 passes, first step outside the
+    1e-2 band at 177 / 145 with 2 / 1 passes; tools/diag_drift.py, B200).  On C2 the 2-pass form is not even faster
+    (2.27 ms vs 2.09 ms: its 128-byte K slabs halve the bytes in flight per pipeline stage).  fp64 is unaffected."""
+    _global_value = 3
 
 
 class kron_outer_inner_pairing(_feature_flag):

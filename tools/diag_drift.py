@@ -23,7 +23,7 @@ def run(d, g, n0, steps, tag, **kw):
         X[n0:] = X[torch.randint(0, n0, (steps,), generator=gen)]
     y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen, dtype=torch.float64)).unsqueeze(-1)
     torch.set_default_dtype(torch.float32)
-    ctxs = [S.backward_gemm_tf32_passes(kw.get("passes", 2)), S.kron_directional_grad(kw.get("directional", True))]
+    ctxs = [S.backward_gemm_tf32_passes(kw.get("passes", 3)), S.kron_directional_grad(kw.get("directional", True))]
     for c in ctxs: c.__enter__()
     orig_gram = ops._gram
     if kw.get("nosym"):
@@ -72,10 +72,10 @@ def run(d, g, n0, steps, tag, **kw):
 
 if __name__ == "__main__":
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 80
-    run(2, 48, 128, steps, "sites passes2 (default)", sites=True)
-    run(2, 48, 128, steps, "sites passes1", sites=True, passes=1)
-    run(2, 48, 128, steps, "fresh passes2 (default)")
-    run(2, 48, 128, steps, "fresh passes3", passes=3)
+    run(2, 48, 128, steps, "sites passes3 (default)", sites=True)
+    run(2, 48, 128, steps, "sites passes2", sites=True, passes=2)
+    run(2, 48, 128, steps, "fresh passes3 (default)")
+    run(2, 48, 128, steps, "fresh passes2", passes=2)
     if steps <= 100:
         run(2, 48, 128, steps, "nosym", nosym=True)
         run(2, 40, 128, steps, "g40 (SIMT gemm)")
