@@ -166,6 +166,27 @@ int wiski_kron_pair_grad_dir_axes_f32(const float* cols, const float* dirs, int 
                                       int axis_u, int axis_v, const float* Z, const float* P, float* Zout, int64_t c,
                                       double* out3, const int64_t* h_lay, void* stream);
 
+/* ---- row-sharded multi-GPU path: compute + layout exchange in ONE kernel over NVLink peer memory.
+ * The reference has no multi-device path (SURVEY.md §8 row e); the sharded model keeps the panels row-sharded along
+ * grid axis 0 and needs all rows of a column block for the axis pair that contains axis 0.  Instead of an all-to-all
+ * pass between the kernels, the producing kernel's own stores go to the consumers' buffers: dst[j] is a device pointer
+ * into rank j's peer-mapped receive buffer (torch.distributed._symmetric_memory / cudaIpc), at the place where THIS
+ * rank's part starts.  Callers order producer and consumer with a device-side barrier over all ranks.
+ *   mode 1 (row slab -> column blocks): X [m_loc, c]; column block j (c / n_dst columns) -> dst[j], a [m_loc, c / n_dst] panel
+ *   mode 2 (column block -> row slabs): X [m, c], axis_u = 0; rows of axis-0 range j -> dst[j], a [m / n_dst, c] panel
+ * Tensor-core kernels only (status 3 when the shape is not theirs: 32-point axes, c % 16 == 0, n_dst <= 8).
+ * h_lay_x / h_lay_zp: (ld, cw, cstride) of the inputs (X; Z then P) or NULL for plain row-major panels. */
+int wiski_kron_pair_apply_push_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int axis_u, int axis_v,
+                                   const float* X, int64_t c, const int64_t* h_lay_x, float* const* dst, int n_dst, int mode,
+                                   void* stream);
+int wiski_kron_pair_grad_dir_push_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,
+                                      int axis_u, int axis_v, const float* Z, const float* P, int64_t c, double* out3,
+                                      const int64_t* h_lay_zp, float* const* dst, int n_dst, void* stream);
+/* Out = P @ M with column block j written at dst[j] (mode 1 of the above for the panel GEMM); work: the scratch of
+ * wiski_panel_rmul_ex_f32 (terms = 2 only, else NULL). */
+int wiski_panel_rmul_push_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, int terms, float* const* dst,
+                              int n_dst, float* work, void* stream);
+
 /* ---- k7: panel right-multiply  Out = P @ M,  P,Out [m,r], M [r,r2], Out [m,r2]  (Out must not alias P)
  * (replaces current_root.matmul(inner_root) / current_inv_root^T.matmul(inner_inv_root),
  * updated_root_lazy_tensor.py:97-100,115-117, and Kuu_Lmat @ qmat_solve, batched_fixed_noise_online_gp.py:376). */

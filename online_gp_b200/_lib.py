@@ -45,7 +45,8 @@ EXPORTED = ["wiski_last_error", "wiski_abi_version", "wiski_launch_count", "wisk
             "wiski_kron_fused_pair_grad_lay_f32", "wiski_gram_chunked_f32", "wiski_panel_rmul_chunked_f32",
             "wiski_kron_fused_pair_grad_dir_lay_f32", "wiski_kron_tc_enable", "wiski_gram_sym_f32",
             "wiski_panel_rmul_ex_f32", "wiski_gram_chunked_sym_f32",
-            "wiski_kron_pair_apply_axes_f32", "wiski_kron_pair_grad_dir_axes_f32", "wiski_panel_rmul_ex_work_elems"] + [
+            "wiski_kron_pair_apply_axes_f32", "wiski_kron_pair_grad_dir_axes_f32", "wiski_panel_rmul_ex_work_elems",
+            "wiski_kron_pair_apply_push_f32", "wiski_kron_pair_grad_dir_push_f32", "wiski_panel_rmul_push_f32"] + [
     f"{n}_{sfx}" for n in _sigs(c_float, POINTER(c_float)) for sfx in ("f32", "f64")]
 
 
@@ -84,6 +85,14 @@ def load():
     lib.wiski_kron_pair_apply_axes_f32.argtypes = [_P, c_int, _I64P, c_int64, c_int, c_int, _P, _P, c_int64, _I64P, _S]
     lib.wiski_kron_pair_grad_dir_axes_f32.restype = c_int
     lib.wiski_kron_pair_grad_dir_axes_f32.argtypes = [_P, _P, c_int, _I64P, c_int64, c_int, c_int, _P, _P, _P, c_int64, _P, _I64P, _S]
+    _PP = POINTER(c_void_p)
+    lib.wiski_kron_pair_apply_push_f32.restype = c_int
+    lib.wiski_kron_pair_apply_push_f32.argtypes = [_P, c_int, _I64P, c_int64, c_int, c_int, _P, c_int64, _I64P, _PP, c_int, c_int, _S]
+    lib.wiski_kron_pair_grad_dir_push_f32.restype = c_int
+    lib.wiski_kron_pair_grad_dir_push_f32.argtypes = [_P, _P, c_int, _I64P, c_int64, c_int, c_int, _P, _P, c_int64, _P, _I64P, _PP,
+                                                      c_int, _S]
+    lib.wiski_panel_rmul_push_f32.restype = c_int
+    lib.wiski_panel_rmul_push_f32.argtypes = [_P, c_int64, c_int64, _P, c_int64, c_int, _PP, c_int, _P, _S]
     lib.wiski_gram_chunked_sym_f32.restype = c_int
     lib.wiski_gram_chunked_sym_f32.argtypes = [_P, _P, c_int64, c_int64, c_int64, _P, _P, _S]
     lib.wiski_gram_sym_f32.restype = c_int

@@ -38,6 +38,21 @@ void count_launches(int n);   // kernels enqueued by this library (bench.py repo
 
 constexpr int kNumSMs = 148;  // B200
 
+// Destinations of a launch that pushes its result into the peers' (NVLink-mapped) buffers; see kron_tc.cu (PushMaps)
+// and gemm_tc.cu (o_ptrs).  dst[j] = where this rank's part starts in rank j's buffer.
+struct PushDst {
+    float* const* dst;
+    int n_dst;
+    int mode;      // 1: column block j -> rank j;  2: axis-0 range j of the rows -> rank j
+};
+
+// kron_tc.cu: two Kronecker axes per pass on the tensor pipe (tcgen05 / TMEM / TMA); return 3 for shapes they do not take
+int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gmax, int au, int av, const float* X, float* Y,
+                       int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof, const PushDst* push = nullptr);
+int tc_pair_grad_dir_axes(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int au, int av,
+                          const float* Z, const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st,
+                          const int64_t* h_lay, const PushDst* push = nullptr);
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // round-to-nearest, never contracted into FMA: used where the reference's op order must be reproduced exactly

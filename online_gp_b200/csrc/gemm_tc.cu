@@ -138,6 +138,9 @@ struct Batching {
     // a_kwrap > 0: the K coordinate of A wraps after a_kwrap k-blocks while B keeps advancing:  A [B_0 ; B_1] = A B_0 + A B_1
     //   (panel GEMM with only the small operand split: B_0 = M, B_1 = M - tf32(M), see tc_panel_rmul_f32 terms = 2)
     int a_kwrap;
+    // o_ptrs[0] != NULL (with o_cw > 0): column block j of the result is written at o_ptrs[j] (row-major, pitch ld_out)
+    // instead of out + j * o_cstride: the blocks go straight into the peers' NVLink-mapped buffers (PushDst mode 1)
+    float* o_ptrs[8];
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -379,7 +382,7 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 int64_t ncol0 = n0 + c0;                 // column of this 32-wide group inside its block
                 if (bt.o_cw > 0) {
                     const int64_t blk = ncol0 / bt.o_cw;
-                    obase += blk * bt.o_cstride;
+                    obase = bt.o_ptrs[0] != nullptr ? bt.o_ptrs[blk] : obase + blk * bt.o_cstride;
                     ncol0 -= blk * bt.o_cw;
                 }
                 uint32_t v[32];
@@ -583,10 +586,11 @@ int64_t tc_rmul_work_elems(int64_t r, int64_t r2) { return 2 * ceil_div(r, 32) *
 // panel's truncation error is independent from row to row, so it averages out of every sum over grid rows taken
 // downstream (the hyper-parameter gradient), while an error in M would be shared by all rows.
 int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st,
-                      int64_t nblk, int terms, float* work) {
+                      int64_t nblk, int terms, float* work, const PushDst* push) {
     if (!tc_shape_ok(m, r, r2)) return 3;
     if (terms == 2 && work == nullptr) terms = 3;
     if (nblk > 1 && (r2 % nblk != 0 || (r2 / nblk) % 32 != 0)) return 3;
+    if (push != nullptr && (push->mode != 1 || push->n_dst != nblk || nblk < 2 || nblk > 8)) return 3;
     CUtensorMap tmA, tmB;
     int ntiles;
     int bn = pick_bn(r2, &ntiles);
@@ -594,6 +598,10 @@ int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int6
     bt.terms = terms == 3 ? 3 : 1;
     int64_t ld_out = r2;
     if (nblk > 1) { bt.o_cw = r2 / nblk; bt.o_cstride = m * (r2 / nblk); ld_out = r2 / nblk; }
+    if (push != nullptr) {
+        for (int j = 0; j < push->n_dst; ++j) bt.o_ptrs[j] = push->dst[j];
+        Out = push->dst[0];
+    }
     if (terms == 1 || terms == 2) {
         constexpr int BK1 = 32, ST1 = 4;                                    // 4 x (16 KB + bn * 128 B) <= 176 KB
         if (int rc = make_map(&tmA, P, m, r, 128, false, BK1)) return rc;

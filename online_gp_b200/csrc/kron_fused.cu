@@ -25,11 +25,6 @@ int tc_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, in
                   int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof);
 int tc_pair_grad_dir(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,
                      const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st, const int64_t* h_lay);
-int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gmax, int au, int av, const float* X, float* Y,
-                       int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof);
-int tc_pair_grad_dir_axes(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int au, int av,
-                          const float* Z, const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st,
-                          const int64_t* h_lay);
 
 // tensor-core pair kernels on (default) / off (SIMT kernels of this file): env WISKI_KRON_TC=0 or wiski_kron_tc_enable(0)
 static int g_use_tc = -1;
@@ -671,6 +666,49 @@ int wiski_kron_pair_grad_dir_axes_f32(const float* cols, const float* dirs, int 
                                           h_lay);
     wiski::set_error("kron_pair_grad_dir_axes: axes (%d, %d) need the tensor-core path", axis_u, axis_v);
     return 3;
+}
+
+/* Pushing variants for the row-sharded multi-GPU path (tensor-core kernels only; 3 = shape not supported): the result
+ * leaves through TMA stores into the peers' NVLink-mapped buffers, dst[j] = where this rank's part starts on rank j.
+ *   mode 1: X is a row slab [m_loc, c]; column block j (c / n_dst columns) goes to dst[j], a [m_loc, c / n_dst] panel
+ *   mode 2: X is a column block [m, c] (all rows), axis_u = 0; the rows of axis-0 range j go to dst[j], a [m / n_dst, c] panel
+ * h_lay_x: (ld, cw, cstride) of X or NULL (plain). */
+int wiski_kron_pair_apply_push_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int axis_u, int axis_v,
+                                   const float* X, int64_t c, const int64_t* h_lay_x, float* const* dst, int n_dst, int mode,
+                                   void* stream) {
+    if (d < 2 || d > WISKI_MAX_DIMS || axis_u < 0 || axis_v <= axis_u || axis_v >= d || dst == nullptr || n_dst < 1 || n_dst > 8) {
+        wiski::set_error("kron_pair_apply_push: bad axes / destinations");
+        return 1;
+    }
+    int64_t lay[6] = {c, c, 0, c, c, 0};
+    if (h_lay_x != nullptr) { lay[0] = h_lay_x[0]; lay[1] = h_lay_x[1]; lay[2] = h_lay_x[2]; }
+    const wiski::PushDst pd{dst, n_dst, mode};
+    const int rc = wiski::tc_pair_apply_axes(cols, d, h_g, gmax, axis_u, axis_v, X, nullptr, c, wiski::as_stream(stream), lay,
+                                             nullptr, &pd);
+    if (rc == 3) wiski::set_error("kron_pair_apply_push: axes (%d, %d), c=%lld, n_dst=%d, mode %d not supported", axis_u, axis_v,
+                                  (long long)c, n_dst, mode);
+    return rc;
+}
+
+/* Directional backward pair pass whose Zout = T_v T_u Z is pushed (mode 2: axis_u = 0, rows of axis-0 range j -> dst[j]).
+ * h_lay_zp: (ld, cw, cstride) of Z then of P, or NULL (both plain [m, c]). */
+int wiski_kron_pair_grad_dir_push_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,
+                                      int axis_u, int axis_v, const float* Z, const float* P, int64_t c, double* out3,
+                                      const int64_t* h_lay_zp, float* const* dst, int n_dst, void* stream) {
+    if (d < 2 || d > WISKI_MAX_DIMS || axis_u < 0 || axis_v <= axis_u || axis_v >= d || dirs == nullptr || dst == nullptr ||
+        n_dst < 1 || n_dst > 8) {
+        wiski::set_error("kron_pair_grad_dir_push: bad axes / operands");
+        return 1;
+    }
+    int64_t lay[9] = {c, c, 0, c, c, 0, c, c, 0};
+    if (h_lay_zp != nullptr)
+        for (int i = 0; i < 6; ++i) lay[i] = h_lay_zp[i];
+    const wiski::PushDst pd{dst, n_dst, 2};
+    const int rc = wiski::tc_pair_grad_dir_axes(cols, dirs, d, h_g, gmax, axis_u, axis_v, Z, P, nullptr, c, out3,
+                                                wiski::as_stream(stream), lay, &pd);
+    if (rc == 3) wiski::set_error("kron_pair_grad_dir_push: axes (%d, %d), c=%lld, n_dst=%d not supported", axis_u, axis_v,
+                                  (long long)c, n_dst);
+    return rc;
 }
 
 int wiski_kron_fused_pair_grad_dir_lay_f32(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax,

@@ -26,6 +26,7 @@
 //   warps 4-11  workers: two groups of 4 warps (one TMEM lane quadrant each); group g owns MMA tiles g and g + 2
 // TMEM: 4 slots (group x tile) of 128 columns: A raw [0,32) | A remainder [32,64) | D [64,128).
 #include <stdlib.h>
+#include <string.h>
 #include "tc_ptx.cuh"
 
 namespace wiski {
@@ -58,6 +59,22 @@ struct Geom {
 // where element (row, col) of a panel lives: ptr + (col / cw) * cstride + row * ld + col % cw
 struct Lay {
     long long ld, cw, cstride;
+};
+
+// Pushing results into the peers' memory (row-sharded multi-GPU path): instead of ONE output tensor map the kernel gets
+// one per destination rank, each over that rank's peer-mapped receive buffer (NVLink / NVSwitch), so the layout change
+// between the row-sharded and the column-sharded panel happens in the producing kernel's own TMA stores:
+//   mode 1  column block j of the tile's columns belongs to rank j      (row slab -> all rows of my columns)
+//   mode 2  the tile's axis-u range splits into n_dst equal parts, part i belongs to rank i (u = grid axis 0:
+//           column-sharded panel -> my rows of every column block); box_u = axis-u extent of one store
+constexpr int MAXP = 8;
+struct PushMaps {
+    CUtensorMap m[MAXP];
+};
+struct Push {
+    int mode;            // 0 = off
+    int box_u;           // mode 2: axis-u lines per store (<= 8 for the gradient pass, = u_loc for the apply pass)
+    int u_loc;           // mode 2: axis-u lines per destination rank (32 / n_dst)
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -167,12 +184,15 @@ struct ApplyParams {
     const float* col_u;      // 32 floats each
     const float* col_v;
     long long* prof;         // PROF instantiation only: 13 counters
+    Push push;
 };
 
 // PROF: accumulate clock64() deltas of the roles' phases into p.prof (test_kron_tc prof); compiled out otherwise
 #define KTC_TICK(slot) do { if (PROF) { const long long now_ = clock64(); pr[slot] += now_ - tl; tl = now_; } } while (0)
 template <int NST, bool PROF>
-__global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, const ApplyParams p) {
+__global__ void __launch_bounds__(NTHREADS, 1)
+pair_apply_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                     const __grid_constant__ PushMaps pm, const ApplyParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer stays derived from the __shared__ array: LDS / STS
     uint8_t* timg = smem;                                                   // v big | v small | u big | u small
@@ -352,7 +372,15 @@ __global__ void __launch_bounds__(NTHREADS, 1) pair_apply_tc_kernel(const __grid
                     fence_proxy_async_smem();
                     named_bar_sync(4 + grp, 128);
                     if (store_thread) {
-                        tma_store_box(&tmY, ybuf + j * STAGE_F, tile_coords(g, c0y, blk, f0, f1, 0, 8 * j));
+                        if (p.push.mode == 0) {
+                            tma_store_box(&tmY, ybuf + j * STAGE_F, tile_coords(g, c0y, blk, f0, f1, 0, 8 * j));
+                        } else if (p.push.mode == 1) {
+                            tma_store_box(&pm.m[blk], ybuf + j * STAGE_F, tile_coords(g, c0y, 0, f0, f1, 0, 8 * j));
+                        } else {                                           // [32 u][8 v][16 w]: u_loc lines per rank
+                            const Coords kc = tile_coords(g, c0y, 0, f0, f1, 0, 8 * j);
+                            for (int i = 0; i * p.push.u_loc < G; ++i)
+                                tma_store_box(&pm.m[i], ybuf + j * STAGE_F + i * p.push.u_loc * (8 * CB), kc);
+                        }
                         tma_store_commit();
                     }
                 }
@@ -391,12 +419,13 @@ struct GradParams {
     const float* dir_u;
     const float* dir_v;
     double* out3;
+    Push push;
 };
 
 template <bool STORE, int NST>
 __global__ void __launch_bounds__(NTHREADS, 1)
 pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_constant__ CUtensorMap tmZv,
-                        const __grid_constant__ CUtensorMap tmO, const GradParams p) {
+                        const __grid_constant__ CUtensorMap tmO, const __grid_constant__ PushMaps pm, const GradParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer stays derived from the __shared__ array: LDS / STS
     // images: [T_v ; T'_v] big (64 rows, 8 KB) | the same, remainder | [T_u ; T'_u] big | remainder
@@ -619,7 +648,15 @@ pair_grad_dir_tc_kernel(const __grid_constant__ CUtensorMap tmPu, const __grid_c
                         fence_proxy_async_smem();
                         named_bar_sync(4 + grp, 128);
                         if (store_thread) {
-                            tma_store_box(&tmO, sbuf + j * STAGE_F, tile_coords(g, c0o, blko, f0, f1, 8 * j, 0));
+                            if (p.push.mode == 0) {
+                                tma_store_box(&tmO, sbuf + j * STAGE_F, tile_coords(g, c0o, blko, f0, f1, 8 * j, 0));
+                            } else {                                       // [8 u][32 v][16 w] in pieces of box_u lines
+                                for (int q = 0; q * p.push.box_u < 8; ++q) {
+                                    const int u = 8 * j + q * p.push.box_u, rk = u / p.push.u_loc;
+                                    tma_store_box(&pm.m[rk], sbuf + j * STAGE_F + q * p.push.box_u * (G * CB),
+                                                  tile_coords(g, c0o, 0, f0, f1, u - rk * p.push.u_loc, 0));
+                                }
+                            }
                             tma_store_commit();
                         }
                     }
@@ -758,25 +795,62 @@ static bool use_direct_store(const Geom& g, const Lay& l) {
     return g.sv * l.ld * 4 >= (1ll << 19);
 }
 
+// Destination maps of a pushing launch (see PushMaps).  dst[j] = where this rank's part starts in rank j's buffer:
+//   mode 1: a [rows, c / n_dst] panel (ld = c / n_dst) holding MY rows of rank j's column block
+//   mode 2: a [rows / n_dst, c] panel (ld = c) holding rank j's axis-0 lines of MY columns
+static int fill_push(PushMaps& pm, Push& push, const Geom& g, const MapDims& md, const PushDst& pd, int64_t c, int box_v,
+                     bool grad) {
+    memset(&pm, 0, sizeof(pm));
+    push.mode = pd.mode;
+    push.box_u = push.u_loc = G;
+    if (pd.n_dst < 1 || pd.n_dst > MAXP || pd.dst == nullptr) return 3;
+    if (pd.mode == 1) {
+        if (c % ((int64_t)pd.n_dst * CB) != 0) return 3;
+        const int64_t cw = c / pd.n_dst;
+        for (int j = 0; j < pd.n_dst; ++j)
+            if (int rc = make_map5(&pm.m[j], pd.dst[j], g, md, Lay{cw, cw, 0}, cw, box_v, grad ? 8 : G)) return rc;
+        return 0;
+    }
+    if (pd.mode != 2 || g.pos_u != g.pos_blk || G % pd.n_dst != 0) return 3;     // u must be the slowest grid axis
+    push.u_loc = G / pd.n_dst;
+    push.box_u = grad ? (push.u_loc < 8 ? push.u_loc : 8) : push.u_loc;
+    MapDims md2 = md;
+    md2.ext[g.pos_u - 1] = push.u_loc;
+    for (int j = 0; j < pd.n_dst; ++j)
+        if (int rc = make_map5(&pm.m[j], pd.dst[j], g, md2, Lay{c, c, 0}, c, box_v, push.box_u)) return rc;
+    return 0;
+}
+
 }  // namespace ktc
 
 // Y = (T_au x T_av) X on the tensor pipe for any two 32-point grid axes au < av (the other axes act as batch indices).
 // Returns 3 when the shape / layout is not supported.
+// push != NULL: Y is ignored, the result goes to the peers' buffers (ktc::PushMaps).
 int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gmax, int au, int av, const float* X, float* Y,
-                       int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof) {
+                       int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof, const PushDst* push) {
     using namespace ktc;
     Geom g;
     MapDims md;
     if (!make_geom(g, md, d, h_g, au, av, c)) return 3;
-    const Lay lx = lay_of(h_lay, 0, c), ly = lay_of(h_lay, 1, c);
+    const Lay lx = lay_of(h_lay, 0, c);
+    Lay ly = lay_of(h_lay, 1, c);
     CUtensorMap tmX, tmY;
-    if (int rc = make_map5(&tmX, X, g, md, lx, c, G, 8)) return rc;
-    if (int rc = make_map5(&tmY, Y, g, md, ly, c, 8, G)) return rc;
+    PushMaps pm;
     ApplyParams p;
+    p.push = Push{0, G, G};
+    if (int rc = make_map5(&tmX, X, g, md, lx, c, G, 8)) return rc;
+    if (push != nullptr) {
+        if (int rc = fill_push(pm, p.push, g, md, *push, c, 8, false)) return rc;
+        tmY = tmX;
+        ly = push->mode == 1 ? Lay{c / push->n_dst, c / push->n_dst, 0} : Lay{c, c, 0};
+    } else {
+        memset(&pm, 0, sizeof(pm));
+        if (int rc = make_map5(&tmY, Y, g, md, ly, c, 8, G)) return rc;
+    }
     p.cwx = (int)lx.cw;
     p.cwy = (int)ly.cw;
     p.ly = ly;
-    p.Ydirect = use_direct_store(g, ly) ? Y : nullptr;
+    p.Ydirect = (push == nullptr && use_direct_store(g, ly)) ? Y : nullptr;
     p.g = g;
     p.col_u = cols + (int64_t)au * gmax;
     p.col_v = cols + (int64_t)av * gmax;
@@ -785,7 +859,7 @@ int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gma
     auto kfn = prof != nullptr ? pair_apply_tc_kernel<kApplyStages, true> : pair_apply_tc_kernel<kApplyStages, false>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_tc(attr)");
     const long long grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
-    kfn<<<(unsigned)grid, NTHREADS, smem, st>>>(tmX, tmY, p);
+    kfn<<<(unsigned)grid, NTHREADS, smem, st>>>(tmX, tmY, pm, p);
     WISKI_CHECK_LAUNCH("kron_tc(pair_apply)");
     count_launches(1);
     return 0;
@@ -793,29 +867,41 @@ int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gma
 
 int tc_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X, float* Y,
                   int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof) {
-    return tc_pair_apply_axes(cols, d, h_g, gmax, 2 * pair, 2 * pair + 1, X, Y, c, st, h_lay, prof);
+    return tc_pair_apply_axes(cols, d, h_g, gmax, 2 * pair, 2 * pair + 1, X, Y, c, st, h_lay, prof, nullptr);
 }
 
 // Directional backward pair pass on the tensor pipe for the axes au < av; out3 (3 doubles, accumulated):
 // <grad_au, dirs_au>, <grad_av, dirs_av>, <Z', K' P'>.  Zout may be NULL.
 int tc_pair_grad_dir_axes(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int au, int av,
                           const float* Z, const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st,
-                          const int64_t* h_lay) {
+                          const int64_t* h_lay, const PushDst* push) {
     using namespace ktc;
     Geom g;
     MapDims md;
     if (!make_geom(g, md, d, h_g, au, av, c)) return 3;
-    const Lay lz = lay_of(h_lay, 0, c), lp = lay_of(h_lay, 1, c), lo = lay_of(h_lay, 2, c);
+    const Lay lz = lay_of(h_lay, 0, c), lp = lay_of(h_lay, 1, c);
+    Lay lo = lay_of(h_lay, 2, c);
     CUtensorMap tmPu, tmZv, tmO;
+    PushMaps pm;
+    GradParams p;
+    p.push = Push{0, G, G};
+    memset(&pm, 0, sizeof(pm));
     if (int rc = make_map5(&tmPu, P, g, md, lp, c, G, 8)) return rc;
     if (int rc = make_map5(&tmZv, Z, g, md, lz, c, 8, G)) return rc;
-    if (int rc = make_map5(&tmO, Zout != nullptr ? Zout : P, g, md, Zout != nullptr ? lo : lp, c, G, 8)) return rc;
-    GradParams p;
+    if (push != nullptr) {                       // Zout (T_v T_u Z) goes to the peers' buffers, split along axis u
+        if (push->mode != 2) return 3;
+        if (int rc = fill_push(pm, p.push, g, md, *push, c, G, true)) return rc;
+        tmO = tmPu;
+        lo = Lay{c, c, 0};
+        Zout = const_cast<float*>(P);            // (only its non-NULL-ness is used below: the STORE instantiation)
+    } else if (int rc = make_map5(&tmO, Zout != nullptr ? Zout : P, g, md, Zout != nullptr ? lo : lp, c, G, 8)) {
+        return rc;
+    }
     p.cwz = (int)lz.cw;
     p.cwp = (int)lp.cw;
     p.cwo = (int)lo.cw;
     p.lo = lo;
-    p.Odirect = (Zout != nullptr && use_direct_store(g, lo)) ? Zout : nullptr;
+    p.Odirect = (push == nullptr && Zout != nullptr && use_direct_store(g, lo)) ? Zout : nullptr;
     p.g = g;
     p.col_u = cols + (int64_t)au * gmax;
     p.col_v = cols + (int64_t)av * gmax;
@@ -827,11 +913,11 @@ int tc_pair_grad_dir_axes(const float* cols, const float* dirs, int d, const int
     if (Zout != nullptr) {
         auto kfn = pair_grad_dir_tc_kernel<true, kGradStages>;
         WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_tc(attr)");
-        kfn<<<(unsigned)grid, NTHREADS, smem, st>>>(tmPu, tmZv, tmO, p);
+        kfn<<<(unsigned)grid, NTHREADS, smem, st>>>(tmPu, tmZv, tmO, pm, p);
     } else {
         auto kfn = pair_grad_dir_tc_kernel<false, kGradStages>;
         WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_tc(attr)");
-        kfn<<<(unsigned)grid, NTHREADS, smem, st>>>(tmPu, tmZv, tmO, p);
+        kfn<<<(unsigned)grid, NTHREADS, smem, st>>>(tmPu, tmZv, tmO, pm, p);
     }
     WISKI_CHECK_LAUNCH("kron_tc(pair_grad_dir)");
     count_launches(1);
@@ -840,7 +926,7 @@ int tc_pair_grad_dir_axes(const float* cols, const float* dirs, int d, const int
 
 int tc_pair_grad_dir(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int pair, const float* Z,
                      const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st, const int64_t* h_lay) {
-    return tc_pair_grad_dir_axes(cols, dirs, d, h_g, gmax, 2 * pair, 2 * pair + 1, Z, P, Zout, c, out3, st, h_lay);
+    return tc_pair_grad_dir_axes(cols, dirs, d, h_g, gmax, 2 * pair, 2 * pair + 1, Z, P, Zout, c, out3, st, h_lay, nullptr);
 }
 
 }  // namespace wiski

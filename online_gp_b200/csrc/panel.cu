@@ -12,7 +12,7 @@ namespace wiski {
 int tc_gram_f32(const float* A, const float* Bm, int64_t m, int64_t r, int64_t r2, float* G, float* work,
                 cudaStream_t st, int64_t nblk = 1, bool symmetric = false);
 int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, float* Out, cudaStream_t st,
-                      int64_t nblk = 1, int terms = 3, float* work = nullptr);
+                      int64_t nblk = 1, int terms = 3, float* work = nullptr, const PushDst* push = nullptr);
 int64_t tc_rmul_work_elems(int64_t r, int64_t r2);
 int64_t tc_gram_work_elems(int64_t m, int64_t r, int64_t r2);
 
@@ -824,6 +824,21 @@ int wiski_panel_rmul_chunked_f32(const float* P, int64_t m, int64_t r, const flo
     if (rc != 3) return rc;
     wiski::set_error("panel_rmul_chunked: shape m=%lld r=%lld r2=%lld nblk=%lld not supported by the tensor-core path",
                      (long long)m, (long long)r, (long long)r2, (long long)nblk);
+    return 3;
+}
+/* The same product with column block j written at dst[j] (row-major [m, r2 / n_dst]): dst[j] points into rank j's
+ * NVLink-mapped receive buffer, so the row -> column layout change of the sharded backward happens in the GEMM's own
+ * epilogue stores (no separate all-to-all pass). */
+int wiski_panel_rmul_push_f32(const float* P, int64_t m, int64_t r, const float* M, int64_t r2, int terms, float* const* dst,
+                              int n_dst, float* work, void* stream) {
+    WISKI_CHECK_ARG(dst != nullptr && n_dst >= 2 && n_dst <= 8 && r2 % n_dst == 0 && terms >= 1 && terms <= 3,
+                    "panel_rmul_push: bad destinations / terms");
+    for (int j = 0; j < n_dst; ++j) WISKI_CHECK_ARG(dst[j] != nullptr, "panel_rmul_push: NULL destination %d", j);
+    const wiski::PushDst pd{dst, n_dst, 1};
+    int rc = wiski::tc_panel_rmul_f32(P, m, r, M, r2, nullptr, wiski::as_stream(stream), n_dst, terms, work, &pd);
+    if (rc != 3) return rc;
+    wiski::set_error("panel_rmul_push: shape m=%lld r=%lld r2=%lld n_dst=%d not supported by the tensor-core path",
+                     (long long)m, (long long)r, (long long)r2, n_dst);
     return 3;
 }
 int64_t wiski_qmv_work_elems(int64_t m, int64_t r, int64_t c) { return wiski::qmv_blocks(m) * r * c; }

@@ -8,7 +8,7 @@
 
 namespace wiski {
 int tc_gram_f32(const float*, const float*, int64_t, int64_t, int64_t, float*, float*, cudaStream_t, int64_t nblk = 1, bool symmetric = false);
-int tc_panel_rmul_f32(const float*, int64_t, int64_t, const float*, int64_t, float*, cudaStream_t, int64_t nblk = 1, int terms = 3, float* work = nullptr);
+int tc_panel_rmul_f32(const float*, int64_t, int64_t, const float*, int64_t, float*, cudaStream_t, int64_t nblk = 1, int terms = 3, float* work = nullptr, const PushDst* push = nullptr);
 int64_t tc_gram_work_elems(int64_t, int64_t, int64_t);
 int tc_panel_rmul_nt_f32(const float*, int64_t, int64_t, const float*, int64_t, float*, cudaStream_t);
 }

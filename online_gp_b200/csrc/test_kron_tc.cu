@@ -11,11 +11,6 @@
 #include "common.cuh"
 
 namespace wiski {
-int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gmax, int au, int av, const float* X, float* Y,
-                       int64_t c, cudaStream_t st, const int64_t* h_lay, long long* prof);
-int tc_pair_grad_dir_axes(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int au, int av,
-                          const float* Z, const float* P, float* Zout, int64_t c, double* out3, cudaStream_t st,
-                          const int64_t* h_lay);
 int fused_pair_apply(const float* cols, int d, const int64_t* h_g, int64_t gmax, int pair, const float* X, float* Y,
                      int64_t c, cudaStream_t st, const int64_t* h_lay);
 int fused_pair_grad_jvp(const float* cols, const float* dirs, int d, const int64_t* h_g, int64_t gmax, int pair,

@@ -383,6 +383,40 @@ def _fused_pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store, chunk_z=1, 
     return Zout
 
 
+# ---- pushing variants (row-sharded multi-GPU path): the result leaves through the kernel's own stores into the peers'
+# NVLink-mapped buffers; `dst` = ctypes table of device pointers (one per rank, parallel._PushBuffers.dst)
+def _fused_pair_apply_push(cols, sizes, pair, X, dst, n_dst, mode):
+    """(T_u x T_v) X pushed to the peers.  mode 1: X is a row slab [m_loc, c], column block j -> rank j (a [m_loc, c / n_dst]
+    panel at dst[j]); mode 2: X holds all rows of a column block, axis_u = 0, rows of axis-0 range j -> rank j."""
+    d, gmax = cols.shape
+    m, c = X.shape
+    h_g = (c_int64 * d)(*sizes)
+    au, av = _pair_axes(pair)
+    _call_fn("wiski_kron_fused_pair_apply", _lib.load().wiski_kron_pair_apply_push_f32, _ptr(cols), d, h_g, gmax, au, av,
+             _ptr(X), c, None, dst, int(n_dst), int(mode), _stream())
+
+
+def _fused_pair_grad_dir_push(cols, dirs, sizes, pair, Z, P, out3, dst, n_dst):
+    """Directional backward pair pass on plain [m, c] operands (axis_u = 0) whose Zout = T_v T_u Z is pushed to the peers:
+    rows of axis-0 range j -> rank j (a [m / n_dst, c] panel at dst[j])."""
+    d, gmax = cols.shape
+    m, c = P.shape
+    h_g = (c_int64 * d)(*sizes)
+    au, av = _pair_axes(pair)
+    _call_fn("wiski_kron_fused_pair_grad", _lib.load().wiski_kron_pair_grad_dir_push_f32, _ptr(cols), _ptr(dirs), d, h_g, gmax,
+             au, av, _ptr(Z), _ptr(P), c, _ptr(out3), None, dst, int(n_dst), _stream())
+
+
+def rmul_push(P, M, dst, n_dst, terms=3):
+    """P M with column block j (r2 / n_dst columns) written at dst[j] (a [m, r2 / n_dst] panel on rank j); no autograd."""
+    _require_cuda(P, M)
+    P, M = P.contiguous(), M.contiguous()
+    m, r = P.shape
+    r2 = M.shape[1]
+    _call_fn("wiski_panel_rmul", _lib.load().wiski_panel_rmul_push_f32, _ptr(P), m, r, _ptr(M), r2, int(terms), dst, int(n_dst),
+             _ptr(_rmul_work(r, r2, terms, P.device)), _stream())
+
+
 def _by_axis(out, pairs, d):
     """out [npairs, 3] (per pair: axis_u, axis_v, scale) -> the d directional sums ordered by grid axis."""
     order = [0] * d

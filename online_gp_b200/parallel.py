@@ -28,6 +28,7 @@ from two captured CUDA graphs.
 Mirrors, for one output and an Identity stem, ``OnlineSKIRegression.evaluate`` / ``.update``
 (``online_gp/models/online_ski_regression.py:64-78,113-146``) on top of the same kernels as the single-GPU path.
 """
+import ctypes
 import math
 import os
 import warnings
@@ -43,6 +44,46 @@ from .likelihoods import FNMGLikelihood
 
 
 # ---------------------------------------------------------------------------------------------- communication
+class _PushBuffers:
+    """Four peer-mapped regions (A..D, `numel` elements each) of one symmetric allocation per rank: the receive buffers
+    of the kernels that push their result straight into the consumers' memory over NVLink (``ops.*_push``).
+
+    Use in one streaming step (W ranks, rank p, panel [m_loc, c], cw = c / W, part = m_loc * cw elements):
+      A  (T_a x T_b) L        pushed by the slab-local pair pass      -> all rows of my columns   [W m_loc, cw]
+      B  K L                  pushed by the column-sharded pair pass  -> my rows of every block   [W, m_loc, cw]
+      C  L grad_Q             pushed by the panel GEMM's epilogue      -> all rows of my columns
+      D  (T_0 x T_v) Z        pushed by the column-sharded grad pass   -> my rows of every block
+    Rank p always writes part p of a region on rank j.  Every push is followed by ``barrier()`` (all ranks' producers
+    have finished) before the region is read; a region is rewritten one step later, with at least one barrier after
+    its last reader on every rank (A, C: read by the pass that pushes D; B: by the Gram / prediction ops that precede the
+    push of C; D: by the last pair pass, followed by next step's barrier after A)."""
+
+    REGIONS = ("A", "B", "C", "D")
+
+    def __init__(self, buf, hdl, peers, numel, rank, world):
+        self.buf, self.hdl, self.peers = buf, hdl, peers
+        self.numel, self.rank, self.world = numel, rank, world
+        self._tables = {}
+        self.c_pushed = False        # region C holds the pushed gradient panel of the Gram backward (consumed once)
+
+    def local(self, name, numel=None):
+        k = self.REGIONS.index(name)
+        return self.buf[k * self.numel:k * self.numel + (self.numel if numel is None else numel)]
+
+    def dst(self, name, part):
+        """ctypes table: for every rank j the device address of part `rank` (part elements) of region `name` on rank j."""
+        key = (name, part)
+        if key not in self._tables:
+            k = self.REGIONS.index(name)
+            isz = self.buf.element_size()
+            self._tables[key] = (ctypes.c_void_p * self.world)(
+                *[pv.data_ptr() + (k * self.numel + self.rank * part) * isz for pv in self.peers])
+        return self._tables[key]
+
+    def barrier(self):
+        self.hdl.barrier(0)
+
+
 class Comm:
     """Thin wrapper over a torch.distributed process group (None => single process, every collective a no-op)."""
 
@@ -53,6 +94,49 @@ class Comm:
         self.rank = dist.get_rank(group) if self.enabled else 0
         self._a2a_ok = self.enabled and dist.get_backend(group) != "gloo"
         self.xbuf = self._xhdl = self._xpeers = self._xstreams = None      # peer-memory exchange (enable_peer_exchange)
+        self.push = None                                                    # _PushBuffers (enable_push)
+
+    def enable_push(self, numel, dtype, device):
+        """Collective.  Sets up the peer-mapped receive regions of the pushing kernels (``_PushBuffers``); returns them,
+        or None when peer memory is unavailable or WISKI_PUSH_EXCHANGE=0 (then the exchanges run as separate passes)."""
+        self.push = None
+        if (self.world == 1 or self.world > 8 or not self._a2a_ok or dtype != torch.float32
+                or os.environ.get("WISKI_PUSH_EXCHANGE", "1") == "0"):
+            return None
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            gname = group.group_name
+            try:
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    symm.enable_symm_mem_for_group(gname)
+            except Exception:                       # noqa: BLE001 - newer torch enables groups implicitly
+                pass
+            buf = symm.empty(4 * numel, dtype=dtype, device=device)
+            hdl = symm.rendezvous(buf, gname)
+            peers = [hdl.get_buffer(p, (4 * numel,), dtype) for p in range(self.world)]
+            if any(pv.device != buf.device for pv in peers):
+                ok = 0
+        except Exception as err:                    # noqa: BLE001
+            warnings.warn(f"peer-memory push unavailable ({type(err).__name__}: {err})")
+            ok = 0
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return None
+        buf.zero_()
+        self.push = _PushBuffers(buf, hdl, peers, numel, self.rank, self.world)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=self.group)
+        return self.push
+
+    def push_buffers(self, numel, like):
+        pb = self.push
+        if pb is None or pb.buf.dtype != like.dtype or pb.numel != numel:
+            return None
+        return pb
 
     def allreduce_(self, t):
         if self.world > 1:
@@ -250,6 +334,18 @@ class _ShardedKronFn(torch.autograd.Function):
             ctx.col_pair, ctx.loc_pair = ops.kron_pairs(plan.sizes, directional=ctx.dirs is not None)
             slab = [plan.g0_loc] + plan.sizes[1:]
             cw = X.shape[1] // W
+            pb = comm.push_buffers(X.numel(), X) if (ctx.dirs is not None and W > 1) else None
+            ctx.pushed = pb is not None
+            if pb is not None:
+                # compute + exchange in one kernel each: the pair passes store into the peers' regions A / B
+                part = plan.m_loc * cw
+                ops._fused_pair_apply_push(cols, slab, ctx.loc_pair, X.contiguous(), pb.dst("A", part), W, 1)
+                pb.barrier()
+                X23c = pb.local("A").view(W * plan.m_loc, cw)                          # all rows of my columns
+                ops._fused_pair_apply_push(cols, plan.sizes, ctx.col_pair, X23c, pb.dst("B", part), W, 2)
+                pb.barrier()
+                ctx.save_for_backward(cols, X, X23c)
+                return pb.local("B").view(W, plan.m_loc, cw)                            # my rows of every column block
             xb = comm.send_buffer(W * plan.m_loc * cw, X)            # symmetric (peer-mapped) send buffer or None
             X23s = ops._fused_pair_apply(cols, slab, ctx.loc_pair, X.contiguous(), chunk_out=W,
                                          out=None if xb is None else xb.view(W, plan.m_loc, cw))   # send layout
@@ -274,6 +370,25 @@ class _ShardedKronFn(torch.autograd.Function):
             acc = torch.zeros(d, gmax, dtype=torch.float64, device=X.device)
             slab = [plan.g0_loc] + plan.sizes[1:]
             cw = X.shape[1] // W
+            if ctx.pushed:
+                pb = comm.push
+                part = plan.m_loc * cw
+                Cl = pb.local("C")
+                if pb.c_pushed and gYb.data_ptr() == Cl.data_ptr():
+                    pb.c_pushed = False                  # the Gram backward's GEMM already stored Z = L grad_Q on the owners
+                else:
+                    if pb.c_pushed:
+                        raise RuntimeError("sharded Kronecker backward: the pushed gradient panel was replaced upstream")
+                    Cl.view(W, plan.m_loc, cw).copy_(comm.all_to_all(gYb.contiguous()))
+                Zc = Cl.view(W * plan.m_loc, cw)
+                out = torch.zeros(2, 3, dtype=torch.float64, device=X.device)
+                ops._fused_pair_grad_dir_push(cols, ctx.dirs, plan.sizes, ctx.col_pair, Zc, X23c, out[0], pb.dst("D", part), W)
+                pb.barrier()
+                ops._fused_pair_grad_dir(cols, ctx.dirs, slab, ctx.loc_pair, pb.local("D").view(W, plan.m_loc, cw), X, out[1],
+                                         store=False, chunk_z=W)
+                comm.allreduce_(out)
+                gcols = ops._surrogate_col_grad(cols, ctx.dirs, ops._by_axis(out, [ctx.col_pair, ctx.loc_pair], plan.d), out[-1, 2])
+                return gcols, None, None, None, None
             xb = comm.send_buffer(W * plan.m_loc * cw, X)
             if xb is not None and gYb.untyped_storage().data_ptr() != xb.untyped_storage().data_ptr():
                 gYb = xb.view(W, plan.m_loc, cw).copy_(gYb)         # (the Gram backward normally writes it there itself)
@@ -338,6 +453,14 @@ class _ShardedGramBlocksFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gG):
         (A,) = ctx.saved_tensors
+        pb = ctx.comm.push_buffers(A.shape[0] * gG.shape[1], A) if (ctx.nb > 1 and ctx.nb == ctx.comm.world) else None
+        if pb is not None and settings.kron_directional_grad.on():
+            # Z = L grad_Q, column block j stored on rank j by the GEMM's epilogue (region C); what comes back is the
+            # column-sharded panel the Kronecker backward needs, already in place
+            ops.rmul_push(A, gG.contiguous(), pb.dst("C", A.shape[0] * ctx.cwb), ctx.nb, terms=ops._bwd_terms())
+            pb.barrier()
+            pb.c_pushed = True
+            return None, pb.local("C").view(ctx.nb, A.shape[0], ctx.cwb), None
         xb = ctx.comm.send_buffer(A.shape[0] * gG.shape[1], A) if ctx.nb > 1 else None
         out = None if xb is None else xb.view(ctx.nb, A.shape[0], ctx.cwb)
         return None, ops.rmul_blocks(A, gG.contiguous(), ctx.nb, out=out, terms=ops._bwd_terms()), None
@@ -466,7 +589,10 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             self.Lc = self._rows_to_cols(self.L_loc)           # [m, r / world]: all rows of my columns
         self._pieces = None
         if self.comm.world > 1 and init_x.is_cuda and _fused_ok(self.plan, self.L_loc):
-            self.comm.enable_peer_exchange(self.L_loc.numel(), self.dtype, init_x.device)
+            pushing = (not self._dual and settings.kron_directional_grad.on()
+                       and self.comm.enable_push(self.L_loc.numel(), self.dtype, init_x.device) is not None)
+            if not pushing:
+                self.comm.enable_peer_exchange(self.L_loc.numel(), self.dtype, init_x.device)
         self._graphs = None          # opt-in CUDA-graph replay: enable_cuda_graphs()
         self._n_t = None             # device-side copy of num_data (graph mode)
 
@@ -493,8 +619,9 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         keep = lam > tol * lam.max()
         lam, U = lam[keep].flip(0), U[:, keep].flip(1)
         r_eff = lam.numel()
-        # multiple of 16 x ranks: 16-column tiles must exist in the column-sharded layout of the fused kernels too
-        mult = 16 * comm.world
+        # multiple of 32 x ranks: the column-sharded layout of the fused kernels needs whole 16-column tiles per rank, the
+        # chunked tensor-core panel GEMM whole 32-column groups (1 rank: 16, as the single-GPU model)
+        mult = 16 if comm.world == 1 else 32 * comm.world
         r = ((r_eff + mult - 1) // mult) * mult
         Upad = torch.zeros(n1, r, dtype=self.dtype, device=X.device)
         Upad[:, :r_eff] = U

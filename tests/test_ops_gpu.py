@@ -313,6 +313,59 @@ def test_tensor_core_pair_kernels_match_simt():
     assert torch.allclose(g1, g0, rtol=2e-4, atol=2e-4 * float(g0.abs().max()))
 
 
+@pytest.mark.parametrize("W", [2, 4, 8])
+def test_pushing_kernels_write_the_exchange_layout(W):
+    """The compute + exchange kernels of the row-sharded path (``ops.*_push``), with every "peer" region in local memory:
+    what lands at dst[j] must be exactly block j of the plain kernel's result — column block j (mode 1: slab-local pair
+    pass and the panel GEMM) or the rows of axis-0 range j (mode 2: the pair passes that contain grid axis 0)."""
+    import ctypes
+    ops = _ops()
+    gen = torch.Generator().manual_seed(13 + W)
+    ell = torch.tensor([0.5, 0.8, 0.6, 0.7])
+    grid = torch.linspace(-1.17, 1.17, 32)
+    rr = (grid - grid[0]).abs().unsqueeze(0) / ell.unsqueeze(-1)
+    cols = (torch.exp(-0.5 * rr * rr) * 0.8).to(DEV)
+    dirs = (torch.exp(-0.5 * rr * rr) * rr * rr / ell.unsqueeze(-1)).to(DEV)
+    g0 = 32 // W
+    slab, full = [g0, 32, 32, 32], [32, 32, 32, 32]
+    m_loc, m = g0 * 32 ** 3, 32 ** 4
+    c = 32 * W                       # panel columns; cw = 32 per rank
+    cw = c // W
+
+    def table(buf):                  # buf [W, ...] contiguous: one destination per leading index
+        return (ctypes.c_void_p * W)(*[buf[j].data_ptr() for j in range(W)])
+
+    # mode 1: slab-local pair (1, 2) on a row slab [m_loc, c]
+    X = (torch.randn(m_loc, c, generator=gen) / 10).to(DEV)
+    want = ops._fused_pair_apply(cols, slab, (1, 2), X)
+    got = torch.full((W, m_loc, cw), float("nan"), device=DEV)
+    ops._fused_pair_apply_push(cols, slab, (1, 2), X, table(got), W, 1)
+    for j in range(W):
+        assert torch.equal(got[j], want[:, j * cw:(j + 1) * cw]), j
+    # mode 1, panel GEMM: Z = P M, column block j at dst[j]
+    M = torch.randn(c, c, generator=gen).to(DEV)
+    wantz = ops._rmul(X, M, terms=3)
+    gotz = torch.full((W, m_loc, cw), float("nan"), device=DEV)
+    ops.rmul_push(X, M, table(gotz), W, terms=3)
+    for j in range(W):
+        assert torch.equal(gotz[j], wantz[:, j * cw:(j + 1) * cw]), j
+    del X, want, got, wantz, gotz
+    # mode 2: pair (0, 3) on a column block [m, cw]: rows of axis-0 range j at dst[j]
+    Xc = (torch.randn(m, cw, generator=gen) / 10).to(DEV)
+    Zc = (torch.randn(m, cw, generator=gen) / 10).to(DEV)
+    want = ops._fused_pair_apply(cols, full, (0, 3), Xc)
+    got = torch.full((W, m_loc, cw), float("nan"), device=DEV)
+    ops._fused_pair_apply_push(cols, full, (0, 3), Xc, table(got), W, 2)
+    assert torch.equal(got.view(m, cw), want)
+    o_want = torch.zeros(3, dtype=torch.float64, device=DEV)
+    o_got = torch.zeros(3, dtype=torch.float64, device=DEV)
+    wantz = ops._fused_pair_grad_dir(cols, dirs, full, (0, 3), Zc, Xc, o_want, store=True)
+    gotz = torch.full((W, m_loc, cw), float("nan"), device=DEV)
+    ops._fused_pair_grad_dir_push(cols, dirs, full, (0, 3), Zc, Xc, o_got, table(gotz), W)
+    assert torch.equal(gotz.view(m, cw), wantz)
+    assert torch.allclose(o_got, o_want, rtol=1e-6, atol=0.0)
+
+
 def test_kron_directional_backward_matches_full_gradient():
     """32^4 fused path: the surrogate column gradient of the directional backward has the same inner products with
     dirs[i] and cols[i] as the full column gradient (which is all lengthscale / scale parameters see)."""

@@ -26,7 +26,7 @@ CASES = [
     # (world, extra args): 32^4 fp32 (fused tensor-core pair kernels + chunked layouts) and a generic 3-D grid in fp64
     (2, ["--n0", "48", "--steps", "5", "--graphs"]),
     (2, ["--n0", "48", "--steps", "5", "--graphs", "--dual"]),
-    (2, ["--d", "3", "--g", "16", "--n0", "40", "--steps", "4", "--dtype", "f64"]),
+    (2, ["--dims", "3", "--grid", "16", "--n0", "40", "--steps", "4", "--dtype", "f64"]),
     (2, ["--n0", "40", "--steps", "3", "--q", "3"]),
     (4, ["--n0", "48", "--steps", "5", "--graphs"]),
     (4, ["--n0", "48", "--steps", "4", "--graphs", "--dual"]),

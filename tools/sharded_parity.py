@@ -1,7 +1,7 @@
 """Row-sharded path on real GPUs vs the single-GPU path (run under torchrun, one rank per GPU, NCCL):
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
-      tools/sharded_parity.py [--d 4 --g 32 --n0 48 --steps 4 --q 1]
+      tools/sharded_parity.py [--dims 4 --grid 32 --n0 48 --steps 4 --q 1]
 
 Every rank streams the same synthetic points through ``ShardedOnlineSKIRegression``; rank 0 also runs the same
 stream through the single-GPU ``OnlineSKIRegression`` and compares RMSE / NLL / loss / hyper-parameters step by
@@ -20,8 +20,8 @@ import torch.distributed as dist
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--d", type=int, default=4)
-    ap.add_argument("--g", type=int, default=32)
+    ap.add_argument("--dims", dest="d", type=int, default=4)
+    ap.add_argument("--grid", dest="g", type=int, default=32)
     ap.add_argument("--n0", type=int, default=48)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--q", type=int, default=1)
