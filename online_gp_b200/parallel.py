@@ -438,6 +438,51 @@ class _ShardedKronFn(torch.autograd.Function):
         return acc.to(cols.dtype), None, None, None, None
 
 
+class _DualKronPushFn(torch.autograd.Function):
+    """K L for the dual-layout model with the pushing kernels: L is also kept column-sharded (Lc [m, cw]: all rows of my
+    columns), so both pair passes run on local data and only the LAST one's stores cross NVLink — into region B of every
+    peer, which receives its rows of my column block.  Returns the column blocks [W, m_loc, cw] (region B).
+    Backward: the Gram backward's panel GEMM has already stored Z = L grad_Q column-sharded in region C; both directional
+    pair passes then run locally.  Two NVLink-bound kernels and two barriers per step instead of four and four."""
+
+    @staticmethod
+    def forward(ctx, cols, Lc, plan, comm, dirs):
+        cols = cols.contiguous()
+        ctx.plan, ctx.comm = plan, comm
+        ctx.dirs = dirs.detach().to(cols.dtype).contiguous()
+        W = plan.world
+        cw = Lc.shape[1]
+        pb = comm.push
+        ctx.col_pair, ctx.loc_pair = ops.kron_pairs(plan.sizes, directional=True)
+        X12 = ops._fused_pair_apply(cols, plan.sizes, ctx.loc_pair, Lc)
+        ops._fused_pair_apply_push(cols, plan.sizes, ctx.col_pair, X12, pb.dst("B", plan.m_loc * cw), W, 2)
+        pb.barrier()
+        ctx.save_for_backward(cols, Lc, X12)
+        return pb.local("B").view(W, plan.m_loc, cw)
+
+    @staticmethod
+    def backward(ctx, gYb):
+        plan, comm = ctx.plan, ctx.comm
+        W = plan.world
+        cols, Lc, X12 = ctx.saved_tensors
+        cw = Lc.shape[1]
+        pb = comm.push
+        Cl = pb.local("C")
+        if pb.c_pushed and gYb.data_ptr() == Cl.data_ptr():
+            pb.c_pushed = False
+        else:
+            if pb.c_pushed:
+                raise RuntimeError("sharded Kronecker backward: the pushed gradient panel was replaced upstream")
+            Cl.view(W, plan.m_loc, cw).copy_(comm.all_to_all(gYb.contiguous()))
+        Zc = Cl.view(W * plan.m_loc, cw)
+        out = torch.zeros(2, 3, dtype=torch.float64, device=Lc.device)
+        Z03 = ops._fused_pair_grad_dir(cols, ctx.dirs, plan.sizes, ctx.col_pair, Zc, X12, out[0], store=True)
+        ops._fused_pair_grad_dir(cols, ctx.dirs, plan.sizes, ctx.loc_pair, Z03, Lc, out[1], store=False)
+        comm.allreduce_(out)
+        gcols = ops._surrogate_col_grad(cols, ctx.dirs, ops._by_axis(out, [ctx.col_pair, ctx.loc_pair], plan.d), out[-1, 2])
+        return gcols, None, None, None, None
+
+
 class _ShardedGramBlocksFn(torch.autograd.Function):
     """A_loc^T [B_0 | B_1 | ...] summed over ranks for column blocks Bb [nb, m_loc, cwb] (replicated r x (nb cwb)
     result); gradient w.r.t. the sharded blocks only, returned in the same block layout."""
@@ -589,7 +634,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             self.Lc = self._rows_to_cols(self.L_loc)           # [m, r / world]: all rows of my columns
         self._pieces = None
         if self.comm.world > 1 and init_x.is_cuda and _fused_ok(self.plan, self.L_loc):
-            pushing = (not self._dual and settings.kron_directional_grad.on()
+            pushing = (settings.kron_directional_grad.on()
                        and self.comm.enable_push(self.L_loc.numel(), self.dtype, init_x.device) is not None)
             if not pushing:
                 self.comm.enable_peer_exchange(self.L_loc.numel(), self.dtype, init_x.device)
@@ -681,7 +726,9 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         cols = cols * scale                                                       # Kuu / sigma^2 (:340)
         dirs = self.covar_module.base_kernel.grid_column_dirs(self.covar_module.grid) \
             if settings.kron_directional_grad.on() else None
-        if self.Lc is not None:
+        if self.Lc is not None and comm.push_buffers(self.L_loc.numel(), self.L_loc) is not None and dirs is not None:
+            KL = _DualKronPushFn.apply(cols, self.Lc, plan, comm, dirs)
+        elif self.Lc is not None:
             # dual layout: K L on the column-sharded copy is the ordinary (single-device) Kronecker MVM with its own
             # autograd; one exchange brings it to row-sharded column blocks, the backward sends the gradient back
             cw = self.Lc.shape[1]
