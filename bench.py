@@ -461,7 +461,7 @@ def run_gpu_sharded(args, rank, world, device):
     x, y = synth_stream(d, n_init + STREAM_EXTRA)
     x, y = x.to(dtype), y.to(dtype)
     ctx = (S.max_root_decomposition_size(MAX_ROOT), S.max_cholesky_size(MAX_CHOL), S.cg_tolerance(CG_TOL),
-           S.sharded_dual_layout(bool(args.dual_layout)))
+           S.sharded_dual_layout(not args.single_layout))
     for c in ctx:
         c.__enter__()
     # the same class as N = 1, with the communicator: it drives the row-sharded engine (online_gp_b200/parallel.py)
@@ -557,7 +557,7 @@ def run_gpu_sharded(args, rank, world, device):
                        "rows_per_gpu": m // world,
                        "l2": "per-GPU panel slab (%.2f GB) larger than L2" % (m // world * r * b / 1e9),
                        "step": "evaluate + update (Adam step on Woodbury MLL + condition_on_observations)",
-                       "cuda_graphs": bool(use_graphs), "dual_layout": bool(args.dual_layout),
+                       "cuda_graphs": bool(use_graphs), "dual_layout": not args.single_layout,
                        "kron_directional_grad": bool(S.kron_directional_grad.on()),
                        "exchange": "peer memory" if model.comm.xbuf is not None else "nccl all_to_all",
                        "per_op_timing": "rank 0, eager pass of %d steps before the timed region" % KP},
@@ -679,8 +679,9 @@ def main():
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="N = 1: skip the north-star target grid record")
-    ap.add_argument("--dual-layout", action="store_true",
-                    help="N > 1: settings.sharded_dual_layout (two row <-> column exchanges per step instead of four)")
+    ap.add_argument("--dual-layout", action="store_true", help="(default since round 2; kept for old command lines)")
+    ap.add_argument("--single-layout", action="store_true",
+                    help="N > 1: turn settings.sharded_dual_layout off (four row <-> column exchanges per step instead of two)")
     ap.add_argument("--no-graphs", action="store_true", help="run the timed steps eagerly instead of replaying CUDA graphs")
     ap.add_argument("--cpu-budget", type=float, default=45.0, help="seconds of CPU work for the cpu_baseline leg")
     args = ap.parse_args()

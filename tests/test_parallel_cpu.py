@@ -214,7 +214,7 @@ def _fused_worker(rank, world, port, ret, directional=True):
     y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen)).unsqueeze(-1)
     out = []
     with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64), S.eval_cg_tolerance(1e-13), \
-            S.kron_directional_grad(directional):
+            S.kron_directional_grad(directional), S.sharded_dual_layout(False):
         saved = _install_fused_emulation(ops, parallel, g)
         try:
             if directional:

@@ -7,5 +7,5 @@ mkdir -p gpurun_out
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 600 python -m pytest tests/test_sharded_gpu.py -m gpu -q > gpurun_out/n${N}_sharded_pytest.log 2>&1; echo "sharded pytest rc=$?"; tail -5 gpurun_out/n${N}_sharded_pytest.log
 timeout 200 $T --master-port 29513 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/n${N}_bench.json 2> gpurun_out/n${N}_bench.err; echo "bench rc=$?"; cut -c1-600 gpurun_out/n${N}_bench.json
-timeout 200 $T --master-port 29514 bench.py --gpus $N --steps 20 --warmup 3 --dual-layout > gpurun_out/n${N}_bench_dual.json 2> gpurun_out/n${N}_bench_dual.err; echo "bench dual rc=$?"; cut -c1-400 gpurun_out/n${N}_bench_dual.json
+timeout 200 $T --master-port 29514 bench.py --gpus $N --steps 20 --warmup 3 --single-layout > gpurun_out/n${N}_bench_single.json 2> gpurun_out/n${N}_bench_single.err; echo "bench single-layout rc=$?"; cut -c1-400 gpurun_out/n${N}_bench_single.json
 timeout 200 $T --master-port 29515 tools/profile_step_sharded.py > gpurun_out/n${N}_profile.txt 2>&1; echo "profile rc=$?"; grep -v "^CPU" gpurun_out/n${N}_profile.txt | head -45

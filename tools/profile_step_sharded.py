@@ -16,7 +16,7 @@ os.environ.setdefault("NCCL_MAX_P2P_NCHANNELS", "64")
 dist.init_process_group("nccl", device_id=dev)
 d, g, q, n_init, _lr, _ = bench.WORKLOADS["powerplant_4d_g32"]
 x, y = bench.synth_stream(d, n_init + 64)
-with S.max_root_decomposition_size(512), S.max_cholesky_size(2048), S.cg_tolerance(1e-2), S.sharded_dual_layout("--dual" in sys.argv):
+with S.max_root_decomposition_size(512), S.max_cholesky_size(2048), S.cg_tolerance(1e-2), S.sharded_dual_layout("--single" not in sys.argv):
     model = ShardedOnlineSKIRegression(x[:n_init].to(dev), y[:n_init].to(dev), lr=5e-3, grid_size=g, grid_bound=1.0, comm=Comm())
     xd, yd = x[n_init:].to(dev), y[n_init:].to(dev)
     def step(t):
