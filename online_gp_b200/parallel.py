@@ -627,7 +627,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         self.plan = ShardPlan(sizes, self.comm.world, self.comm.rank)
         self.dtype = init_y.dtype
         self.gp_optimizer = torch.optim.Adam(self.parameters(), lr=lr)
-        self._dual = settings.sharded_dual_layout.on()
+        self._dual = settings.sharded_dual_layout.on() and self.comm.world > 1    # (one rank: the slab already holds all rows)
         self.Lc = None
         self._init_caches(init_x, init_y[:, 0], torch.ones_like(init_y[:, 0]))
         if self._dual:
