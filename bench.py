@@ -124,6 +124,19 @@ def algorithmic_work(m, r, b, d, g):
     }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from ONE `ncu --set full` capture of the step's kernels on
+# 1 x B200 (profiles/r02_ncu_step_kernels.md; BASELINE config 2: m = 2^20, r = 432, fp32).  Ops with two launches per
+# step (the two pair passes) carry the mean of the two.
+NCU_TRAFFIC_C2 = {"wiski_panel_rmul": 3.583e9, "wiski_gram": 4.059e9, "wiski_kron_fused_pair_apply": 3.704e9,
+                  "wiski_kron_fused_pair_grad": 4.522e9, "wiski_panel_lowrank_update2": 7.840e9}
+
+
+def ncu_traffic(dom, m, r, b, d, g):
+    if (m, r, b, d, g) == (1 << 20, 432, 4, 4, 32) and dom in NCU_TRAFFIC_C2:
+        return NCU_TRAFFIC_C2[dom], "profiles/r02_ncu_step_kernels.md (ncu --set full, same workload, 1 x B200)"
+    return None, "no ncu capture for this shape (see profiles/)"
+
+
 def roofline_of(prof_events, KP, m, r, b, d, g):
     """per-op device time (CUDA events around every library call of an eager pass) -> per-op table + roofline of the
     dominant op (frac against the measured peak of MEASURED_PEAKS.json)."""
@@ -145,14 +158,16 @@ def roofline_of(prof_events, KP, m, r, b, d, g):
         avg_ms = sum(big_t) / len(big_t)
         if bound == "hbm":
             ach = work / (avg_ms * 1e-3) / 1e9
+            traffic, tsrc = ncu_traffic(dom, m, r, b, d, g)
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": None, "peak_source": peak_src, "ms_per_launch": avg_ms, "algorithmic_bytes_per_launch": work,
-                    "note": "m x r fp32 panel pass; DRAM traffic per launch is not measurable inside this run — see the "
-                            "ncu captures under profiles/ (r02_ncu_*.md)"}
+                    "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "ms_per_launch": avg_ms,
+                    "algorithmic_bytes_per_launch": work}
         else:
             ach = work / (avg_ms * 1e-3) / 1e12
+            traffic, tsrc = ncu_traffic(dom, m, r, b, d, g)
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf_peak, "traffic": None, "peak_source": peak_src + " (bf16 dense cuBLAS)",
+                    "frac": ach / tf_peak, "traffic": traffic, "traffic_source": tsrc,
+                    "peak_source": peak_src + " (bf16 dense cuBLAS)",
                     "ms_per_launch": avg_ms, "algorithmic_flops_per_launch": work,
                     "tf32_3x_frac_of_half_bf16_peak": 3.0 * ach / (0.5 * tf_peak),
                     "note": "fp32 result via 3xTF32: the kernel issues 3x these flops on the tensor pipe, whose tf32 "

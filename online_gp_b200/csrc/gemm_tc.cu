@@ -138,6 +138,10 @@ struct Batching {
     // a_kwrap > 0: the K coordinate of A wraps after a_kwrap k-blocks while B keeps advancing:  A [B_0 ; B_1] = A B_0 + A B_1
     //   (panel GEMM with only the small operand split: B_0 = M, B_1 = M - tf32(M), see tc_panel_rmul_f32 terms = 2)
     int a_kwrap;
+    // round_a (SPLIT = false kernels): the A tile is rounded to NEAREST tf32 in shared memory before the products (the
+    //   tensor core itself truncates, which biases every product by ~-2^-12: harmless per value, not for a gradient that
+    //   drives 8 000 Adam steps)
+    int round_a;
     // o_ptrs[0] != NULL (with o_cw > 0): column block j of the result is written at o_ptrs[j] (row-major, pitch ld_out)
     // instead of out + j * o_cstride: the blocks go straight into the peers' NVLink-mapped buffers (PushDst mode 1)
     float* o_ptrs[8];
@@ -342,6 +346,17 @@ tc_gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int kb = 0; kb < nkb; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 uint8_t* sA = smem + (size_t)stage * STAGE_BYTES;
+                if (!SPLIT && bt.round_a) {
+                    for (int i = t; i < A_BYTES / 16; i += 128) {
+                        uint4* a = reinterpret_cast<uint4*>(sA) + i;
+                        uint4 v = *a;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.x) : "f"(__uint_as_float(v.x)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.y) : "f"(__uint_as_float(v.y)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.z) : "f"(__uint_as_float(v.z)));
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(v.w) : "f"(__uint_as_float(v.w)));
+                        *a = v;
+                    }
+                }
 #pragma unroll 4
                 for (int i = t; i < ((!SPLIT || bt.terms == 1) ? 0 : nvec); i += 128) {
                     // vectors [0, A_BYTES/16) belong to A (big at sA, small at sA + A_BYTES), the rest to B
@@ -617,6 +632,7 @@ int tc_panel_rmul_f32(const float* P, int64_t m, int64_t r, const float* M, int6
         if (int rc = make_map(&tmB, work, 2 * rpad, r2, BK1, true)) return rc;
         bt.a_kstride = bt.b_kstride = 2 * rpad;
         bt.a_kwrap = (int)(rpad / BK1);
+        bt.round_a = 1;
         return launch<true, false, BK1, ST1, false>(tmA, tmB, Out, m, r2, 2 * rpad, bn, ntiles, 2 * rpad, 1, ld_out, 0, st,
                                                     "tc_panel_rmul(tf32, M split)", &bt);
     }

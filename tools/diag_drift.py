@@ -70,8 +70,30 @@ def run(d, g, n0, steps, tag, **kw):
         for c in ctxs: c.__exit__(None, None, None)
         torch.set_default_dtype(torch.float32)
 
+def time_rmul():
+    P = torch.randn(1 << 20, 432, device="cuda:0")
+    M = torch.randn(432, 432, device="cuda:0")
+    ref = None
+    for terms in (3, 2, 1):
+        for _ in range(3):
+            Z = ops._rmul(P, M, terms=terms)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            Z = ops._rmul(P, M, terms=terms)
+        e1.record()
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = Z.double()
+        err = (Z.double() - ref)
+        print(f"[rmul m=2^20 r=432 terms={terms}] {e0.elapsed_time(e1) / 10:.3f} ms  max|err| vs 3-pass {float(err.abs().max()):.3e}  "
+              f"mean err {float(err.mean()):.3e}  (max|Z| {float(ref.abs().max()):.1f})")
+
+
 if __name__ == "__main__":
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 80
+    time_rmul()
     run(2, 48, 128, steps, "sites passes3 (default)", sites=True)
     run(2, 48, 128, steps, "sites passes2", sites=True, passes=2)
     run(2, 48, 128, steps, "fresh passes3 (default)")
