@@ -143,7 +143,14 @@ __global__ void lowrank_update_kernel(T* __restrict__ P, int64_t m, int64_t r, c
 // coefficient read from shared memory feeds ROWS FMAs (q = 8: 2 x 8 FMA per element against 8 B of HBM traffic — the
 // per-row kernel above re-reads U and Vt from L1 for every row and is L1-bound for q > 2).
 // The ROWS x QP partial dots are reduced across the warp by recursive halving (N - 1 shuffles for N values).
-template <typename T, int QP, int ROWS>
+// VEC elements per lane and load (16-byte vectors when r % VEC == 0: 4 x fewer load / LDS instructions and 4 x the bytes in
+// flight per warp — with q = 8 the 48 KB of coefficients leave room for 16 warps per SM only, and scalar loads then kept
+// just 8 KB per SM in flight: 33 % of HBM on the 128^3 / q = 8 workload before, see profiles/r02_*road3d*).
+template <typename T, int VEC>
+struct alignas(sizeof(T) * VEC) VecT {
+    T v[VEC];
+};
+template <typename T, int QP, int ROWS, int VEC>
 __global__ void __launch_bounds__(256) lowrank_update2_kernel(T* __restrict__ P0, T* __restrict__ P1, int64_t m, int64_t r,
                                                               const T* __restrict__ U, const T* __restrict__ Vt0,
                                                               const T* __restrict__ Vt1, int q) {
@@ -152,6 +159,7 @@ __global__ void __launch_bounds__(256) lowrank_update2_kernel(T* __restrict__ P0
     T* Vs = Us + (int64_t)QP * r;                    // [2][QP][r]
     T* red = Vs + (int64_t)2 * QP * r;               // [8 warps][ROWS * QP]
     constexpr int N = ROWS * QP;
+    using V = VecT<T, VEC>;
     const int npanels = P1 != nullptr ? 2 : 1;
     for (int64_t e = threadIdx.x; e < (int64_t)QP * r; e += blockDim.x) {
         const int t = (int)(e / r);
@@ -175,15 +183,24 @@ __global__ void __launch_bounds__(256) lowrank_update2_kernel(T* __restrict__ P0
         T dot[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) dot[i] = T(0);
-        for (int64_t j = lane; j < r; j += 32) {
-            T x[ROWS];
+        for (int64_t j = (int64_t)lane * VEC; j < r; j += 32 * VEC) {
+            V x[ROWS];
 #pragma unroll
-            for (int rr = 0; rr < ROWS; ++rr) x[rr] = rr < nvalid ? base[(int64_t)rr * r + j] : T(0);
+            for (int rr = 0; rr < ROWS; ++rr) {
+                if (rr < nvalid) {
+                    x[rr] = *reinterpret_cast<const V*>(base + (int64_t)rr * r + j);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) x[rr].v[e] = T(0);
+                }
+            }
 #pragma unroll
             for (int t = 0; t < QP; ++t) {
-                const T u = Us[(int64_t)t * r + j];
+                const V u = *reinterpret_cast<const V*>(Us + (int64_t)t * r + j);
 #pragma unroll
-                for (int rr = 0; rr < ROWS; ++rr) dot[rr * QP + t] += x[rr] * u;
+                for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) dot[rr * QP + t] += x[rr].v[e] * u.v[e];
             }
         }
         // recursive halving: afterwards every lane holds the warp total of value `idx`
@@ -216,19 +233,28 @@ __global__ void __launch_bounds__(256) lowrank_update2_kernel(T* __restrict__ P0
         T dsum[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) dsum[i] = myred[i];
-        for (int64_t j = lane; j < r; j += 32) {
-            T x[ROWS];
+        for (int64_t j = (int64_t)lane * VEC; j < r; j += 32 * VEC) {
+            V x[ROWS];
 #pragma unroll
-            for (int rr = 0; rr < ROWS; ++rr) x[rr] = rr < nvalid ? base[(int64_t)rr * r + j] : T(0);
+            for (int rr = 0; rr < ROWS; ++rr) {
+                if (rr < nvalid) {
+                    x[rr] = *reinterpret_cast<const V*>(base + (int64_t)rr * r + j);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) x[rr].v[e] = T(0);
+                }
+            }
 #pragma unroll
             for (int t = 0; t < QP; ++t) {
-                const T v = Vk[(int64_t)t * r + j];
+                const V v = *reinterpret_cast<const V*>(Vk + (int64_t)t * r + j);
 #pragma unroll
-                for (int rr = 0; rr < ROWS; ++rr) x[rr] += dsum[rr * QP + t] * v;
+                for (int rr = 0; rr < ROWS; ++rr)
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) x[rr].v[e] += dsum[rr * QP + t] * v.v[e];
             }
 #pragma unroll
             for (int rr = 0; rr < ROWS; ++rr)
-                if (rr < nvalid) base[(int64_t)rr * r + j] = x[rr];
+                if (rr < nvalid) *reinterpret_cast<V*>(base + (int64_t)rr * r + j) = x[rr];
         }
     }
 }
@@ -566,9 +592,11 @@ static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const
         return P1 != nullptr ? lowrank_update<T>(P1, m, r, U, Vt1, q, stream) : 0;
     }
     cudaStream_t st = as_stream(stream);
+    const bool vec = r % (16 / (int64_t)sizeof(T)) == 0 && (reinterpret_cast<uintptr_t>(P0) & 15) == 0 &&
+                     (reinterpret_cast<uintptr_t>(P1) & 15) == 0;
 #define LR2(QP, ROWS)                                                                                                        \
     do {                                                                                                                     \
-        auto kfn = lowrank_update2_kernel<T, QP, ROWS>;                                                                      \
+        auto kfn = vec ? lowrank_update2_kernel<T, QP, ROWS, 16 / (int)sizeof(T)> : lowrank_update2_kernel<T, QP, ROWS, 1>;   \
         WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lowrank2(attr)"); \
         int64_t groups = ceil_div(m, ROWS) * (P1 != nullptr ? 2 : 1);                                                        \
         int per_sm = smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 4;                                                       \

@@ -764,14 +764,15 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             KLb = P["KL"].detach()
             nb, cwb = KLb.shape[0], KLb.shape[2]
             a = self._q_solve(P, P["c"].detach())
-            mu_loc = P["Kb"].detach().clone()
-            for j in range(nb):
-                mu_loc -= ops.panel_rmul(KLb[j], a[j * cwb:(j + 1) * cwb].contiguous())      # :376
-            mean = comm.allreduce_(ops.left_interp(idx_l, val_l, mu_loc))         # :206-210
+            # W* (K b - K L Q^-1 c) (:206-210, :376) without materialising the m-vector: the stencil rows of K b and of K L
+            # are gathered once (the K L rows also serve the variance) and meet in ONE all-reduce of q x (1 + r) numbers
+            G = comm.allreduce_(torch.cat([ops.left_interp(idx_l, val_l, P["Kb"].detach())]
+                                          + [ops.left_interp(idx_l, val_l, KLb[j]) for j in range(nb)], dim=1))
+            T = G[:, 1:].t()
+            mean = G[:, :1] - T.t() @ a
             q = x.shape[0]
             Wt = ops.left_t_interp(idx, val, torch.eye(q, dtype=self.dtype, device=x.device), plan.m)
             c1 = ops.left_interp(idx, val, ops.kron_toeplitz_matmul(P["cols"].detach(), plan.sizes, Wt))
-            T = comm.allreduce_(torch.cat([ops.left_interp(idx_l, val_l, KLb[j]) for j in range(nb)], dim=1)).t()
             cov = (c1 - T.t() @ self._q_solve(P, T)) * P["noise"]                  # :222-228
             var = cov.diagonal().unsqueeze(-1) + P["noise"]                        # predict(): + second_noise
         return mean, var
