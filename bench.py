@@ -165,13 +165,19 @@ def roofline_of(prof_events, KP, m, r, b, d, g):
         else:
             ach = work / (avg_ms * 1e-3) / 1e12
             traffic, tsrc = ncu_traffic(dom, m, r, b, d, g)
-            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                    "frac": ach / tf_peak, "traffic": traffic, "traffic_source": tsrc,
-                    "peak_source": peak_src + " (bf16 dense cuBLAS)",
+            # The fp32 GEMMs run as 3xTF32 on the tensor pipe: B200 has no fp32 tensor path, kind::tf32 runs at half the
+            # bf16 rate, and an fp32-accurate product costs three tf32 MMAs.  The roof of an fp32-accurate GEMM is therefore
+            # the measured dense bf16 rate / 6; `frac` is quoted against it, `frac_of_bf16_peak` against the raw figure.
+            fp32_peak = tf_peak / 6.0
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": ach / fp32_peak, "frac_of_bf16_peak": ach / tf_peak, "bf16_peak": tf_peak,
+                    "traffic": traffic, "traffic_source": tsrc,
+                    "peak_source": peak_src + " (bf16 dense cuBLAS) / 6: kind::tf32 = half the bf16 rate, 3 tf32 MMAs per "
+                                              "fp32-accurate product (3xTF32)",
                     "ms_per_launch": avg_ms, "algorithmic_flops_per_launch": work,
-                    "tf32_3x_frac_of_half_bf16_peak": 3.0 * ach / (0.5 * tf_peak),
-                    "note": "fp32 result via 3xTF32: the kernel issues 3x these flops on the tensor pipe, whose tf32 "
-                            "rate is half the bf16 rate the peak was measured with"}
+                    "hbm_view": {"algorithmic_bytes_per_launch": 2.0 * m * r * b, "achieved_GBps": 2.0 * m * r * b / (avg_ms * 1e-3) / 1e9,
+                                 "frac_of_hbm_peak": 2.0 * m * r * b / (avg_ms * 1e-3) / 1e9 / hbm_peak},
+                    "note": "algorithmic flops = 2 m r r2 (fp32 GEMM); the kernel issues 3x that many tf32 flops"}
     return per_op, roof
 
 
