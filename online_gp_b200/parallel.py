@@ -95,6 +95,7 @@ class Comm:
         self._a2a_ok = self.enabled and dist.get_backend(group) != "gloo"
         self.xbuf = self._xhdl = self._xpeers = self._xstreams = None      # peer-memory exchange (enable_peer_exchange)
         self.push = None                                                    # _PushBuffers (enable_push)
+        self._far = None                                                    # (symmetric buffer, group name): enable_fast_allreduce
 
     def enable_push(self, numel, dtype, device):
         """Collective.  Sets up the peer-mapped receive regions of the pushing kernels (``_PushBuffers``); returns them,
@@ -140,8 +141,44 @@ class Comm:
 
     def allreduce_(self, t):
         if self.world > 1:
+            far = self._far
+            if (far is not None and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+                    and 0 < t.numel() <= far[0].numel() and (t.numel() * 4) % 16 == 0):
+                # latency-sized sums (r x r Gram partials, r x q projections, gathered stencil rows): every rank copies its
+                # addend into its symmetric buffer and reads all peers' over NVLink in ONE kernel — no ring, no protocol
+                # hand-shakes (NCCL's LL all-reduce takes several times longer for these sizes on 8 GPUs)
+                res = torch.ops.symm_mem.one_shot_all_reduce_copy(far[0][:t.numel()], t.view(-1), "sum", far[1])
+                t.view(-1).copy_(res)
+                return t
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
+
+    def enable_fast_allreduce(self, device, max_elems=1 << 19):
+        """Collective.  One symmetric fp32 buffer (2 MB) for the one-shot all-reduce of small replicated quantities;
+        WISKI_SYMM_ALLREDUCE=0 keeps every sum on NCCL."""
+        self._far = None
+        if self.world == 1 or not self._a2a_ok or os.environ.get("WISKI_SYMM_ALLREDUCE", "1") == "0":
+            return False
+        ok = 1
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            gname = group.group_name
+            buf = symm.empty(max_elems, dtype=torch.float32, device=device)
+            symm.rendezvous(buf, gname)
+            probe = torch.ones(8, dtype=torch.float32, device=device)
+            res = torch.ops.symm_mem.one_shot_all_reduce_copy(buf[:8], probe, "sum", gname)
+            if float(res.sum().item()) != 8.0 * self.world:
+                ok = 0
+        except Exception as err:                    # noqa: BLE001
+            warnings.warn(f"symmetric-memory all-reduce unavailable ({type(err).__name__}: {err}); using NCCL")
+            ok = 0
+        flag = torch.tensor([ok], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return False
+        self._far = (buf, gname)
+        return True
 
     def allgather(self, t):
         """[world, *t.shape]"""
@@ -638,6 +675,8 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
                        and self.comm.enable_push(self.L_loc.numel(), self.dtype, init_x.device) is not None)
             if not pushing:
                 self.comm.enable_peer_exchange(self.L_loc.numel(), self.dtype, init_x.device)
+        if self.comm.world > 1 and init_x.is_cuda and self.dtype == torch.float32:
+            self.comm.enable_fast_allreduce(init_x.device)
         self._graphs = None          # opt-in CUDA-graph replay: enable_cuda_graphs()
         self._n_t = None             # device-side copy of num_data (graph mode)
 
@@ -654,6 +693,10 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         self.D_logdet = D.log().sum()
         self.num_data = n0
         self.b_loc = ops.left_t_interp(idx, val, (y / D).unsqueeze(-1), plan.m_loc)
+        # the interpolation cache b = W^T D^-1 y is an m-vector (4 MB at m = 2^20): every rank keeps it whole as well (each
+        # update scatters q s entries), so building K b needs no all-gather
+        gidx, gval = self.covar_module._compute_grid(X)
+        self.b_full = ops.left_t_interp(gidx, gval.detach(), (y / D).unsqueeze(-1), plan.m)
         vval = val / D.clamp_min(1e-7).sqrt().unsqueeze(-1)
         max_rank = settings.max_root_decomposition_size.value()
         n1 = min(n0, max_rank)
@@ -742,7 +785,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm, dirs)         # :348  column blocks [nb, m_loc, r / nb]
         r = self.L_loc.shape[1]
         Q = _ShardedGramBlocksFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355
-        b_full = comm.allgather(self.b_loc).reshape(plan.m, 1)
+        b_full = self.b_full
         Kb_full = ops.kron_toeplitz_matmul(cols, plan.sizes, b_full)              # :366
         Kb = _ShardSliceFn.apply(Kb_full, plan, comm)
         c = _ShardedGramFn.apply(self.L_loc, Kb, comm)                            # :360-361
@@ -845,6 +888,8 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         self.response_cache.add_((y * y / D).sum())           # in place: graph replays must see the running values
         self.D_logdet.add_(D.log().sum())
         ops.scatter_add_(self.b_loc, idx_l, val_l, (y / D).unsqueeze(-1))
+        gidx, gval = self.covar_module._compute_grid(x)
+        ops.scatter_add_(self.b_full, gidx, gval.detach(), (y / D).unsqueeze(-1))
         self._root_update(idx_l, val_l / D.clamp_min(1e-7).sqrt().unsqueeze(-1))
         self.num_data += x.shape[0]
         if self._n_t is not None:
