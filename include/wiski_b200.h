@@ -174,6 +174,8 @@ int wiski_kron_pair_grad_dir_axes_f32(const float* cols, const float* dirs, int 
  * rank's part starts.  Callers order producer and consumer with a device-side barrier over all ranks.
  *   mode 1 (row slab -> column blocks): X [m_loc, c]; column block j (c / n_dst columns) -> dst[j], a [m_loc, c / n_dst] panel
  *   mode 2 (column block -> row slabs): X [m, c], axis_u = 0; rows of axis-0 range j -> dst[j], a [m / n_dst, c] panel
+ *   mode 3 = mode 2 with 32-column store boxes (c % 32 == 0; apply pass only): 128-byte row pieces instead of 64-byte ones,
+ *            which NVLink carries 1.6x faster
  * Tensor-core kernels only (status 3 when the shape is not theirs: 32-point axes, c % 16 == 0, n_dst <= 8).
  * h_lay_x / h_lay_zp: (ld, cw, cstride) of the inputs (X; Z then P) or NULL for plain row-major panels. */
 int wiski_kron_pair_apply_push_f32(const float* cols, int d, const int64_t* h_g, int64_t gmax, int axis_u, int axis_v,

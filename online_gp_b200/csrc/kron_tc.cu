@@ -67,6 +67,10 @@ struct Lay {
 //   mode 1  column block j of the tile's columns belongs to rank j      (row slab -> all rows of my columns)
 //   mode 2  the tile's axis-u range splits into n_dst equal parts, part i belongs to rank i (u = grid axis 0:
 //           column-sharded panel -> my rows of every column block); box_u = axis-u extent of one store
+//   mode 3  (apply pass only) mode 2 with 32-column store boxes: a CTA works on the two 16-column tiles of a 32-column
+//           group back to back, keeps the first one's result in the spare TMEM columns [96,128) of its slots and stores
+//           both as ONE [u_loc][8 v][32 columns] box per rank — 128-byte row pieces, which NVLink carries at 665 GB/s
+//           against 417 GB/s for 64-byte ones (profiles/r02_p2p_store_bandwidth_n2.txt)
 constexpr int MAXP = 8;
 struct PushMaps {
     CUtensorMap m[MAXP];
@@ -122,13 +126,19 @@ __device__ __forceinline__ BDesc make_bdesc(uint32_t b_big, uint32_t b_small) {
     return b;
 }
 // D[slot] = A[slot] (128 x 32, in TMEM) * B (32 x N), 3xTF32: 12 tcgen05.mma of 128 x N x 8.  Warp-collective (all lanes).
-__device__ __forceinline__ void issue_mma_tile(uint32_t tslot, const BDesc& b, uint32_t idesc) {
+__device__ __forceinline__ void issue_mma_tile(uint32_t tslot, const BDesc& b, uint32_t idesc, uint32_t d_off = 64) {
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
-        umma_tf32_ts_elect(tslot + 64, tslot + 32 + ks * 8, b.big[ks], idesc, ks > 0 ? 1u : 0u);   // remainder(A) * big(B)
-        umma_tf32_ts_elect(tslot + 64, tslot + ks * 8, b.small[ks], idesc, 1u);                    // big(A) * remainder(B)
-        umma_tf32_ts_elect(tslot + 64, tslot + ks * 8, b.big[ks], idesc, 1u);                      // big(A) * big(B)
+        umma_tf32_ts_elect(tslot + d_off, tslot + 32 + ks * 8, b.big[ks], idesc, ks > 0 ? 1u : 0u);   // remainder(A) * big(B)
+        umma_tf32_ts_elect(tslot + d_off, tslot + ks * 8, b.small[ks], idesc, 1u);                    // big(A) * remainder(B)
+        umma_tf32_ts_elect(tslot + d_off, tslot + ks * 8, b.big[ks], idesc, 1u);                      // big(A) * big(B)
     }
+}
+// it-th tile of this CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ..; in pair mode (Push mode 3) the two 16-column
+// tiles (2 s, 2 s + 1) of 32-column group s = blockIdx.x + (it / 2) gridDim.x, one after the other (chunk index is the
+// fastest part of the tile id, so the two differ in the column chunk only)
+__device__ __forceinline__ long long tile_of(long long it, bool pair) {
+    return pair ? 2 * ((long long)blockIdx.x + (it >> 1) * gridDim.x) + (it & 1) : (long long)blockIdx.x + it * gridDim.x;
 }
 
 __device__ __forceinline__ void decode_tile(const Geom& g, long long tile, int& cc, int& f0, int& f1) {
@@ -232,7 +242,9 @@ pair_apply_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         if (lane == 0) {
             long long seq = 0;
             long long pr[2] = {0, 0}, tl = PROF ? clock64() : 0;
-            for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+            for (long long itp = 0;; ++itp) {
+                const long long tile = tile_of(itp, p.push.mode == 3);
+                if (tile >= g.n_tiles) break;
                 int cc, f0, f1;
                 decode_tile(g, tile, cc, f0, f1);
                 const int col0 = cc * CB, blk = col0 / p.cwx;
@@ -259,7 +271,11 @@ pair_apply_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             const BDesc bv = make_bdesc(timg_a, timg_a + TIMG_B), bu = make_bdesc(timg_a + 2 * TIMG_B, timg_a + 3 * TIMG_B);
             uint32_t use = 0;
             long long pr[2] = {0, 0}, tl = PROF ? clock64() : 0;
-            for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+            const bool pair = p.push.mode == 3;
+            for (long long itm = 0;; ++itm) {
+                if (tile_of(itm, pair) >= g.n_tiles) break;
+                // pair mode: the final result of the first half-tile goes to the spare columns [96,128) and waits there
+                const uint32_t d_keep = (pair && (itm & 1) == 0) ? 96u : 64u;
 #pragma unroll
                 for (int phase = 0; phase < 2; ++phase, ++use) {
 #pragma unroll
@@ -268,7 +284,7 @@ pair_apply_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
                         mbar_wait(&B.a_ready[slot], use & 1);
                         KTC_TICK(0);
                         tc_fence_after();
-                        issue_mma_tile(tmem_base + slot * SLOT_COLS, phase == 0 ? bv : bu, idesc);
+                        issue_mma_tile(tmem_base + slot * SLOT_COLS, phase == 0 ? bv : bu, idesc, phase == 0 ? 64u : d_keep);
                         umma_commit_elect(&B.d_ready[slot]);
                         KTC_TICK(1);
                     }
@@ -289,7 +305,10 @@ pair_apply_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
         uint32_t use = 0;
         long long it = 0;
         long long pr[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, tl = PROF ? clock64() : 0;
-        for (long long tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x, ++it) {
+        const bool pair = p.push.mode == 3;
+        for (;; ++it) {
+            const long long tile = tile_of(it, pair);
+            if (tile >= g.n_tiles) break;
             int cc, f0, f1;
             decode_tile(g, tile, cc, f0, f1);
             // ---- axis v: rows (u, w), K = v'
@@ -348,6 +367,41 @@ pair_apply_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
             // results -> ybuf as four [32 u][8 v][16 w] boxes (conflict free) -> one TMA store per MMA tile
             const int col0 = cc * CB, blk = col0 / p.cwy;
             const int c0y = col0 - blk * p.cwy;
+            if (pair) {
+                // first half-tile: its result stays in TMEM columns [96,128); second: both halves leave as 32-column boxes,
+                // one MMA tile (= [32 u][8 v][32 columns], 32 KB) per group at a time through ybuf
+                const bool second = (it & 1) != 0;
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int j = grp + 2 * jj, slot = grp * 2 + jj;
+                    mbar_wait(&B.d_ready[slot], use & 1);
+                    if (!second) continue;
+                    tc_fence_after();
+                    float* og = ybuf + grp * (2 * STAGE_F) + hi * (2 * CB) + w;
+                    if (jj == 1) {                                   // the group's box of jj = 0 must have been read out
+                        if (store_thread) tma_store_wait_read<0>();
+                        named_bar_sync(4 + grp, 128);
+                    }
+                    uint32_t d[32];
+                    tmem_ld32(tlane + slot * SLOT_COLS + 96, d);     // columns [c0, c0 + 16): the first half-tile
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) og[u * (8 * 2 * CB)] = __uint_as_float(d[u]);
+                    tmem_ld32(tlane + slot * SLOT_COLS + 64, d);     // columns [c0 + 16, c0 + 32)
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) og[u * (8 * 2 * CB) + CB] = __uint_as_float(d[u]);
+                    fence_proxy_async_smem();
+                    named_bar_sync(4 + grp, 128);
+                    if (store_thread) {
+                        const Coords kc = tile_coords(g, c0y - CB, 0, f0, f1, 0, 8 * j);
+                        for (int i = 0; i * p.push.u_loc < G; ++i)
+                            tma_store_box(&pm.m[i], ybuf + grp * (2 * STAGE_F) + i * p.push.u_loc * (8 * 2 * CB), kc);
+                        tma_store_commit();
+                    }
+                }
+                ++use;
+                tc_fence_before();
+                continue;
+            }
 #pragma unroll
             for (int jj = 0; jj < 2; ++jj) {
                 const int j = grp + 2 * jj, slot = grp * 2 + jj;
@@ -737,7 +791,7 @@ static bool make_geom(Geom& g, MapDims& md, int d, const int64_t* h_g, int au, i
 // Column-chunked operands (cw < c) must be stacked blocks [nblk][rows][cw] (ld = cw, cstride = rows * cw): the block
 // index then folds into the slowest real row group.
 static int make_map5(CUtensorMap* map, const float* base, const Geom& g, const MapDims& md, const Lay& l, int64_t c,
-                     int box_v, int box_u) {
+                     int box_v, int box_u, int box_cols = CB) {
     TcEncodeTiledFn enc = tc_encode_fn();
     if (enc == nullptr) {
         set_error("kron_tc: cuTensorMapEncodeTiled unavailable");
@@ -754,7 +808,7 @@ static int make_map5(CUtensorMap* map, const float* base, const Geom& g, const M
     cuuint64_t gstr[4];
     cuuint32_t box[5], estr[5] = {1u, 1u, 1u, 1u, 1u};
     gdim[0] = (cuuint64_t)l.cw;
-    box[0] = (cuuint32_t)CB;
+    box[0] = (cuuint32_t)box_cols;
     for (int i = 0; i < 4; ++i) {
         const int pos = i + 1;
         gdim[pos] = (cuuint64_t)md.ext[i] * (pos == g.pos_blk ? (cuuint64_t)nblk : 1u);
@@ -811,13 +865,15 @@ static int fill_push(PushMaps& pm, Push& push, const Geom& g, const MapDims& md,
             if (int rc = make_map5(&pm.m[j], pd.dst[j], g, md, Lay{cw, cw, 0}, cw, box_v, grad ? 8 : G)) return rc;
         return 0;
     }
-    if (pd.mode != 2 || g.pos_u != g.pos_blk || G % pd.n_dst != 0) return 3;     // u must be the slowest grid axis
+    if ((pd.mode != 2 && pd.mode != 3) || g.pos_u != g.pos_blk || G % pd.n_dst != 0) return 3;     // u = the slowest grid axis
+    if (pd.mode == 3 && (grad || c % (2 * CB) != 0)) return 3;
     push.u_loc = G / pd.n_dst;
     push.box_u = grad ? (push.u_loc < 8 ? push.u_loc : 8) : push.u_loc;
     MapDims md2 = md;
     md2.ext[g.pos_u - 1] = push.u_loc;
     for (int j = 0; j < pd.n_dst; ++j)
-        if (int rc = make_map5(&pm.m[j], pd.dst[j], g, md2, Lay{c, c, 0}, c, box_v, push.box_u)) return rc;
+        if (int rc = make_map5(&pm.m[j], pd.dst[j], g, md2, Lay{c, c, 0}, c, box_v, push.box_u, pd.mode == 3 ? 2 * CB : CB))
+            return rc;
     return 0;
 }
 
@@ -843,6 +899,11 @@ int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gma
         if (int rc = fill_push(pm, p.push, g, md, *push, c, 8, false)) return rc;
         tmY = tmX;
         ly = push->mode == 1 ? Lay{c / push->n_dst, c / push->n_dst, 0} : Lay{c, c, 0};
+        if (push->mode == 3 && getenv("WISKI_PUSH_64B") != nullptr) {
+            // (A/B switch for the timings in profiles/: WISKI_PUSH_64B=1 keeps the 16-column boxes of mode 2)
+            p.push.mode = 2;
+            if (int rc = fill_push(pm, p.push, g, md, PushDst{push->dst, push->n_dst, 2}, c, 8, false)) return rc;
+        }
     } else {
         memset(&pm, 0, sizeof(pm));
         if (int rc = make_map5(&tmY, Y, g, md, ly, c, 8, G)) return rc;
@@ -858,7 +919,8 @@ int tc_pair_apply_axes(const float* cols, int d, const int64_t* h_g, int64_t gma
     const size_t smem = 1024 + 4 * TIMG_B + (size_t)kApplyStages * STAGE_B + TILE_B + (2 * kApplyStages + 8) * 8 + 16;
     auto kfn = prof != nullptr ? pair_apply_tc_kernel<kApplyStages, true> : pair_apply_tc_kernel<kApplyStages, false>;
     WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "kron_tc(attr)");
-    const long long grid = g.n_tiles < kNumSMs ? g.n_tiles : kNumSMs;
+    const long long units = p.push.mode == 3 ? g.n_tiles / 2 : g.n_tiles;      // pair mode: a CTA takes 32-column groups
+    const long long grid = units < kNumSMs ? units : kNumSMs;
     kfn<<<(unsigned)grid, NTHREADS, smem, st>>>(tmX, tmY, pm, p);
     WISKI_CHECK_LAUNCH("kron_tc(pair_apply)");
     count_launches(1);

@@ -387,7 +387,8 @@ def _fused_pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store, chunk_z=1, 
 # NVLink-mapped buffers; `dst` = ctypes table of device pointers (one per rank, parallel._PushBuffers.dst)
 def _fused_pair_apply_push(cols, sizes, pair, X, dst, n_dst, mode):
     """(T_u x T_v) X pushed to the peers.  mode 1: X is a row slab [m_loc, c], column block j -> rank j (a [m_loc, c / n_dst]
-    panel at dst[j]); mode 2: X holds all rows of a column block, axis_u = 0, rows of axis-0 range j -> rank j."""
+    panel at dst[j]); mode 2: X holds all rows of a column block, axis_u = 0, rows of axis-0 range j -> rank j; mode 3: mode 2
+    with 32-column store boxes (c % 32 == 0)."""
     d, gmax = cols.shape
     m, c = X.shape
     h_g = (c_int64 * d)(*sizes)

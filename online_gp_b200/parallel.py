@@ -379,7 +379,7 @@ class _ShardedKronFn(torch.autograd.Function):
                 ops._fused_pair_apply_push(cols, slab, ctx.loc_pair, X.contiguous(), pb.dst("A", part), W, 1)
                 pb.barrier()
                 X23c = pb.local("A").view(W * plan.m_loc, cw)                          # all rows of my columns
-                ops._fused_pair_apply_push(cols, plan.sizes, ctx.col_pair, X23c, pb.dst("B", part), W, 2)
+                ops._fused_pair_apply_push(cols, plan.sizes, ctx.col_pair, X23c, pb.dst("B", part), W, 3 if cw % 32 == 0 else 2)
                 pb.barrier()
                 ctx.save_for_backward(cols, X, X23c)
                 return pb.local("B").view(W, plan.m_loc, cw)                            # my rows of every column block
@@ -492,7 +492,7 @@ class _DualKronPushFn(torch.autograd.Function):
         pb = comm.push
         ctx.col_pair, ctx.loc_pair = ops.kron_pairs(plan.sizes, directional=True)
         X12 = ops._fused_pair_apply(cols, plan.sizes, ctx.loc_pair, Lc)
-        ops._fused_pair_apply_push(cols, plan.sizes, ctx.col_pair, X12, pb.dst("B", plan.m_loc * cw), W, 2)
+        ops._fused_pair_apply_push(cols, plan.sizes, ctx.col_pair, X12, pb.dst("B", plan.m_loc * cw), W, 3 if cw % 32 == 0 else 2)
         pb.barrier()
         ctx.save_for_backward(cols, Lc, X12)
         return pb.local("B").view(W, plan.m_loc, cw)
@@ -754,7 +754,11 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
                 # Lc += (L p) (C p^T)[:, my columns]
                 cw = self.Lc.shape[1]
                 t_full = self.comm.allgather(ops.panel_rmul(self.L_loc, p)).reshape(self.plan.m, p.shape[1])
-                self.Lc.addmm_(t_full, CpT[:, self.comm.rank * cw:(self.comm.rank + 1) * cw])
+                w = CpT[:, self.comm.rank * cw:(self.comm.rank + 1) * cw]
+                if p.shape[1] == 1:
+                    self.Lc.addcmul_(t_full, w)          # rank-1: one streaming pass (the SIMT sgemm of addmm takes 1.7x as long)
+                else:
+                    self.Lc.addmm_(t_full, w)
             ops.panel_lowrank_update2_(self.L_loc, self.B_loc, p, CpT, Cp @ p.t())
 
     # ---- pieces with grad (Kuu / sigma^2, K L, Q, K b, c)  — batched_fixed_noise_online_gp.py:334-366

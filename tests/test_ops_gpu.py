@@ -357,6 +357,18 @@ def test_pushing_kernels_write_the_exchange_layout(W):
     got = torch.full((W, m_loc, cw), float("nan"), device=DEV)
     ops._fused_pair_apply_push(cols, full, (0, 3), Xc, table(got), W, 2)
     assert torch.equal(got.view(m, cw), want)
+    # mode 3: the same result through 32-column store boxes (two 16-column tiles per CTA step, the first one's result
+    # parked in TMEM); also on a wider block (4 column groups per row of tiles)
+    got.fill_(float("nan"))
+    ops._fused_pair_apply_push(cols, full, (0, 3), Xc, table(got), W, 3)
+    assert torch.equal(got.view(m, cw), want)
+    if W == 2:
+        Xw = (torch.randn(m, 128, generator=gen) / 10).to(DEV)
+        wantw = ops._fused_pair_apply(cols, full, (0, 3), Xw)
+        gotw = torch.full((W, m_loc, 128), float("nan"), device=DEV)
+        ops._fused_pair_apply_push(cols, full, (0, 3), Xw, table(gotw), W, 3)
+        assert torch.equal(gotw.view(m, 128), wantw)
+        del Xw, wantw, gotw
     o_want = torch.zeros(3, dtype=torch.float64, device=DEV)
     o_got = torch.zeros(3, dtype=torch.float64, device=DEV)
     wantz = ops._fused_pair_grad_dir(cols, dirs, full, (0, 3), Zc, Xc, o_want, store=True)
