@@ -210,6 +210,17 @@ int wiski_panel_lowrank_update2_f32(float* P0, float* P1, int64_t m, int64_t r, 
                                     const float* Vt1, int64_t q, void* stream);
 int wiski_panel_lowrank_update2_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
                                     const double* Vt1, int64_t q, void* stream);
+/* The same launch with a by-product: Tout [m,q] = P0 U of the rows BEFORE the update (the vector the dual-layout sharded
+ * model all-gathers to update its column-sharded copy) — saves a separate pass over P0. */
+int wiski_panel_lowrank_update2_t_f32(float* P0, float* P1, int64_t m, int64_t r, const float* U, const float* Vt0,
+                                      const float* Vt1, int64_t q, float* Tout, void* stream);
+int wiski_panel_lowrank_update2_t_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
+                                      const double* Vt1, int64_t q, double* Tout, void* stream);
+/* P[m,c] += T[m,q] W[q,c] in place (q <= 32), one streaming pass.  Used by the row-sharded model with the dual layout: the
+ * column-sharded copy of the root panel follows the rank-q update `collect_vector` (updated_root_lazy_tensor.py:97-100)
+ * through T = L p, gathered from all ranks, and W = the local columns of C p^T. */
+int wiski_panel_outer_add_f32(float* P, int64_t m, int64_t c, const float* T, int64_t q, const float* W, void* stream);
+int wiski_panel_outer_add_f64(double* P, int64_t m, int64_t c, const double* T, int64_t q, const double* W, void* stream);
 
 /* ---- k10: Gram  G = A^T @ Bm,  A [m,r], Bm [m,r2], G [r,r2]  (Q - I = L^T (K L), and L^T (K b);
  * batched_fixed_noise_online_gp.py:352-355,360-361).  work = scratch of wiski_gram_work_elems(m,r,r2) elements. */

@@ -153,7 +153,7 @@ struct alignas(sizeof(T) * VEC) VecT {
 template <typename T, int QP, int ROWS, int VEC>
 __global__ void __launch_bounds__(256) lowrank_update2_kernel(T* __restrict__ P0, T* __restrict__ P1, int64_t m, int64_t r,
                                                               const T* __restrict__ U, const T* __restrict__ Vt0,
-                                                              const T* __restrict__ Vt1, int q) {
+                                                              const T* __restrict__ Vt1, int q, T* __restrict__ t_out) {
     extern __shared__ __align__(16) unsigned char smem_lr[];
     T* Us = reinterpret_cast<T*>(smem_lr);          // [QP][r]
     T* Vs = Us + (int64_t)QP * r;                    // [2][QP][r]
@@ -233,6 +233,10 @@ __global__ void __launch_bounds__(256) lowrank_update2_kernel(T* __restrict__ P0
         T dsum[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) dsum[i] = myred[i];
+        if (t_out != nullptr && k == 0 && lane < N) {          // by-product: (P0 U)[row, t] of the rows BEFORE the update
+            const int rr = lane / QP, t = lane - rr * QP;
+            if (rr < nvalid && t < q) t_out[(row0 + rr) * q + t] = myred[lane];
+        }
         for (int64_t j = (int64_t)lane * VEC; j < r; j += 32 * VEC) {
             V x[ROWS];
 #pragma unroll
@@ -581,13 +585,17 @@ static int lowrank_update(T* P, int64_t m, int64_t r, const T* U, const T* Vt, i
 
 // P1 / Vt1 may be NULL (single panel).  Falls back to the per-row kernel when U and Vt do not fit in shared memory.
 template <typename T>
-static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const T* Vt0, const T* Vt1, int64_t q, void* stream) {
+static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const T* Vt0, const T* Vt1, int64_t q, void* stream,
+                           T* t_out = nullptr) {
     WISKI_CHECK_ARG(m >= 0 && r >= 1 && q >= 1 && q <= 32, "panel_lowrank_update2: need 1 <= q <= 32 (q=%lld)", (long long)q);
     WISKI_CHECK_ARG((P1 == nullptr) == (Vt1 == nullptr), "panel_lowrank_update2: P1 and Vt1 go together");
     if (m == 0) return 0;
     const int qp = q == 1 ? 1 : q <= 2 ? 2 : q <= 4 ? 4 : q <= 8 ? 8 : q <= 16 ? 16 : 32;
     const size_t smem = ((size_t)3 * qp * r + 8 * 32) * sizeof(T);
     if (smem > 200 * 1024) {
+        if (t_out != nullptr) {
+            if (int rc = panel_rmul<T>(P0, m, r, U, q, t_out, stream)) return rc;
+        }
         if (int rc = lowrank_update<T>(P0, m, r, U, Vt0, q, stream)) return rc;
         return P1 != nullptr ? lowrank_update<T>(P1, m, r, U, Vt1, q, stream) : 0;
     }
@@ -602,7 +610,7 @@ static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const
         int per_sm = smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 4;                                                       \
         int64_t blocks = ceil_div(groups, 8);                                                                                \
         if (blocks > (int64_t)kNumSMs * per_sm) blocks = (int64_t)kNumSMs * per_sm;                                          \
-        kfn<<<(unsigned)blocks, 256, smem, st>>>(P0, P1, m, r, U, Vt0, Vt1, (int)q);                                         \
+        kfn<<<(unsigned)blocks, 256, smem, st>>>(P0, P1, m, r, U, Vt0, Vt1, (int)q, t_out);                                  \
     } while (0)
     if (qp == 1) LR2(1, 8);
     else if (qp == 2) LR2(2, 8);
@@ -612,6 +620,53 @@ static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const
     else LR2(32, 1);
 #undef LR2
     WISKI_CHECK_LAUNCH("panel_lowrank_update2");
+    count_launches(1);
+    return 0;
+}
+
+
+// ------------------------------------------------------------------ P[m x c] += T[m x q] W[q x c]   (q <= 32)
+// The column-sharded copy of the root panel follows the rank-q update through the m x q vector T = L p gathered from all
+// ranks: one streaming pass (16-byte vectors, W in shared memory), HBM-bound.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) outer_add_kernel(T* __restrict__ P, int64_t m, int64_t c, const T* __restrict__ Tv,
+                                                        int q, const T* __restrict__ W) {
+    extern __shared__ __align__(16) unsigned char smem_oa[];
+    T* Ws = reinterpret_cast<T*>(smem_oa);          // [q][c]
+    for (int64_t e = threadIdx.x; e < (int64_t)q * c; e += blockDim.x) Ws[e] = W[e];
+    __syncthreads();
+    using V = VecT<T, VEC>;
+    const int64_t vec_per_row = c / VEC;
+    const int64_t total = m * vec_per_row;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = e / vec_per_row, j = (e - row * vec_per_row) * VEC;
+        V x = *reinterpret_cast<const V*>(P + row * c + j);
+        for (int k = 0; k < q; ++k) {
+            const T t = Tv[row * q + k];
+            const V w = *reinterpret_cast<const V*>(Ws + (int64_t)k * c + j);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) x.v[v] += t * w.v[v];
+        }
+        *reinterpret_cast<V*>(P + row * c + j) = x;
+    }
+}
+template <typename T>
+static int outer_add(T* P, int64_t m, int64_t c, const T* Tv, int64_t q, const T* W, void* stream) {
+    WISKI_CHECK_ARG(m >= 0 && c >= 1 && q >= 1 && q <= 32, "panel_outer_add: need 1 <= q <= 32 (q=%lld)", (long long)q);
+    if (m == 0) return 0;
+    const size_t smem = (size_t)q * c * sizeof(T);
+    WISKI_CHECK_ARG(smem <= 200 * 1024, "panel_outer_add: q x c coefficients do not fit in shared memory");
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const bool vec = c % VEC == 0 && (reinterpret_cast<uintptr_t>(P) & 15) == 0;
+    auto kfn = vec ? outer_add_kernel<T, VEC> : outer_add_kernel<T, 1>;
+    if (smem > 48 * 1024)
+        WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "outer_add(attr)");
+    const int64_t work = m * (c / (vec ? VEC : 1));
+    int64_t blocks = ceil_div(work, 256 * 4);
+    if (blocks > (int64_t)kNumSMs * 8) blocks = (int64_t)kNumSMs * 8;
+    if (blocks < 1) blocks = 1;
+    kfn<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(P, m, c, Tv, (int)q, W);
+    WISKI_CHECK_LAUNCH("panel_outer_add");
     count_launches(1);
     return 0;
 }
@@ -780,6 +835,20 @@ int wiski_panel_lowrank_update_f32(float* P, int64_t m, int64_t r, const float* 
 int wiski_panel_lowrank_update2_f32(float* P0, float* P1, int64_t m, int64_t r, const float* U, const float* Vt0,
                                     const float* Vt1, int64_t q, void* stream) {
     return wiski::lowrank_update2<float>(P0, P1, m, r, U, Vt0, Vt1, q, stream);
+}
+int wiski_panel_lowrank_update2_t_f32(float* P0, float* P1, int64_t m, int64_t r, const float* U, const float* Vt0,
+                                      const float* Vt1, int64_t q, float* Tout, void* stream) {
+    return wiski::lowrank_update2<float>(P0, P1, m, r, U, Vt0, Vt1, q, stream, Tout);
+}
+int wiski_panel_lowrank_update2_t_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
+                                      const double* Vt1, int64_t q, double* Tout, void* stream) {
+    return wiski::lowrank_update2<double>(P0, P1, m, r, U, Vt0, Vt1, q, stream, Tout);
+}
+int wiski_panel_outer_add_f32(float* P, int64_t m, int64_t c, const float* T, int64_t q, const float* W, void* stream) {
+    return wiski::outer_add<float>(P, m, c, T, q, W, stream);
+}
+int wiski_panel_outer_add_f64(double* P, int64_t m, int64_t c, const double* T, int64_t q, const double* W, void* stream) {
+    return wiski::outer_add<double>(P, m, c, T, q, W, stream);
 }
 int wiski_panel_lowrank_update2_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
                                     const double* Vt1, int64_t q, void* stream) {

@@ -716,7 +716,7 @@ def panel_lowrank_update_(P, U, Vt):
     return P
 
 
-def panel_lowrank_update2_(P0, P1, U, Vt0, Vt1):
+def panel_lowrank_update2_(P0, P1, U, Vt0, Vt1, return_t=False):
     """In place, one launch: P0 <- P0 + (P0 @ U) @ Vt0 and P1 <- P1 + (P1 @ U) @ Vt1 (the root / inverse-root pair of the
     rank-q update; U [r,q] shared, Vt [q,r]).  q > 32 is applied in column blocks of 32 — exact, because
     I + U Vt is only ever used here with Vt = C U^T blocks that the callers already chunk; see ``_apply``."""
@@ -725,9 +725,24 @@ def panel_lowrank_update2_(P0, P1, U, Vt0, Vt1):
         raise ValueError("panel_lowrank_update2_: panels must be contiguous and of equal shape")
     m, r = P0.shape
     q = U.shape[1]
+    if return_t:            # also hand back P0 @ U of the rows before the update (by-product of the same pass)
+        T = torch.empty(m, q, dtype=P0.dtype, device=P0.device)
+        _call("wiski_panel_lowrank_update2_t", P0.dtype, _ptr(P0), _ptr(P1), m, r, _ptr(U.contiguous()), _ptr(Vt0.contiguous()),
+              _ptr(Vt1.contiguous()), q, _ptr(T), _stream())
+        return P0, P1, T
     _call("wiski_panel_lowrank_update2", P0.dtype, _ptr(P0), _ptr(P1), m, r, _ptr(U.contiguous()), _ptr(Vt0.contiguous()),
           _ptr(Vt1.contiguous()), q, _stream())
     return P0, P1
+
+
+def panel_outer_add_(P, T, W):
+    """In place, one streaming pass: P [m,c] += T [m,q] @ W [q,c] (q <= 32)."""
+    _require_cuda(P, T, W)
+    if not P.is_contiguous() or T.shape[0] != P.shape[0] or W.shape != (T.shape[1], P.shape[1]):
+        raise ValueError("panel_outer_add_: P [m,c] contiguous, T [m,q], W [q,c]")
+    m, c = P.shape
+    _call("wiski_panel_outer_add", P.dtype, _ptr(P), m, c, _ptr(T.contiguous()), T.shape[1], _ptr(W.contiguous()), _stream())
+    return P
 
 
 def q_matvec(L, KL, v):

@@ -750,16 +750,14 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             C, Cp = _sym_factors(p)
             CpT = C @ p.t()
             if self.Lc is not None:
-                # the same update on the column-sharded copy: L p for ALL rows (all-gather of an m x q vector), then
-                # Lc += (L p) (C p^T)[:, my columns]
+                # the same update on the column-sharded copy: L p for ALL rows — a by-product of the rank-q launch on the
+                # row slab, all-gathered as an m x q vector — then Lc += (L p) (C p^T)[:, my columns]
                 cw = self.Lc.shape[1]
-                t_full = self.comm.allgather(ops.panel_rmul(self.L_loc, p)).reshape(self.plan.m, p.shape[1])
-                w = CpT[:, self.comm.rank * cw:(self.comm.rank + 1) * cw]
-                if p.shape[1] == 1:
-                    self.Lc.addcmul_(t_full, w)          # rank-1: one streaming pass (the SIMT sgemm of addmm takes 1.7x as long)
-                else:
-                    self.Lc.addmm_(t_full, w)
-            ops.panel_lowrank_update2_(self.L_loc, self.B_loc, p, CpT, Cp @ p.t())
+                _, _, t_loc = ops.panel_lowrank_update2_(self.L_loc, self.B_loc, p, CpT, Cp @ p.t(), return_t=True)
+                t_full = self.comm.allgather(t_loc).reshape(self.plan.m, p.shape[1])
+                ops.panel_outer_add_(self.Lc, t_full, CpT[:, self.comm.rank * cw:(self.comm.rank + 1) * cw].contiguous())
+            else:
+                ops.panel_lowrank_update2_(self.L_loc, self.B_loc, p, CpT, Cp @ p.t())
 
     # ---- pieces with grad (Kuu / sigma^2, K L, Q, K b, c)  — batched_fixed_noise_online_gp.py:334-366
     def _noise(self):

@@ -245,6 +245,24 @@ def test_lowrank_update_both_panels_one_launch(dt, m, r, q):
     ops.panel_lowrank_update2_(g0, g1, U.to(DEV), V0.to(DEV), V1.to(DEV))
     tol = _tol(dt) if dt == torch.float64 else dict(rtol=1e-4, atol=1e-4)
     assert torch.allclose(g0.cpu().double(), r0, **tol) and torch.allclose(g1.cpu().double(), r1, **tol)
+    # the same launch with its by-product: P0 @ U of the rows before the update
+    g0, g1 = P0.to(DEV).clone(), P1.to(DEV).clone()
+    _, _, T = ops.panel_lowrank_update2_(g0, g1, U.to(DEV), V0.to(DEV), V1.to(DEV), return_t=True)
+    assert torch.allclose(g0.cpu().double(), r0, **tol) and torch.allclose(g1.cpu().double(), r1, **tol)
+    assert torch.allclose(T.cpu().double(), P0.double() @ U.double(), **tol)
+
+
+@pytest.mark.parametrize("dt", DT)
+@pytest.mark.parametrize("m,c,q", [(4096, 224, 1), (1000, 64, 3), (777, 30, 8), (2048, 432, 32)])
+def test_panel_outer_add(dt, m, c, q):
+    ops = _ops()
+    gen = torch.Generator().manual_seed(9)
+    P = torch.randn(m, c, generator=gen, dtype=dt)
+    T = torch.randn(m, q, generator=gen, dtype=dt)
+    W = torch.randn(q, c, generator=gen, dtype=dt)
+    got = ops.panel_outer_add_(P.clone().to(DEV), T.to(DEV), W.to(DEV)).cpu()
+    ref = P.double() + T.double() @ W.double()
+    assert torch.allclose(got.double(), ref, **(dict(rtol=1e-12, atol=1e-12) if dt == torch.float64 else dict(rtol=1e-5, atol=1e-5)))
 
 
 @pytest.mark.parametrize("m,r", [(4096, 128), (5000, 432), (2048, 512), (3000, 256)])
