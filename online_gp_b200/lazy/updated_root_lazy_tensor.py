@@ -63,6 +63,16 @@ def _sym_factors_iterative(p, iters=18):
     return C, -((Z / rc) @ C)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 class UpdatedRootLazyTensor(LazyTensor):
     def __init__(self, initial_tensor=None, n_shape=None, initial_is_root=True, root=None, inv_root=None):
         r"""
@@ -176,8 +186,48 @@ class UpdatedRootLazyTensor(LazyTensor):
         root, inv_root = self.collect_vector(vector)
         return UpdatedRootLazyTensor(tensor, initial_is_root=False, root=root, inv_root=inv_root)
 
+    # ---- settings.overlap_root_update: inverse-root half of an in-place rank-q update on a side stream
+    def prestart_update_sparse(self, idx, vval):
+        """First half of ``update_sparse(idx, vval, inplace=True)``: projections p = B^T v and the square-root factors on
+        the current stream, then the in-place update of the inverse-root panel on a side stream.  The caller MUST follow
+        up with ``update_sparse(idx, vval, inplace=True)`` (same stencils), which joins the side stream and updates the
+        root panel.  Returns False (nothing started) when the update does not have the one-block row-local form."""
+        self.root_decomposition()
+        self.root_inv_decomposition()
+        if (getattr(self, "_pending", None) is not None or self.tensor is not None or not self.inv_root.is_cuda
+                or settings.root_update_mode.value() != "sym" or not 1 <= idx.shape[0] <= 32):
+            return False
+        vval = vval.detach()
+        Bs = self._panels(self.inv_root)
+        vvs = [vval] * len(Bs) if vval.dim() == 2 else list(vval.reshape(-1, *vval.shape[-2:]))
+        ps = [ops.left_interp(idx, vv, B).t().contiguous() for B, vv in zip(Bs, vvs)]
+        facs = [_sym_factors(p) for p in ps]
+        coef = [(p, (C @ p.t()).contiguous(), (Cp @ p.t()).contiguous()) for p, (C, Cp) in zip(ps, facs)]
+        main = torch.cuda.current_stream()
+        side = _side_stream(self.inv_root.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            for B, (p, _, CppT) in zip(Bs, coef):
+                ops.panel_lowrank_update1_(B, p, CppT)
+        self._pending = (idx, coef, side)
+        return True
+
+    def _finish_pending(self, idx):
+        pend_idx, coef, side = self._pending
+        self._pending = None
+        torch.cuda.current_stream().wait_stream(side)
+        if pend_idx.shape != idx.shape or pend_idx.data_ptr() != idx.data_ptr():
+            raise RuntimeError("update_sparse: a pre-started update is pending for other stencils")
+        for L, (p, CpT, _) in zip(self._panels(self.root), coef):
+            ops.panel_lowrank_update1_(L, p, CpT)
+        return self
+
     def update_sparse(self, idx, vval, inplace=False):
         """v = W^T D^-1/2 given by its stencils: idx [q,s] (shared by all outputs), vval [q,s] or [t,q,s]."""
+        if getattr(self, "_pending", None) is not None:
+            if not inplace:
+                raise RuntimeError("update_sparse: a pre-started in-place update is pending")
+            return self._finish_pending(idx)
         self.root_decomposition()
         self.root_inv_decomposition()
         vval = vval.detach()             # the panels are state, not part of any autograd graph

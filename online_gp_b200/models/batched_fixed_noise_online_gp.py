@@ -440,6 +440,23 @@ class FixedNoiseOnlineSKIGP(GP):
         return MultivariateNormal(pred_mean, pred_cov)
 
     # ------------------------------------------------------------------ conditioning
+    def prestart_condition(self, X, Y, noise=None):
+        """settings.overlap_root_update: start the inverse-root half of the in-place conditioning on (X, Y) on a side
+        stream (see ``UpdatedRootLazyTensor.prestart_update_sparse``).  Must be followed by
+        ``condition_on_observations(X, Y, noise, inplace=True)`` with the same arguments."""
+        if noise is None:
+            noise = torch.ones_like(Y)
+        idx, val = _stencils(self.covar_module(X).evaluate_kernel())
+        if (noise.shape[:-2] != self._batch_shape or noise.shape[-1] == 1) and noise.dim() < 3:
+            nd = noise.transpose(-1, -2)
+        else:
+            nd = noise
+        old = self._kernel_cache
+        if nd.dim() == 2:
+            nd = nd.expand(old["interpolation_cache"].shape[0], -1)
+        new_w_dinv = val.unsqueeze(0) / (nd.clamp_min(1e-7) ** 0.5).unsqueeze(-1)          # as in _update_cache_dicts (:163-168)
+        return old["WtW"].prestart_update_sparse(idx, new_w_dinv.contiguous())
+
     def condition_on_observations(self, X, Y, noise=None, inplace=False):
         if noise is None:
             noise = torch.ones_like(Y)

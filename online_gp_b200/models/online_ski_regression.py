@@ -162,6 +162,7 @@ class OnlineSKIRegression(torch.nn.Module):
         self._graph_phase(None)
 
         stem_loss = self._update_stem(inputs, targets) if update_stem else 0.
+        self._prestart_condition(inputs, targets)
         gp_loss = self._update_gp_tensor(inputs, targets) if update_gp else 0.
         with torch.no_grad():
             self.gp.condition_on_observations(self.stem(inputs), targets, torch.ones_like(targets), inplace=True)
@@ -176,6 +177,13 @@ class OnlineSKIRegression(torch.nn.Module):
     def _stem_has_batchnorm(self):
         # `_get_features` only exists to refresh BatchNorm statistics; without such layers it is a no-op
         return any(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in self.stem.modules())
+
+    def _prestart_condition(self, inputs, targets):
+        """settings.overlap_root_update: the inverse-root half of the conditioning that ends this step goes to a side
+        stream now, under the hyper-parameter step (features of a stem without parameters only: they cannot change)."""
+        if (settings.overlap_root_update.on() and inputs.is_cuda and not any(True for _ in self.stem.parameters())):
+            with torch.no_grad():
+                self.gp.prestart_condition(self.stem(inputs), targets, torch.ones_like(targets))
 
     def _update_gp_tensor(self, inputs, targets):
         """Adam step on -MLL (logdet value skipped, gradient kept); returns the loss as a detached device tensor."""
@@ -307,6 +315,7 @@ class OnlineSKIRegression(torch.nn.Module):
         G.load(inputs, targets)
         if G.upd is None:
             def body():
+                self._prestart_condition(G.x, G.y)
                 loss = self._update_gp_tensor(G.x, G.y)
                 with torch.no_grad():
                     self.gp.condition_on_observations(self.stem(G.x), G.y, torch.ones_like(G.y), inplace=True)

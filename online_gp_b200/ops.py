@@ -735,6 +735,17 @@ def panel_lowrank_update2_(P0, P1, U, Vt0, Vt1, return_t=False):
     return P0, P1
 
 
+def panel_lowrank_update1_(P, U, Vt):
+    """In place: P <- P + (P @ U) @ Vt through the several-rows-per-warp kernel of ``panel_lowrank_update2_`` (one panel)."""
+    _require_cuda(P, U, Vt)
+    if not P.is_contiguous():
+        raise ValueError("panel_lowrank_update1_: panel must be contiguous")
+    m, r = P.shape
+    _call("wiski_panel_lowrank_update2", P.dtype, _ptr(P), _ptr(None), m, r, _ptr(U.contiguous()), _ptr(Vt.contiguous()),
+          _ptr(None), U.shape[1], _stream())
+    return P
+
+
 def panel_outer_add_(P, T, W):
     """In place, one streaming pass: P [m,c] += T [m,q] @ W [q,c] (q <= 32)."""
     _require_cuda(P, T, W)

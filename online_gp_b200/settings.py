@@ -186,6 +186,16 @@ class backward_gemm_tf32_passes(_value_context):
     _global_value = 3
 
 
+class overlap_root_update(_feature_flag):
+    """Streaming ``update()``: the in-place rank-q update of the INVERSE-root panel B (HBM-bound, 0.8 ms at m = 2^20,
+    r = 432) does not depend on the hyper-parameter step, and nothing in that step reads B.  With this flag it is issued on
+    a side stream before the MLL backward, whose first big kernel — the 3xTF32 panel GEMM — is tensor-bound and leaves 3/4
+    of the HBM bandwidth idle; the root panel L (read by the backward) is updated afterwards as before.  Same kernels, same
+    operands, same order per panel: results are bit-identical to the serial schedule.  The fork / join is by stream events,
+    so it is captured into the CUDA graph of ``update`` like everything else."""
+    _state = True
+
+
 class kron_outer_inner_pairing(_feature_flag):
     """32^4 grids, tensor-core pair kernels: pair the grid axes as (1,2) + (0,3) instead of (0,1) + (2,3).  Every tile of the
     pair (0,1) is 1024 rows that lie 1024 rows apart (one 64-byte piece per 2 MB page); the tiles of (0,3) are 32 runs of 32

@@ -21,7 +21,7 @@ def install():
     from online_gp_b200 import ops
 
     saved = {k: getattr(ops, k) for k in ("_require_cuda", "_interp_fwd", "_gather", "_scatter_add", "_kron_mm",
-                                          "_kron_bwd_cols", "_rmul", "_gram", "panel_lowrank_update_", "panel_lowrank_update2_", "panel_outer_add_",
+                                          "_kron_bwd_cols", "_rmul", "_gram", "panel_lowrank_update_", "panel_lowrank_update2_", "panel_lowrank_update1_", "panel_outer_add_",
                                           "q_matvec",
                                           "cg_solve", "kron_axis_apply", "kron_axis_contract")}
     orig_init = ops.GridSpec.__init__
@@ -103,6 +103,7 @@ def install():
         out = (lowrank(P0, U, Vt0), lowrank(P1, U, Vt1))
         return out + (T,) if return_t else out
     ops.panel_lowrank_update2_ = lowrank2
+    ops.panel_lowrank_update1_ = lowrank
     ops.panel_outer_add_ = lambda P, T, W: P.add_(T @ W)
     ops.q_matvec = q_matvec
     ops.cg_solve = cg_solve
