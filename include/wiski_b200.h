@@ -216,6 +216,14 @@ int wiski_panel_lowrank_update2_t_f32(float* P0, float* P1, int64_t m, int64_t r
                                       const float* Vt1, int64_t q, float* Tout, void* stream);
 int wiski_panel_lowrank_update2_t_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
                                       const double* Vt1, int64_t q, double* Tout, void* stream);
+/* The same launch with its resident footprint capped at max_blocks_per_sm CTAs per SM (0 = no cap): for a launch that runs
+ * on a side stream UNDER other kernels (settings.overlap_root_update), so that it leaves the block slots, registers and
+ * shared memory the main stream's kernels need; 1 CTA per SM (8 warps x 8 rows x 16-byte loads in flight) still streams at
+ * ~2/3 of the HBM bandwidth. */
+int wiski_panel_lowrank_update2_occ_f32(float* P0, float* P1, int64_t m, int64_t r, const float* U, const float* Vt0,
+                                        const float* Vt1, int64_t q, int max_blocks_per_sm, void* stream);
+int wiski_panel_lowrank_update2_occ_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
+                                        const double* Vt1, int64_t q, int max_blocks_per_sm, void* stream);
 /* P[m,c] += T[m,q] W[q,c] in place (q <= 32), one streaming pass.  Used by the row-sharded model with the dual layout: the
  * column-sharded copy of the root panel follows the rank-q update `collect_vector` (updated_root_lazy_tensor.py:97-100)
  * through T = L p, gathered from all ranks, and W = the local columns of C p^T. */

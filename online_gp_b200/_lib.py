@@ -33,6 +33,7 @@ def _sigs(real, realp):
         "wiski_panel_lowrank_update2": [_P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _S],
         "wiski_panel_outer_add": [_P, c_int64, c_int64, _P, c_int64, _P, _S],
         "wiski_panel_lowrank_update2_t": [_P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, _S],
+        "wiski_panel_lowrank_update2_occ": [_P, _P, c_int64, c_int64, _P, _P, _P, c_int64, c_int, _S],
         "wiski_gram": [_P, _P, c_int64, c_int64, c_int64, _P, _P, _S],
         "wiski_q_matvec": [_P, _P, c_int64, c_int64, _P, c_int64, _P, _P, _S],
         "wiski_cg_solve": [_P, _P, c_int64, c_int64, _P, c_int64, real, c_int, c_int, _P, POINTER(c_int), realp, _P, _S],

@@ -586,7 +586,7 @@ static int lowrank_update(T* P, int64_t m, int64_t r, const T* U, const T* Vt, i
 // P1 / Vt1 may be NULL (single panel).  Falls back to the per-row kernel when U and Vt do not fit in shared memory.
 template <typename T>
 static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const T* Vt0, const T* Vt1, int64_t q, void* stream,
-                           T* t_out = nullptr) {
+                           T* t_out = nullptr, int max_blocks_per_sm = 0) {
     WISKI_CHECK_ARG(m >= 0 && r >= 1 && q >= 1 && q <= 32, "panel_lowrank_update2: need 1 <= q <= 32 (q=%lld)", (long long)q);
     WISKI_CHECK_ARG((P1 == nullptr) == (Vt1 == nullptr), "panel_lowrank_update2: P1 and Vt1 go together");
     if (m == 0) return 0;
@@ -608,6 +608,7 @@ static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const
         WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lowrank2(attr)"); \
         int64_t groups = ceil_div(m, ROWS) * (P1 != nullptr ? 2 : 1);                                                        \
         int per_sm = smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 4;                                                       \
+        if (max_blocks_per_sm > 0 && per_sm > max_blocks_per_sm) per_sm = max_blocks_per_sm;                                 \
         int64_t blocks = ceil_div(groups, 8);                                                                                \
         if (blocks > (int64_t)kNumSMs * per_sm) blocks = (int64_t)kNumSMs * per_sm;                                          \
         kfn<<<(unsigned)blocks, 256, smem, st>>>(P0, P1, m, r, U, Vt0, Vt1, (int)q, t_out);                                  \
@@ -843,6 +844,14 @@ int wiski_panel_lowrank_update2_t_f32(float* P0, float* P1, int64_t m, int64_t r
 int wiski_panel_lowrank_update2_t_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
                                       const double* Vt1, int64_t q, double* Tout, void* stream) {
     return wiski::lowrank_update2<double>(P0, P1, m, r, U, Vt0, Vt1, q, stream, Tout);
+}
+int wiski_panel_lowrank_update2_occ_f32(float* P0, float* P1, int64_t m, int64_t r, const float* U, const float* Vt0,
+                                        const float* Vt1, int64_t q, int max_blocks_per_sm, void* stream) {
+    return wiski::lowrank_update2<float>(P0, P1, m, r, U, Vt0, Vt1, q, stream, nullptr, max_blocks_per_sm);
+}
+int wiski_panel_lowrank_update2_occ_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
+                                        const double* Vt1, int64_t q, int max_blocks_per_sm, void* stream) {
+    return wiski::lowrank_update2<double>(P0, P1, m, r, U, Vt0, Vt1, q, stream, nullptr, max_blocks_per_sm);
 }
 int wiski_panel_outer_add_f32(float* P, int64_t m, int64_t c, const float* T, int64_t q, const float* W, void* stream) {
     return wiski::outer_add<float>(P, m, c, T, q, W, stream);

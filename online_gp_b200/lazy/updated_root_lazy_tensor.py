@@ -16,6 +16,8 @@ When r < m both drop the component of v outside span(L), exactly like the refere
 
 A leading batch dimension (one element per GP output) is supported by looping; panels are [t, m, r].
 """
+import os
+
 import torch
 
 from .. import ops, settings
@@ -208,7 +210,8 @@ class UpdatedRootLazyTensor(LazyTensor):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             for B, (p, _, CppT) in zip(Bs, coef):
-                ops.panel_lowrank_update1_(B, p, CppT)
+                # 1 CTA per SM: the main stream's kernels keep finding free block slots / registers next to it
+                ops.panel_lowrank_update1_(B, p, CppT, max_blocks_per_sm=int(os.environ.get("WISKI_OVERLAP_OCC", "1")))
         self._pending = (idx, coef, side)
         return True
 

@@ -735,14 +735,15 @@ def panel_lowrank_update2_(P0, P1, U, Vt0, Vt1, return_t=False):
     return P0, P1
 
 
-def panel_lowrank_update1_(P, U, Vt):
-    """In place: P <- P + (P @ U) @ Vt through the several-rows-per-warp kernel of ``panel_lowrank_update2_`` (one panel)."""
+def panel_lowrank_update1_(P, U, Vt, max_blocks_per_sm=0):
+    """In place: P <- P + (P @ U) @ Vt through the several-rows-per-warp kernel of ``panel_lowrank_update2_`` (one panel).
+    max_blocks_per_sm > 0 caps the launch's resident CTAs per SM (a launch meant to run under other kernels)."""
     _require_cuda(P, U, Vt)
     if not P.is_contiguous():
         raise ValueError("panel_lowrank_update1_: panel must be contiguous")
     m, r = P.shape
-    _call("wiski_panel_lowrank_update2", P.dtype, _ptr(P), _ptr(None), m, r, _ptr(U.contiguous()), _ptr(Vt.contiguous()),
-          _ptr(None), U.shape[1], _stream())
+    _call("wiski_panel_lowrank_update2_occ", P.dtype, _ptr(P), _ptr(None), m, r, _ptr(U.contiguous()), _ptr(Vt.contiguous()),
+          _ptr(None), U.shape[1], int(max_blocks_per_sm), _stream())
     return P
 
 
