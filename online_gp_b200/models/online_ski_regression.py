@@ -180,10 +180,15 @@ class OnlineSKIRegression(torch.nn.Module):
 
     def _prestart_condition(self, inputs, targets):
         """settings.overlap_root_update: the inverse-root half of the conditioning that ends this step goes to a side
-        stream now, under the hyper-parameter step (features of a stem without parameters only: they cannot change)."""
-        if (settings.overlap_root_update.on() and inputs.is_cuda and not any(True for _ in self.stem.parameters())):
-            with torch.no_grad():
-                self.gp.prestart_condition(self.stem(inputs), targets, torch.ones_like(targets))
+        stream now, under the hyper-parameter step — only when the features do not depend on trainable stem parameters
+        (then they are the same tensor values the conditioning will see after the step)."""
+        if not (settings.overlap_root_update.on() and inputs.is_cuda):
+            return
+        feats = self.stem(inputs)
+        if feats.requires_grad:
+            return
+        with torch.no_grad():
+            self.gp.prestart_condition(feats, targets, torch.ones_like(targets))
 
     def _update_gp_tensor(self, inputs, targets):
         """Adam step on -MLL (logdet value skipped, gradient kept); returns the loss as a detached device tensor."""
