@@ -609,6 +609,12 @@ static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const
         int64_t groups = ceil_div(m, ROWS) * (P1 != nullptr ? 2 : 1);                                                        \
         int per_sm = smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 4;                                                       \
         if (max_blocks_per_sm > 0 && per_sm > max_blocks_per_sm) per_sm = max_blocks_per_sm;                                 \
+        /* a launch meant to run UNDER other kernels: ask for the largest shared-memory carve-out, the configuration the    \
+           tensor-core kernels need - an SM cannot change its L1 / shared split while a CTA is resident, and with the       \
+           default split every other kernel that needs more shared memory would wait for this one to drain */              \
+        if (max_blocks_per_sm > 0)                                                                                           \
+            WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout,                      \
+                                                  (int)cudaSharedmemCarveoutMaxShared), "lowrank2(carveout)");             \
         int64_t blocks = ceil_div(groups, 8);                                                                                \
         if (blocks > (int64_t)kNumSMs * per_sm) blocks = (int64_t)kNumSMs * per_sm;                                          \
         kfn<<<(unsigned)blocks, 256, smem, st>>>(P0, P1, m, r, U, Vt0, Vt1, (int)q, t_out);                                  \
