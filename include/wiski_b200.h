@@ -153,6 +153,13 @@ int wiski_kron_fused_pair_grad_dir_lay_f32(const float* cols, const float* dirs,
  * variable WISKI_KRON_TC=0 sets the initial state) — used by the A/B timings of bench.py and the parity tests. */
 int wiski_kron_tc_enable(int on);      /* on < 0: query only */
 
+/* "Background" launches: while the flag is set, the HBM-bound panel passes (rank-q update, skinny Gram / panel product)
+ * are launched with a small resident footprint (1 - 2 CTAs per SM) and the largest shared-memory carve-out, so that the
+ * host layer can put them on a side stream UNDER a tensor-bound kernel of the main stream (settings.overlap_root_update):
+ * the persistent tcgen05 kernels still find their block slots, and no SM has to drain to change its L1 / shared split.
+ * Returns the previous state; on < 0 queries only.  Process-global (one host thread per process). */
+int wiski_set_background(int on);
+
 /* The two pair passes for ANY two 32-point grid axes axis_u < axis_v (the remaining axes are batch indices; at most two
  * of the three index groups before / between / after the pair may be non-trivial — always true for d <= 4).
  * For a 32^4 grid the host layer pairs the axes as (1,2) + (0,3) instead of (0,1) + (2,3): a tile of the pair (0,1) is
@@ -216,14 +223,6 @@ int wiski_panel_lowrank_update2_t_f32(float* P0, float* P1, int64_t m, int64_t r
                                       const float* Vt1, int64_t q, float* Tout, void* stream);
 int wiski_panel_lowrank_update2_t_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
                                       const double* Vt1, int64_t q, double* Tout, void* stream);
-/* The same launch with its resident footprint capped at max_blocks_per_sm CTAs per SM (0 = no cap): for a launch that runs
- * on a side stream UNDER other kernels (settings.overlap_root_update), so that it leaves the block slots, registers and
- * shared memory the main stream's kernels need; 1 CTA per SM (8 warps x 8 rows x 16-byte loads in flight) still streams at
- * ~2/3 of the HBM bandwidth. */
-int wiski_panel_lowrank_update2_occ_f32(float* P0, float* P1, int64_t m, int64_t r, const float* U, const float* Vt0,
-                                        const float* Vt1, int64_t q, int max_blocks_per_sm, void* stream);
-int wiski_panel_lowrank_update2_occ_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
-                                        const double* Vt1, int64_t q, int max_blocks_per_sm, void* stream);
 /* P[m,c] += T[m,q] W[q,c] in place (q <= 32), one streaming pass.  Used by the row-sharded model with the dual layout: the
  * column-sharded copy of the root panel follows the rank-q update `collect_vector` (updated_root_lazy_tensor.py:97-100)
  * through T = L p, gathered from all ranks, and W = the local columns of C p^T. */

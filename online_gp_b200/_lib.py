@@ -33,7 +33,6 @@ def _sigs(real, realp):
         "wiski_panel_lowrank_update2": [_P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _S],
         "wiski_panel_outer_add": [_P, c_int64, c_int64, _P, c_int64, _P, _S],
         "wiski_panel_lowrank_update2_t": [_P, _P, c_int64, c_int64, _P, _P, _P, c_int64, _P, _S],
-        "wiski_panel_lowrank_update2_occ": [_P, _P, c_int64, c_int64, _P, _P, _P, c_int64, c_int, _S],
         "wiski_gram": [_P, _P, c_int64, c_int64, c_int64, _P, _P, _S],
         "wiski_q_matvec": [_P, _P, c_int64, c_int64, _P, c_int64, _P, _P, _S],
         "wiski_cg_solve": [_P, _P, c_int64, c_int64, _P, c_int64, real, c_int, c_int, _P, POINTER(c_int), realp, _P, _S],
@@ -49,7 +48,7 @@ EXPORTED = ["wiski_last_error", "wiski_abi_version", "wiski_launch_count", "wisk
             "wiski_kron_fused_pair_grad_dir_lay_f32", "wiski_kron_tc_enable", "wiski_gram_sym_f32",
             "wiski_panel_rmul_ex_f32", "wiski_gram_chunked_sym_f32",
             "wiski_kron_pair_apply_axes_f32", "wiski_kron_pair_grad_dir_axes_f32", "wiski_panel_rmul_ex_work_elems",
-            "wiski_kron_pair_apply_push_f32", "wiski_kron_pair_grad_dir_push_f32", "wiski_panel_rmul_push_f32"] + [
+            "wiski_set_background", "wiski_kron_pair_apply_push_f32", "wiski_kron_pair_grad_dir_push_f32", "wiski_panel_rmul_push_f32"] + [
     f"{n}_{sfx}" for n in _sigs(c_float, POINTER(c_float)) for sfx in ("f32", "f64")]
 
 
@@ -104,6 +103,8 @@ def load():
     lib.wiski_panel_rmul_ex_f32.argtypes = [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, _P, _P, _S]
     lib.wiski_panel_rmul_ex_work_elems.restype = c_int64
     lib.wiski_panel_rmul_ex_work_elems.argtypes = [c_int64, c_int64]
+    lib.wiski_set_background.restype = c_int
+    lib.wiski_set_background.argtypes = [c_int]
     lib.wiski_kron_tc_enable.restype = c_int
     lib.wiski_kron_tc_enable.argtypes = [c_int]
     lib.wiski_kron_fused_pair_apply_lay_f32.restype = c_int

@@ -38,6 +38,19 @@ void count_launches(int n);   // kernels enqueued by this library (bench.py repo
 
 constexpr int kNumSMs = 148;  // B200
 
+// "Background" launches (wiski_set_background): HBM-bound passes the host layer puts on a side stream UNDER a tensor-bound
+// kernel (settings.overlap_root_update).  They keep a small resident footprint (1 - 2 CTAs per SM) so that the persistent
+// tcgen05 kernels and the latency-bound r x r chain still find block slots, registers and shared memory, and they ask for
+// the largest shared-memory carve-out — the split the tensor-core kernels need: an SM cannot change its L1 / shared split
+// while any CTA is resident, so with the default split every kernel that needs more shared memory would wait for the
+// background launch to drain (measured: the main stream stalled for the full 0.8 ms).
+int background_mode();
+template <typename K>
+static inline cudaError_t apply_background_carveout(K kfn) {
+    return cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                background_mode() ? (int)cudaSharedmemCarveoutMaxShared : (int)cudaSharedmemCarveoutDefault);
+}
+
 // Destinations of a launch that pushes its result into the peers' (NVLink-mapped) buffers; see kron_tc.cu (PushMaps)
 // and gemm_tc.cu (o_ptrs).  dst[j] = where this rank's part starts in rank j's buffer.
 struct PushDst {

@@ -19,6 +19,8 @@ void set_error(const char* fmt, ...) {
 
 static long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+static int g_background = 0;
+int background_mode() { return g_background; }
 
 template <typename T>
 struct InterpParams {
@@ -296,6 +298,11 @@ extern "C" {
 const char* wiski_last_error(void) { return wiski::g_err; }
 int wiski_abi_version(void) { return 1; }
 long long wiski_launch_count(void) { return __atomic_load_n(&wiski::g_launches, __ATOMIC_RELAXED); }
+int wiski_set_background(int on) {
+    const int prev = wiski::g_background;
+    if (on >= 0) wiski::g_background = on != 0;
+    return prev;
+}
 
 int wiski_interp_fwd_f32(const float* x, int64_t q, int d, const int64_t* h_g, const float* h_lo,
                          const float* h_delta, const float* h_first4, const float* h_last4, const float* h_gmin,

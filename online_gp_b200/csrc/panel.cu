@@ -548,8 +548,12 @@ static int panel_rmul(const T* P, int64_t m, int64_t r, const T* M, int64_t r2, 
     cudaStream_t st = as_stream(stream);
     if (r2 <= 8) {
         int64_t blocks = ceil_div(m, 8);
-        if (blocks > (int64_t)kNumSMs * 16) blocks = (int64_t)kNumSMs * 16;
-        if (r2 == 1) rmul_skinny_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(P, M, Out, m, r, (int)r2);
+        const int64_t cap = (int64_t)kNumSMs * (background_mode() ? 2 : 16);
+        if (blocks > cap) blocks = cap;
+        if (r2 == 1) {
+            WISKI_CHECK_CUDA(apply_background_carveout(rmul_skinny_kernel<T, 1>), "panel_rmul(carveout)");
+            rmul_skinny_kernel<T, 1><<<(unsigned)blocks, 256, 0, st>>>(P, M, Out, m, r, (int)r2);
+        }
         else if (r2 <= 2) rmul_skinny_kernel<T, 2><<<(unsigned)blocks, 256, 0, st>>>(P, M, Out, m, r, (int)r2);
         else if (r2 <= 4) rmul_skinny_kernel<T, 4><<<(unsigned)blocks, 256, 0, st>>>(P, M, Out, m, r, (int)r2);
         else rmul_skinny_kernel<T, 8><<<(unsigned)blocks, 256, 0, st>>>(P, M, Out, m, r, (int)r2);
@@ -586,7 +590,7 @@ static int lowrank_update(T* P, int64_t m, int64_t r, const T* U, const T* Vt, i
 // P1 / Vt1 may be NULL (single panel).  Falls back to the per-row kernel when U and Vt do not fit in shared memory.
 template <typename T>
 static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const T* Vt0, const T* Vt1, int64_t q, void* stream,
-                           T* t_out = nullptr, int max_blocks_per_sm = 0) {
+                           T* t_out = nullptr) {
     WISKI_CHECK_ARG(m >= 0 && r >= 1 && q >= 1 && q <= 32, "panel_lowrank_update2: need 1 <= q <= 32 (q=%lld)", (long long)q);
     WISKI_CHECK_ARG((P1 == nullptr) == (Vt1 == nullptr), "panel_lowrank_update2: P1 and Vt1 go together");
     if (m == 0) return 0;
@@ -608,13 +612,8 @@ static int lowrank_update2(T* P0, T* P1, int64_t m, int64_t r, const T* U, const
         WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "lowrank2(attr)"); \
         int64_t groups = ceil_div(m, ROWS) * (P1 != nullptr ? 2 : 1);                                                        \
         int per_sm = smem > 100 * 1024 ? 1 : smem > 48 * 1024 ? 2 : 4;                                                       \
-        if (max_blocks_per_sm > 0 && per_sm > max_blocks_per_sm) per_sm = max_blocks_per_sm;                                 \
-        /* a launch meant to run UNDER other kernels: ask for the largest shared-memory carve-out, the configuration the    \
-           tensor-core kernels need - an SM cannot change its L1 / shared split while a CTA is resident, and with the       \
-           default split every other kernel that needs more shared memory would wait for this one to drain */              \
-        if (max_blocks_per_sm > 0)                                                                                           \
-            WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout,                      \
-                                                  (int)cudaSharedmemCarveoutMaxShared), "lowrank2(carveout)");             \
+        if (background_mode()) per_sm = 1;                                                                                   \
+        WISKI_CHECK_CUDA(apply_background_carveout(kfn), "lowrank2(carveout)");                                              \
         int64_t blocks = ceil_div(groups, 8);                                                                                \
         if (blocks > (int64_t)kNumSMs * per_sm) blocks = (int64_t)kNumSMs * per_sm;                                          \
         kfn<<<(unsigned)blocks, 256, smem, st>>>(P0, P1, m, r, U, Vt0, Vt1, (int)q, t_out);                                  \
@@ -688,7 +687,8 @@ static inline int64_t gram_splits(int64_t m, int64_t r, int64_t r2) {
 }
 static inline int64_t gram_skinny_blocks(int64_t m) {
     int64_t nb = ceil_div(m, 64);
-    if (nb > (int64_t)kNumSMs * 4) nb = (int64_t)kNumSMs * 4;
+    const int64_t cap = (int64_t)kNumSMs * (background_mode() ? 1 : 4);
+    if (nb > cap) nb = cap;
     if (nb < 1) nb = 1;
     return nb;
 }
@@ -705,6 +705,7 @@ static int gram(const T* A, const T* Bm, int64_t m, int64_t r, int64_t r2, T* G,
 #define GSW(RJ, NP)                                                                                            \
     do {                                                                                                       \
         auto kfn = gram_skinny_warp_kernel<T, RJ, NP>;                                                         \
+        WISKI_CHECK_CUDA(apply_background_carveout(kfn), "gram(carveout)");                                    \
         if (smem > 48 * 1024)                                                                                  \
             WISKI_CHECK_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), \
                              "gram(attr)");                                                                    \
@@ -850,14 +851,6 @@ int wiski_panel_lowrank_update2_t_f32(float* P0, float* P1, int64_t m, int64_t r
 int wiski_panel_lowrank_update2_t_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
                                       const double* Vt1, int64_t q, double* Tout, void* stream) {
     return wiski::lowrank_update2<double>(P0, P1, m, r, U, Vt0, Vt1, q, stream, Tout);
-}
-int wiski_panel_lowrank_update2_occ_f32(float* P0, float* P1, int64_t m, int64_t r, const float* U, const float* Vt0,
-                                        const float* Vt1, int64_t q, int max_blocks_per_sm, void* stream) {
-    return wiski::lowrank_update2<float>(P0, P1, m, r, U, Vt0, Vt1, q, stream, nullptr, max_blocks_per_sm);
-}
-int wiski_panel_lowrank_update2_occ_f64(double* P0, double* P1, int64_t m, int64_t r, const double* U, const double* Vt0,
-                                        const double* Vt1, int64_t q, int max_blocks_per_sm, void* stream) {
-    return wiski::lowrank_update2<double>(P0, P1, m, r, U, Vt0, Vt1, q, stream, nullptr, max_blocks_per_sm);
 }
 int wiski_panel_outer_add_f32(float* P, int64_t m, int64_t c, const float* T, int64_t q, const float* W, void* stream) {
     return wiski::outer_add<float>(P, m, c, T, q, W, stream);

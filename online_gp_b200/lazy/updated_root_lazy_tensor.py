@@ -16,8 +16,6 @@ When r < m both drop the component of v outside span(L), exactly like the refere
 
 A leading batch dimension (one element per GP output) is supported by looping; panels are [t, m, r].
 """
-import os
-
 import torch
 
 from .. import ops, settings
@@ -63,16 +61,6 @@ def _sym_factors_iterative(p, iters=18):
     rc = c.sqrt()
     C, _ = torch.linalg.inv_ex(eye + Y * rc)
     return C, -((Z / rc) @ C)
-
-
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    key = (device.type, device.index)
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
-    return _SIDE_STREAMS[key]
 
 
 class UpdatedRootLazyTensor(LazyTensor):
@@ -206,12 +194,11 @@ class UpdatedRootLazyTensor(LazyTensor):
         facs = [_sym_factors(p) for p in ps]
         coef = [(p, (C @ p.t()).contiguous(), (Cp @ p.t()).contiguous()) for p, (C, Cp) in zip(ps, facs)]
         main = torch.cuda.current_stream()
-        side = _side_stream(self.inv_root.device)
+        side = ops.side_stream(self.inv_root.device)
         side.wait_stream(main)
-        with torch.cuda.stream(side):
+        with torch.cuda.stream(side), ops.background():
             for B, (p, _, CppT) in zip(Bs, coef):
-                # 1 CTA per SM: the main stream's kernels keep finding free block slots / registers next to it
-                ops.panel_lowrank_update1_(B, p, CppT, max_blocks_per_sm=int(os.environ.get("WISKI_OVERLAP_OCC", "1")))
+                ops.panel_lowrank_update1_(B, p, CppT)
         self._pending = (idx, coef, side)
         return True
 

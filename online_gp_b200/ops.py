@@ -678,16 +678,18 @@ class _GramFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, B, symmetric=False):
         ctx.save_for_backward(A, B)
+        ctx.bg = is_background()         # forward ran as a background pass on a side stream: so does the backward
         return _gram(A, B, symmetric)
 
     @staticmethod
     def backward(ctx, gG):
         A, B = ctx.saved_tensors
         gA = gB = None
-        if ctx.needs_input_grad[0]:
-            gA = _rmul(B, gG.t().contiguous(), _bwd_terms())
-        if ctx.needs_input_grad[1]:
-            gB = _rmul(A, gG.contiguous(), _bwd_terms())
+        with background(ctx.bg):
+            if ctx.needs_input_grad[0]:
+                gA = _rmul(B, gG.t().contiguous(), _bwd_terms())
+            if ctx.needs_input_grad[1]:
+                gB = _rmul(A, gG.contiguous(), _bwd_terms())
         return gA, gB, None
 
 
@@ -735,15 +737,45 @@ def panel_lowrank_update2_(P0, P1, U, Vt0, Vt1, return_t=False):
     return P0, P1
 
 
-def panel_lowrank_update1_(P, U, Vt, max_blocks_per_sm=0):
-    """In place: P <- P + (P @ U) @ Vt through the several-rows-per-warp kernel of ``panel_lowrank_update2_`` (one panel).
-    max_blocks_per_sm > 0 caps the launch's resident CTAs per SM (a launch meant to run under other kernels)."""
+class background:
+    """Context manager: library launches inside run in "background" form (small resident footprint, largest shared-memory
+    carve-out; ``wiski_set_background``) — for HBM-bound passes put on a side stream under a tensor-bound kernel."""
+
+    def __init__(self, on=True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = _lib.load().wiski_set_background(1 if self.on else 0)
+        return self
+
+    def __exit__(self, *exc):
+        _lib.load().wiski_set_background(self.prev)
+        return False
+
+
+def is_background():
+    return bool(_lib.load().wiski_set_background(-1))
+
+
+_SIDE_STREAMS = {}
+
+
+def side_stream(device):
+    """The one side stream per device used by the overlap schedules (settings.overlap_root_update)."""
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
+def panel_lowrank_update1_(P, U, Vt):
+    """In place: P <- P + (P @ U) @ Vt through the several-rows-per-warp kernel of ``panel_lowrank_update2_`` (one panel)."""
     _require_cuda(P, U, Vt)
     if not P.is_contiguous():
         raise ValueError("panel_lowrank_update1_: panel must be contiguous")
     m, r = P.shape
-    _call("wiski_panel_lowrank_update2_occ", P.dtype, _ptr(P), _ptr(None), m, r, _ptr(U.contiguous()), _ptr(Vt.contiguous()),
-          _ptr(None), U.shape[1], int(max_blocks_per_sm), _stream())
+    _call("wiski_panel_lowrank_update2", P.dtype, _ptr(P), _ptr(None), m, r, _ptr(U.contiguous()), _ptr(Vt.contiguous()),
+          _ptr(None), U.shape[1], _stream())
     return P
 
 

@@ -103,7 +103,7 @@ def install():
         out = (lowrank(P0, U, Vt0), lowrank(P1, U, Vt1))
         return out + (T,) if return_t else out
     ops.panel_lowrank_update2_ = lowrank2
-    ops.panel_lowrank_update1_ = lambda P, U, Vt, max_blocks_per_sm=0: lowrank(P, U, Vt)
+    ops.panel_lowrank_update1_ = lowrank
     ops.panel_outer_add_ = lambda P, T, W: P.add_(T @ W)
     ops.q_matvec = q_matvec
     ops.cg_solve = cg_solve
