@@ -768,12 +768,18 @@ def side_stream(device):
     return _SIDE_STREAMS[key]
 
 
-def panel_lowrank_update1_(P, U, Vt):
-    """In place: P <- P + (P @ U) @ Vt through the several-rows-per-warp kernel of ``panel_lowrank_update2_`` (one panel)."""
+def panel_lowrank_update1_(P, U, Vt, return_t=False):
+    """In place: P <- P + (P @ U) @ Vt through the several-rows-per-warp kernel of ``panel_lowrank_update2_`` (one panel);
+    return_t: also P @ U of the rows before the update."""
     _require_cuda(P, U, Vt)
     if not P.is_contiguous():
         raise ValueError("panel_lowrank_update1_: panel must be contiguous")
     m, r = P.shape
+    if return_t:
+        T = torch.empty(m, U.shape[1], dtype=P.dtype, device=P.device)
+        _call("wiski_panel_lowrank_update2_t", P.dtype, _ptr(P), _ptr(None), m, r, _ptr(U.contiguous()), _ptr(Vt.contiguous()),
+              _ptr(None), U.shape[1], _ptr(T), _stream())
+        return P, T
     _call("wiski_panel_lowrank_update2", P.dtype, _ptr(P), _ptr(None), m, r, _ptr(U.contiguous()), _ptr(Vt.contiguous()),
           _ptr(None), U.shape[1], _stream())
     return P

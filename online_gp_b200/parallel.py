@@ -590,6 +590,19 @@ class _ShardedGramFn(torch.autograd.Function):
         return None, ops._rmul(A, gG.contiguous(), ops._bwd_terms()), None
 
 
+class _AllReduceFwdFn(torch.autograd.Function):
+    """Sum of per-rank partials whose consumers are replicated: all-reduce forward, identity backward (every rank holds the
+    full gradient of the sum already, and its partial enters the sum with weight one)."""
+
+    @staticmethod
+    def forward(ctx, t, comm):
+        return comm.allreduce_(t.contiguous().clone())
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
 class _ShardSliceFn(torch.autograd.Function):
     """Replicated full vector -> my slab; backward all-gathers the slab gradients so the replicated graph upstream
     receives the complete gradient on every rank."""
@@ -677,6 +690,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
                 self.comm.enable_peer_exchange(self.L_loc.numel(), self.dtype, init_x.device)
         if self.comm.world > 1 and init_x.is_cuda and self.dtype == torch.float32:
             self.comm.enable_fast_allreduce(init_x.device)
+        self._pending_root = None    # (p, C p^T) of a pre-started rank-q update (_prestart_root_update)
         self._graphs = None          # opt-in CUDA-graph replay: enable_cuda_graphs()
         self._n_t = None             # device-side copy of num_data (graph mode)
 
@@ -744,20 +758,48 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
 
     def _root_update(self, idx_l, vval_l):
         """collect_vector (updated_root_lazy_tensor.py:69-119), symmetric-square-root form, panels updated in place."""
+        pend, self._pending_root = self._pending_root, None
         for s0 in range(0, idx_l.shape[0], 32):
-            pT = self.comm.allreduce_(ops.left_interp(idx_l[s0:s0 + 32], vval_l[s0:s0 + 32], self.B_loc))
-            p = pT.t().contiguous()
-            C, Cp = _sym_factors(p)
-            CpT = C @ p.t()
+            if pend is not None:
+                p, CpT = pend                      # inverse-root half already under way on the side stream (_prestart_root_update)
+                torch.cuda.current_stream().wait_stream(ops.side_stream(self.L_loc.device))
+            else:
+                pT = self.comm.allreduce_(ops.left_interp(idx_l[s0:s0 + 32], vval_l[s0:s0 + 32], self.B_loc))
+                p = pT.t().contiguous()
+                C, Cp = _sym_factors(p)
+                CpT = C @ p.t()
             if self.Lc is not None:
                 # the same update on the column-sharded copy: L p for ALL rows — a by-product of the rank-q launch on the
                 # row slab, all-gathered as an m x q vector — then Lc += (L p) (C p^T)[:, my columns]
                 cw = self.Lc.shape[1]
-                _, _, t_loc = ops.panel_lowrank_update2_(self.L_loc, self.B_loc, p, CpT, Cp @ p.t(), return_t=True)
+                if pend is not None:
+                    _, t_loc = ops.panel_lowrank_update1_(self.L_loc, p, CpT, return_t=True)
+                else:
+                    _, _, t_loc = ops.panel_lowrank_update2_(self.L_loc, self.B_loc, p, CpT, Cp @ p.t(), return_t=True)
                 t_full = self.comm.allgather(t_loc).reshape(self.plan.m, p.shape[1])
                 ops.panel_outer_add_(self.Lc, t_full, CpT[:, self.comm.rank * cw:(self.comm.rank + 1) * cw].contiguous())
+            elif pend is not None:
+                ops.panel_lowrank_update1_(self.L_loc, p, CpT)
             else:
                 ops.panel_lowrank_update2_(self.L_loc, self.B_loc, p, CpT, Cp @ p.t())
+
+    def _prestart_root_update(self, x):
+        """settings.overlap_root_update: projection and factors of the rank-q update that ends this step now, the in-place
+        update of the inverse-root slab on a side stream (background launch) under the hyper-parameter step, which never
+        reads it.  ``_root_update`` then joins and updates the root slab.  One block of q <= 32 points only."""
+        if not (settings.overlap_root_update.on() and x.is_cuda and 1 <= x.shape[0] <= 32) or self._pending_root is not None:
+            return
+        with torch.no_grad():
+            idx_l, val_l = self._stencils(x)                 # D = 1 in the streaming update (online_ski_regression.py:122)
+            pT = self.comm.allreduce_(ops.left_interp(idx_l, val_l, self.B_loc))
+            p = pT.t().contiguous()
+            C, Cp = _sym_factors(p)
+            CpT, CppT = (C @ p.t()).contiguous(), (Cp @ p.t()).contiguous()
+            main, side = torch.cuda.current_stream(), ops.side_stream(self.B_loc.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), ops.background():
+                ops.panel_lowrank_update1_(self.B_loc, p, CppT)
+            self._pending_root = (p, CpT)
 
     # ---- pieces with grad (Kuu / sigma^2, K L, Q, K b, c)  — batched_fixed_noise_online_gp.py:334-366
     def _noise(self):
@@ -786,11 +828,24 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         else:
             KL = _ShardedKronFn.apply(cols, self.L_loc, plan, comm, dirs)         # :348  column blocks [nb, m_loc, r / nb]
         r = self.L_loc.shape[1]
-        Q = _ShardedGramBlocksFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355
         b_full = self.b_full
         Kb_full = ops.kron_toeplitz_matmul(cols, plan.sizes, b_full)              # :366
         Kb = _ShardSliceFn.apply(Kb_full, plan, comm)
-        c = _ShardedGramFn.apply(self.L_loc, Kb, comm)                            # :360-361
+        overlap = settings.overlap_root_update.on() and Kb.is_cuda
+        if overlap:
+            # c = L^T K b: the HBM-bound pass over the row slab (and, in the backward, L g_c) runs as a background launch on a
+            # side stream, under the tensor-bound Gram (backward: panel GEMM) issued next on this one; the sum over ranks
+            # stays on this stream, after the Gram's own
+            main, side = torch.cuda.current_stream(), ops.side_stream(Kb.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side), ops.background():
+                c_part = ops.gram(self.L_loc, Kb)
+        Q = _ShardedGramBlocksFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355
+        if overlap:
+            main.wait_stream(side)
+            c = _AllReduceFwdFn.apply(c_part, comm)
+        else:
+            c = _ShardedGramFn.apply(self.L_loc, Kb, comm)                        # :360-361
         Lq, _ = torch.linalg.cholesky_ex(Q, check_errors=False)      # Q >= I: no host-side info check (no sync)
         self._pieces = dict(cols=cols, KL=KL, Q=Q, Lq=Lq, Kb_full=Kb_full, Kb=Kb, c=c, b_full=b_full, noise=noise)
         return self._pieces
@@ -880,6 +935,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         if self._graph_usable(x) and self._graphs.phase == "evaluated":
             return self._update_graphed(x, y)
         self._graph_phase(None)
+        self._prestart_root_update(x)
         loss = self._hyper_step()
         with torch.no_grad():
             self.condition_on_observations(x, y[:, 0], torch.ones_like(y[:, 0]))
@@ -943,6 +999,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         G.load(x, y)
         if G.upd is None:
             def body():
+                self._prestart_root_update(G.x)
                 loss = self._hyper_step()
                 with torch.no_grad():
                     self.condition_on_observations(G.x, G.y[:, 0], torch.ones_like(G.y[:, 0]))

@@ -103,7 +103,11 @@ def install():
         out = (lowrank(P0, U, Vt0), lowrank(P1, U, Vt1))
         return out + (T,) if return_t else out
     ops.panel_lowrank_update2_ = lowrank2
-    ops.panel_lowrank_update1_ = lowrank
+    def lowrank1(P, U, Vt, return_t=False):
+        T = P @ U
+        lowrank(P, U, Vt)
+        return (P, T) if return_t else P
+    ops.panel_lowrank_update1_ = lowrank1
     ops.panel_outer_add_ = lambda P, T, W: P.add_(T @ W)
     ops.q_matvec = q_matvec
     ops.cg_solve = cg_solve
