@@ -16,8 +16,24 @@ def main():
     a = ap.parse_args()
     d, g, q, n_init, lr, desc = bench.WORKLOADS[a.workload]
     from online_gp_b200 import settings as S
-    dev = torch.device("cuda:0")
-    model, xs, ys = bench.build_model(d, g, n_init, lr, torch.float32, dev)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:           # torchrun: the row-sharded engine behind the same class (rank 0 prints its own timeline)
+        import torch.distributed as dist
+        from online_gp_b200.models import OnlineSKIRegression
+        from online_gp_b200.models.stems import Identity
+        from online_gp_b200.parallel import Comm
+        dist.init_process_group("nccl", device_id=dev)
+        x, y = bench.synth_stream(d, n_init + bench.STREAM_EXTRA)
+        with S.max_root_decomposition_size(bench.MAX_ROOT), S.max_cholesky_size(bench.MAX_CHOL):
+            model = OnlineSKIRegression(Identity(d), x[:n_init].to(dev), y[:n_init].to(dev), lr=lr, grid_size=g, grid_bound=1.0,
+                                        comm=Comm())
+        model.set_lr(lr)
+        xs, ys = x[n_init:], y[n_init:]
+    else:
+        model, xs, ys = bench.build_model(d, g, n_init, lr, torch.float32, dev)
     xd, yd = xs.to(dev), ys.to(dev)
     with S.max_root_decomposition_size(bench.MAX_ROOT), S.max_cholesky_size(bench.MAX_CHOL), S.cg_tolerance(bench.CG_TOL):
         model.enable_cuda_graphs(True, warmup_calls=1)
@@ -30,6 +46,9 @@ def main():
             for _ in range(2):
                 bench.one_step(model, xd[t * q:(t + 1) * q], yd[t * q:(t + 1) * q]); t += 1
             torch.cuda.synchronize()
+    if rank != 0:
+        torch.distributed.barrier()
+        os._exit(0)
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
     t0 = evs[0].time_range.start
@@ -45,3 +64,7 @@ def main():
 
 if __name__ == "__main__":
     main()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        sys.stdout.flush()
+        torch.distributed.barrier()
+        os._exit(0)
