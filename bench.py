@@ -266,9 +266,11 @@ def gpu_single(args, workload, K, W, device, cpu_budget, with_cg=True):
         ops.PROFILE = {"names": PROF_NAMES, "events": {}}
         phases = _PhaseTimer(model)
         torch.cuda.synchronize()
-        for _ in range(KP):
-            step_dev(t)
-            t += 1
+        # (serial schedule for this pass: a kernel timed while a background launch shares the SMs says nothing about the kernel)
+        with S.overlap_root_update(False):
+            for _ in range(KP):
+                step_dev(t)
+                t += 1
         torch.cuda.synchronize()
         phase_ms = phases.stop(KP)
         prof, ops.PROFILE = ops.PROFILE, None
@@ -324,7 +326,9 @@ def gpu_single(args, workload, K, W, device, cpu_budget, with_cg=True):
                        "kron_directional_grad": bool(S.kron_directional_grad.on()),
                        "kron_tensor_core_pairs": bool(lib.wiski_kron_tc_enable(1)) or True,
                        "cuda_graphs": bool(use_graphs),
-                       "per_op_timing": "eager pass of %d steps before the timed region (graph replays run no host code)" % KP},
+                       "per_op_timing": "eager pass of %d steps before the timed region, serial schedule (settings.overlap_root_update off: "
+                                        "single-kernel times; the timed region overlaps the background passes)" % KP,
+                       "overlap_root_update": True},
             "clocks": clk,
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": q * (d + 1) * b,
                     "d2h_bytes_per_step": 3 * b + 4},
@@ -511,9 +515,10 @@ def run_gpu_sharded(args, rank, world, device):
     KP = min(K, 5)
     ops.PROFILE = {"names": PROF_NAMES, "events": {}}
     torch.cuda.synchronize()
-    for _ in range(KP):
-        step(xd[t * q:(t + 1) * q], yd[t * q:(t + 1) * q])
-        t += 1
+    with S.overlap_root_update(False):       # serial schedule while single kernels are being timed
+        for _ in range(KP):
+            step(xd[t * q:(t + 1) * q], yd[t * q:(t + 1) * q])
+            t += 1
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     use_graphs = not args.no_graphs
@@ -581,7 +586,8 @@ def run_gpu_sharded(args, rank, world, device):
                        "cuda_graphs": bool(use_graphs), "dual_layout": not args.single_layout,
                        "kron_directional_grad": bool(S.kron_directional_grad.on()),
                        "exchange": "peer memory" if model.comm.xbuf is not None else "nccl all_to_all",
-                       "per_op_timing": "rank 0, eager pass of %d steps before the timed region" % KP},
+                       "per_op_timing": "rank 0, eager pass of %d steps before the timed region, serial schedule" % KP,
+                       "overlap_root_update": True},
             "clocks": clk,
             "e2e": {"value": K / (ms_e2e * 1e-3), "unit": "updates/s", "h2d_bytes_per_step": q * (d + 1) * b,
                     "d2h_bytes_per_step": 3 * b},
