@@ -9,7 +9,7 @@ from ..settings import skip_posterior_variances
 
 
 def sm_partial_mll(ski_gp, new_x, new_y, num_seen):
-    # M := (K_{uu}^{-1} + W'W)^{-1} = K_{uu} - K_{uu}LQ^{-1}L'K_{uu}
+    # inner covariance M = (K_uu^-1 + W^T W)^-1, applied through its Woodbury form K_uu - K_uu L Q^-1 L^T K_uu
     with skip_posterior_variances(False):
         M = ski_gp.prediction_cache["pred_cov"].detach()
     W_y = ski_gp._kernel_cache["interpolation_cache"].detach()         # [t,m,1]
@@ -39,7 +39,7 @@ def sm_partial_mll(ski_gp, new_x, new_y, num_seen):
         if ski_gp.has_learnable_noise:
             quad_term = quad_term / ski_gp._second_noise(o).detach()   # :54-55
 
-        # \log|A_t| = \log|A_{t-1}| - \log(1 + v'w)
+        # matrix determinant lemma: the log-determinant moves by -log(1 + v^T w)
         logdet_term = torch.log(sm_divisor)                            # :59
         out.append((quad_term - logdet_term) / 2)
     partial_mll = torch.stack(out)

@@ -294,7 +294,7 @@ class FixedNoiseOnlineSKIGP(GP):
             self.likelihood = likelihood
         self.has_learnable_noise = learn_additional_noise
 
-        # initialize the kernel caches immediately so we can throw away the data
+        # the training data are folded into the four caches here and not kept (``:92-95``)
         if kernel_cache is None:
             self.covar_module = self.covar_module.to(train_inputs.device)
             self.likelihood = self.likelihood.to(train_inputs.device)
@@ -333,7 +333,6 @@ class FixedNoiseOnlineSKIGP(GP):
         wtw.root_decomposition()
         return wtw._panels(wtw.root)
 
-    # TODO: make _cache_dict a cached object
     def _update_cache_dicts(self, targets, noise_diagonal, stencils, inplace=False):
         """``_update_cache_dicts`` (``:155-171``): targets [q,t], noise_diagonal [t,q]."""
         idx, val = stencils
@@ -345,7 +344,7 @@ class FixedNoiseOnlineSKIGP(GP):
             if key != "WtW":
                 updated[key] = old[key].add_(new[key]) if inplace else new[key] + old[key]
             else:
-                # we need to update "WtW" separately
+                # every cache but "WtW" is additive; the root decomposition gets the rank-q update
                 nd = noise_diagonal.expand(old["interpolation_cache"].shape[0], -1) if noise_diagonal.dim() == 2 \
                     else noise_diagonal
                 root_noise = nd.clamp_min(1e-7) ** 0.5                                       # :163
@@ -522,7 +521,7 @@ class FixedNoiseOnlineSKIGP(GP):
             K = KroneckerToeplitzLazyTensor(K.cols.to(self._dtype), K.sizes,
                                             None if K.dirs is None else K.dirs.to(self._dtype))
             if self.has_learnable_noise:
-                # append 1 / \sigma^2 into the Kuu term in the qmatrix
+                # learnable noise: K_uu / sigma^2, so that Q = I + L^T (K_uu / sigma^2) L (``:338-340``)
                 K = K / self._second_noise(o)
             out.append(K)
         return BatchLazyTensor(out)
