@@ -190,6 +190,25 @@ def _install_fused_emulation(ops, parallel, axis):
         Zo = torch.einsum("cd,oamdwk->oamcwk", Tv, zu).reshape(P.shape)
         return Zo if zout is None else zout.copy_(Zo)
 
+    # ---- the pushing kernels (results stored straight into the peers' regions): emulated by queueing the pieces per
+    # destination on the fake push buffers; `barrier()` then delivers them with one gloo all-gather per queued push
+    def split_for_push(Y, n_dst, mode):
+        if mode == 1:                                        # column block j -> rank j
+            cw = Y.shape[1] // n_dst
+            return [Y[:, j * cw:(j + 1) * cw].contiguous() for j in range(n_dst)]
+        rows = Y.shape[0] // n_dst                           # modes 2 / 3: rows of axis-0 range j -> rank j
+        return [Y[j * rows:(j + 1) * rows].contiguous() for j in range(n_dst)]
+
+    def pair_apply_push(cols, sizes, pair, X, dst, n_dst, mode):
+        dst.queue(split_for_push(pair_apply(cols, sizes, pair, X), n_dst, mode))
+
+    def pair_grad_dir_push(cols, dirs, sizes, pair, Z, P, out3, dst, n_dst):
+        dst.queue(split_for_push(pair_grad_dir(cols, dirs, sizes, pair, Z, P, out3, store=True), n_dst, 2))
+
+    def rmul_push(P, M, dst, n_dst, terms=3):
+        dst.queue(split_for_push(P @ M, n_dst, 1))
+
+    ops._fused_pair_apply_push, ops._fused_pair_grad_dir_push, ops.rmul_push = pair_apply_push, pair_grad_dir_push, rmul_push
     saved = (ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok, ops._fused_pair_grad_dir)
     ops._fused_pair_apply, ops._fused_pair_grad, ops._fused_pair_grad_dir = pair_apply, pair_grad, pair_grad_dir
     parallel._fused_ok = lambda plan, X: plan.d == 4 and all(s == axis for s in plan.sizes) and \
@@ -197,7 +216,47 @@ def _install_fused_emulation(ops, parallel, axis):
     return saved
 
 
-def _fused_worker(rank, world, port, ret, directional=True):
+class _FakePushBuffers:
+    """CPU stand-in of parallel._PushBuffers: the same four regions, `dst()` hands the emulated pushing kernels a handle
+    that queues their per-destination pieces, and `barrier()` delivers every queued push (piece j of rank p lands in part
+    p of the region on rank j) — what the NVLink stores + the symmetric-memory barrier do on the GPUs."""
+    REGIONS = ("A", "B", "C", "D")
+
+    class _Dst:
+        def __init__(self, owner, name, part):
+            self.owner, self.name, self.part = owner, name, part
+
+        def queue(self, pieces):
+            self.owner.pending.append((self.name, self.part, pieces))
+
+    def __init__(self, numel, dtype, rank, world):
+        # one tensor per region: a tensor saved for the backward (region A) must not share its version counter with the
+        # regions written later (the CUDA kernels write through raw pointers, torch ops here do not)
+        self.regions = {n: torch.zeros(numel, dtype=dtype) for n in self.REGIONS}
+        self.buf = self.regions["A"]            # (dtype probe of Comm.push_buffers)
+        self.numel, self.rank, self.world = numel, rank, world
+        self.pending, self.c_pushed, self.barriers = [], False, 0
+
+    def local(self, name, numel=None):
+        return self.regions[name][:self.numel if numel is None else numel]
+
+    def dst(self, name, part):
+        return self._Dst(self, name, part)
+
+    def barrier(self):
+        self.barriers += 1
+        for name, part, pieces in self.pending:
+            assert all(p.numel() == part for p in pieces), (name, part, [p.shape for p in pieces])
+            mine = torch.stack([p.reshape(-1) for p in pieces])                 # [W, part]: row j goes to rank j
+            allp = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(allp, mine)
+            reg = self.local(name)
+            for src in range(self.world):
+                reg[src * part:(src + 1) * part] = allp[src][self.rank]
+        self.pending = []
+
+
+def _fused_worker(rank, world, port, ret, directional=True, push=False, dual=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -214,7 +273,7 @@ def _fused_worker(rank, world, port, ret, directional=True):
     y = (torch.sin(3 * X.sum(-1)) + 0.1 * torch.randn(n0 + steps, generator=gen)).unsqueeze(-1)
     out = []
     with cpu_ops_mock.install(), S.max_cholesky_size(0), S.max_root_decomposition_size(64), S.eval_cg_tolerance(1e-13), \
-            S.kron_directional_grad(directional), S.sharded_dual_layout(False):
+            S.kron_directional_grad(directional), S.sharded_dual_layout(dual):
         saved = _install_fused_emulation(ops, parallel, g)
         try:
             if directional:
@@ -229,6 +288,9 @@ def _fused_worker(rank, world, port, ret, directional=True):
                 front = model = parallel.ShardedOnlineSKIRegression(X[:n0], y[:n0], lr=1e-2, grid_size=g, grid_bound=1.0,
                                                                     comm=parallel.Comm())
             assert parallel._fused_ok(model.plan, model.L_loc)
+            assert (model.Lc is not None) == dual
+            if push:        # what enable_push sets up on GPUs with peer memory
+                model.comm.push = _FakePushBuffers(model.L_loc.numel(), model.L_loc.dtype, rank, world)
             for t in range(steps):
                 xt, yt = X[n0 + t:n0 + t + 1], y[n0 + t:n0 + t + 1]
                 rmse, nll = front.evaluate(xt, yt)
@@ -236,6 +298,9 @@ def _fused_worker(rank, world, port, ret, directional=True):
                 assert P["KL"].shape == (world, model.plan.m_loc, model.L_loc.shape[1] // world)     # column blocks
                 _, loss = front.update(xt, yt)
                 out.append((rmse, nll, loss, float(model._noise())))
+            if push:        # pushes per step: dual layout 2 (K L, Z), single layout 4; every one followed by its barrier
+                assert model.comm.push.barriers == steps * (2 if dual else 4) and not model.comm.push.pending
+                assert model.comm.push.c_pushed is False
         finally:
             ops._fused_pair_apply, ops._fused_pair_grad, parallel._fused_ok, ops._fused_pair_grad_dir = saved
     ret[rank] = out
@@ -243,16 +308,19 @@ def _fused_worker(rank, world, port, ret, directional=True):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("directional", [True, False])
-def test_fused_sharded_orchestration_matches_unsharded_oracle(directional):
-    """The default multi-GPU path (slab-local pair, exchange, column-sharded pair, column blocks through Gram / rmul /
-    gathers, chunked operands in the backward) with the pair kernels emulated on a 4^4 grid; hyper-gradient through
-    the directional passes (default) and through the full column-gradient passes."""
+@pytest.mark.parametrize("directional,push,dual", [(True, False, False), (False, False, False), (True, True, False),
+                                                   (True, True, True)])
+def test_fused_sharded_orchestration_matches_unsharded_oracle(directional, push, dual):
+    """The multi-GPU paths on the fused pair kernels (emulated on a 4^4 grid) against the unsharded oracle:
+    pull exchange (slab-local pair, all-to-all, column-sharded pair, column blocks through Gram / rmul / gathers, chunked
+    operands in the backward) with the directional and the full column-gradient passes; and the pushing kernels — results
+    stored into the peers' regions, barrier protocol, gradient panel pushed by the Gram backward — in the single-layout
+    (4 pushes per step) and the dual-layout form (2 pushes per step: the GPU default)."""
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
-    port = 29500 + (os.getpid() % 2000) + 13 + int(directional)
-    mp.spawn(_fused_worker, args=(world, port, ret, directional), nprocs=world, join=True)
+    port = 29500 + (os.getpid() % 2000) + 13 + int(directional) + 2 * int(push) + 4 * int(dual)
+    mp.spawn(_fused_worker, args=(world, port, ret, directional, push, dual), nprocs=world, join=True)
     from oracle.gridkernel import Hypers
     from oracle.interp import create_grid
     from oracle.wiski_matfree import WiskiMatFree
