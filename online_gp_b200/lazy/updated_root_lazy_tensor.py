@@ -184,7 +184,7 @@ class UpdatedRootLazyTensor(LazyTensor):
         root panel.  Returns False (nothing started) when the update does not have the one-block row-local form."""
         self.root_decomposition()
         self.root_inv_decomposition()
-        if (getattr(self, "_pending", None) is not None or self.tensor is not None or not self.inv_root.is_cuda
+        if (getattr(self, "_pending", None) is not None or self.tensor is not None or not ops.overlap_capable(self.inv_root)
                 or settings.root_update_mode.value() != "sym" or not 1 <= idx.shape[0] <= 32):
             return False
         vval = vval.detach()
@@ -193,19 +193,16 @@ class UpdatedRootLazyTensor(LazyTensor):
         ps = [ops.left_interp(idx, vv, B).t().contiguous() for B, vv in zip(Bs, vvs)]
         facs = [_sym_factors(p) for p in ps]
         coef = [(p, (C @ p.t()).contiguous(), (Cp @ p.t()).contiguous()) for p, (C, Cp) in zip(ps, facs)]
-        main = torch.cuda.current_stream()
-        side = ops.side_stream(self.inv_root.device)
-        side.wait_stream(main)
-        with torch.cuda.stream(side), ops.background():
+        with ops.side_section(self.inv_root.device):
             for B, (p, _, CppT) in zip(Bs, coef):
                 ops.panel_lowrank_update1_(B, p, CppT)
-        self._pending = (idx, coef, side)
+        self._pending = (idx, coef)
         return True
 
     def _finish_pending(self, idx):
-        pend_idx, coef, side = self._pending
+        pend_idx, coef = self._pending
         self._pending = None
-        torch.cuda.current_stream().wait_stream(side)
+        ops.join_side(self.inv_root.device)
         if pend_idx.shape != idx.shape or pend_idx.data_ptr() != idx.data_ptr():
             raise RuntimeError("update_sparse: a pre-started update is pending for other stencils")
         for L, (p, CpT, _) in zip(self._panels(self.root), coef):

@@ -554,17 +554,15 @@ class FixedNoiseOnlineSKIGP(GP):
     @cached(name="prediction_cache")
     def prediction_cache(self):
         KLs = [kl.evaluate() for kl in self.current_inducing_compression_matrix.items]
-        if overlap_root_update.on() and KLs[0].is_cuda and max(KL.shape[-1] for KL in KLs) <= max_cholesky_size.value():
+        if overlap_root_update.on() and ops.overlap_capable(KLs[0]) and max(KL.shape[-1] for KL in KLs) <= max_cholesky_size.value():
             # c = L^T (K b) is one HBM-bound pass over L (and its backward another one): both go to a side stream, under the
             # tensor-bound Gram L^T (K L) / its backward panel GEMM on this one; joined before the solve needs c
             self.Kuu_response              # (its small Kronecker passes stay on this stream)
-            main, side = torch.cuda.current_stream(), ops.side_stream(KLs[0].device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side), ops.background():
+            with ops.side_section(KLs[0].device):
                 self.root_space_projection
             for Q in self.current_qmatrix.items:
                 Q.cholesky()
-            main.wait_stream(side)
+            ops.join_side(KLs[0].device)
         qmat_solve = self.current_qmatrix.inv_matmul(self.root_space_projection)
         prediction_cache = _PredictionCache(self.Kuu_response, KLs, qmat_solve)
         if skip_posterior_variances.off():

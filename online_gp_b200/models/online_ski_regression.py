@@ -182,7 +182,7 @@ class OnlineSKIRegression(torch.nn.Module):
         """settings.overlap_root_update: the inverse-root half of the conditioning that ends this step goes to a side
         stream now, under the hyper-parameter step — only when the features do not depend on trainable stem parameters
         (then they are the same tensor values the conditioning will see after the step)."""
-        if not (settings.overlap_root_update.on() and inputs.is_cuda):
+        if not (settings.overlap_root_update.on() and ops.overlap_capable(inputs)):
             return
         feats = self.stem(inputs)
         if feats.requires_grad:

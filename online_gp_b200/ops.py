@@ -768,6 +768,37 @@ def side_stream(device):
     return _SIDE_STREAMS[key]
 
 
+def overlap_capable(t):
+    """Side-stream overlap applies to CUDA tensors only (a hook the CPU tests replace to exercise the schedule's logic)."""
+    return bool(t.is_cuda)
+
+
+class side_section:
+    """``with side_section(device):`` — fork the side stream from the current stream and run the body on it as background
+    launches; ``join_side(device)`` makes the current stream wait for it.  Stream events only, so both are capturable."""
+
+    def __init__(self, device):
+        self.device = device
+
+    def __enter__(self):
+        side = side_stream(self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        self._stream_ctx = torch.cuda.stream(side)
+        self._stream_ctx.__enter__()
+        self._bg = background()
+        self._bg.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        self._bg.__exit__(*exc)
+        self._stream_ctx.__exit__(*exc)
+        return False
+
+
+def join_side(device):
+    torch.cuda.current_stream().wait_stream(side_stream(device))
+
+
 def panel_lowrank_update1_(P, U, Vt, return_t=False):
     """In place: P <- P + (P @ U) @ Vt through the several-rows-per-warp kernel of ``panel_lowrank_update2_`` (one panel);
     return_t: also P @ U of the rows before the update."""

@@ -762,7 +762,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         for s0 in range(0, idx_l.shape[0], 32):
             if pend is not None:
                 p, CpT = pend                      # inverse-root half already under way on the side stream (_prestart_root_update)
-                torch.cuda.current_stream().wait_stream(ops.side_stream(self.L_loc.device))
+                ops.join_side(self.L_loc.device)
             else:
                 pT = self.comm.allreduce_(ops.left_interp(idx_l[s0:s0 + 32], vval_l[s0:s0 + 32], self.B_loc))
                 p = pT.t().contiguous()
@@ -787,7 +787,8 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         """settings.overlap_root_update: projection and factors of the rank-q update that ends this step now, the in-place
         update of the inverse-root slab on a side stream (background launch) under the hyper-parameter step, which never
         reads it.  ``_root_update`` then joins and updates the root slab.  One block of q <= 32 points only."""
-        if not (settings.overlap_root_update.on() and x.is_cuda and 1 <= x.shape[0] <= 32) or self._pending_root is not None:
+        if not (settings.overlap_root_update.on() and ops.overlap_capable(x) and 1 <= x.shape[0] <= 32) \
+                or self._pending_root is not None:
             return
         with torch.no_grad():
             idx_l, val_l = self._stencils(x)                 # D = 1 in the streaming update (online_ski_regression.py:122)
@@ -795,9 +796,7 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
             p = pT.t().contiguous()
             C, Cp = _sym_factors(p)
             CpT, CppT = (C @ p.t()).contiguous(), (Cp @ p.t()).contiguous()
-            main, side = torch.cuda.current_stream(), ops.side_stream(self.B_loc.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side), ops.background():
+            with ops.side_section(self.B_loc.device):
                 ops.panel_lowrank_update1_(self.B_loc, p, CppT)
             self._pending_root = (p, CpT)
 
@@ -831,18 +830,16 @@ class ShardedOnlineSKIRegression(torch.nn.Module):
         b_full = self.b_full
         Kb_full = ops.kron_toeplitz_matmul(cols, plan.sizes, b_full)              # :366
         Kb = _ShardSliceFn.apply(Kb_full, plan, comm)
-        overlap = settings.overlap_root_update.on() and Kb.is_cuda
+        overlap = settings.overlap_root_update.on() and ops.overlap_capable(Kb)
         if overlap:
             # c = L^T K b: the HBM-bound pass over the row slab (and, in the backward, L g_c) runs as a background launch on a
             # side stream, under the tensor-bound Gram (backward: panel GEMM) issued next on this one; the sum over ranks
             # stays on this stream, after the Gram's own
-            main, side = torch.cuda.current_stream(), ops.side_stream(Kb.device)
-            side.wait_stream(main)
-            with torch.cuda.stream(side), ops.background():
+            with ops.side_section(Kb.device):
                 c_part = ops.gram(self.L_loc, Kb)
         Q = _ShardedGramBlocksFn.apply(self.L_loc, KL, comm) + torch.eye(r, dtype=self.dtype, device=KL.device)   # :352-355
         if overlap:
-            main.wait_stream(side)
+            ops.join_side(Kb.device)
             c = _AllReduceFwdFn.apply(c_part, comm)
         else:
             c = _ShardedGramFn.apply(self.L_loc, Kb, comm)                        # :360-361

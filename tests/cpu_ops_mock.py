@@ -23,7 +23,8 @@ def install():
     saved = {k: getattr(ops, k) for k in ("_require_cuda", "_interp_fwd", "_gather", "_scatter_add", "_kron_mm",
                                           "_kron_bwd_cols", "_rmul", "_gram", "panel_lowrank_update_", "panel_lowrank_update2_", "panel_lowrank_update1_", "panel_outer_add_",
                                           "q_matvec",
-                                          "cg_solve", "kron_axis_apply", "kron_axis_contract")}
+                                          "cg_solve", "kron_axis_apply", "kron_axis_contract", "overlap_capable",
+                                          "side_section", "join_side", "is_background", "background")}
     orig_init = ops.GridSpec.__init__
     orig_bwd = ops._InterpFn.backward
 
@@ -111,6 +112,23 @@ def install():
     ops.panel_outer_add_ = lambda P, T, W: P.add_(T @ W)
     ops.q_matvec = q_matvec
     ops.cg_solve = cg_solve
+
+    # settings.overlap_root_update: the side-stream schedule runs inline on the CPU (same order of operations, no streams)
+    class _Inline:
+        def __init__(self, *a, **k):
+            pass
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    ops.overlap_capable = lambda t: True
+    ops.side_section = _Inline
+    ops.background = _Inline
+    ops.join_side = lambda device: None
+    ops.is_background = lambda: False
     try:
         yield
     finally:
