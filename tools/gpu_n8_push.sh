@@ -1,3 +1,5 @@
+# As run for profiles/r02_bench_n8_push_*.json / r02_bench_n4_push_dual_layout.json (the dual layout was still opt-in then:
+# --dual-layout / --dual are no-ops today, the single layout is --single-layout / --single).
 N=8
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 200 $T --master-port 29523 bench.py --gpus $N --steps 20 --warmup 3 > gpurun_out/n8p_bench.json 2> gpurun_out/n8p_bench.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/n8p_bench.json
